@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""bench.py — DQN training steps/sec (batch 32, 84x84x4 uint8 states) on N B200s, beside the CPU
+restatement of the reference path (BASELINE.json metric).
+
+One "step" = one ReplayMemory.getMinibatch() + one DeepQNetwork.train()
+(/root/reference/src/agent.py:112-114) on synthetic frames of SURVEY §8(d):
+replay 1M x 84x84 u8 (7.06 GB ring in HBM, a 10k-frame random block tiled), batch 32 per GPU,
+A = 4, terminals ~ Bernoulli(0.005), random.seed(1), Xavier weights (RandomState(1)).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--math fp32|tcgen05]
+
+N > 1 is launched by the driver through torch.distributed.run (one rank per GPU, NCCL).  Rank 0
+prints ONE JSON line.  `value` times the fused device path with inputs resident in HBM; `e2e`
+times the public drop-in API from HOST buffers (frames appended with mem.add, RNG state uploaded,
+cost read back) — see DESIGN.md §Measurement.
+"""
+import argparse
+import json
+import os
+import random
+import subprocess
+import sys
+import threading
+import time
+import types
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "DQN training steps/sec (batch 32, 84x84x4)"
+UNIT = "steps/s"
+BLOCK = 10_000
+NUM_ACTIONS = 4
+
+# algorithmic MACs per sample of each GEMM-shaped kernel, nets = 2 for forward kernels
+MAC = {"conv1": 20 * 20 * 32 * 256, "conv2": 9 * 9 * 64 * 512, "conv3": 7 * 7 * 64 * 576, "fc1": 3136 * 512}
+N_PARAMS = 256 * 32 + 512 * 64 + 576 * 64 + 3136 * 512 + 512 * NUM_ACTIONS
+
+
+def make_args(batch):
+    return types.SimpleNamespace(screen_height=84, screen_width=84, history_length=4, batch_size=batch,
+                                 discount_rate=0.99, learning_rate=0.00025, decay_rate=0.95, clip_error=1,
+                                 min_reward=-1, max_reward=1, batch_norm=False, random_seed=1, device_id=0,
+                                 datatype="float32", stochastic_round=False, optimizer="rmsprop",
+                                 target_steps=10000, save_weights_prefix=None)
+
+
+def synthetic_meta(size):
+    g = np.random.default_rng(0)
+    base = g.integers(0, 256, (BLOCK, 84, 84), dtype=np.uint8)
+    actions = g.integers(0, NUM_ACTIONS, size, dtype=np.uint8)
+    rewards = g.integers(-1, 2, size, dtype=np.int64)
+    terminals = g.random(size) < 0.005
+    return base, actions, rewards, terminals
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d.get("bf16_tflops_sustained"),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled every 100 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.t = [], []
+        self.gpu = gpu_index
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+        except OSError:
+            return
+        th = threading.Thread(target=self._read, daemon=True)
+        th.start()
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append(line.strip().split(", "))
+            self.t.append(time.time())
+
+    def stop(self, t0, t1):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        rows = [r for r, t in zip(self.rows, self.t) if t0 - 0.05 <= t <= t1 + 0.15] or self.rows[-3:]
+        sm = [float(r[1]) for r in rows if len(r) >= 9]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.strip() == "Active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(rows[0][2]) if rows and len(rows[0]) >= 3 else None,
+                "power_w_max": max((float(r[3]) for r in rows if len(r) >= 9), default=None),
+                "samples": len(sm), "reasons": reasons}
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_arm(steps, warmup, replay, batch, max_seconds=None):
+    """The reference's hot path restated on the host cores: getMinibatch (numpy ring, CPython
+    `random`, oracle/replay_oracle.py) + train (torch-CPU fp32, oracle/dqn_torch.py)."""
+    import torch
+    from oracle import dqn_oracle as O
+    from oracle.dqn_torch import TorchDQN
+    from oracle.replay_oracle import ReplayOracle
+    base, actions, rewards, terminals = synthetic_meta(replay)
+    ring = ReplayOracle(replay, batch_size=batch)
+    for s in range(0, replay, BLOCK):
+        e = min(replay, s + BLOCK)
+        ring.screens[s:e] = base[:e - s]
+    ring.actions[:], ring.rewards[:], ring.terminals[:] = actions, rewards, terminals
+    ring.count, ring.current = replay, 123456 % replay
+    net = TorchDQN(O.xavier_init(NUM_ACTIONS, 1))
+    rnd = random.Random(1)
+    for _ in range(warmup):
+        net.train(ring.getMinibatch(rnd))
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(steps):
+        net.train(ring.getMinibatch(rnd))
+        done += 1
+        if max_seconds and time.perf_counter() - t0 > max_seconds:
+            break
+    dt = time.perf_counter() - t0
+    return dict(value=done / dt, unit=UNIT, cores=torch.get_num_threads(), kind="port",
+                sample="%d steps of (numpy-ring getMinibatch + torch-CPU fp32 train), replay %d, batch %d, "
+                       "%d torch threads of %d host cpus" % (done, replay, batch, torch.get_num_threads(),
+                                                             os.cpu_count())), dt, done
+
+
+def run_reference(a, rank, world):
+    if rank != 0:
+        return
+    cb, dt, done = cpu_arm(a.steps, a.warmup, a.replay, a.batch)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": a.gpus,
+            "steps": done, "warmup": a.warmup, "ms_per_step": 1e3 * dt / done, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(a, world),
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "Neon --backend cpu cannot run (Neon absent, no network): this is the CPU restatement "
+                    "(oracle port) of getMinibatch+train on the box's host cores"}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(a, world):
+    return {"workload": "configs[1]: synthetic 84x84 uint8 frames, replay %d, batch %d per GPU, history 4, A=%d "
+                        "(fused getMinibatch+train, no env)" % (a.replay, a.batch, NUM_ACTIONS),
+            "replay": a.replay, "batch_per_gpu": a.batch, "global_batch": a.batch * world, "num_actions": NUM_ACTIONS,
+            "math_mode": a.math, "parallelism": "dp%d replicated-replay learners, NCCL grad all-reduce" % world
+            if world > 1 else "single GPU",
+            "l2_policy": "inputs larger than L2: random 35 KB windows of a 7.06 GB ring; weights/activations are the "
+                         "step's own working set"}
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def kernel_model(label, nb, launches_per_step_part):
+    """(bound, algorithmic bytes, algorithmic flops) of one launch of kernel `label`."""
+    f = lambda macs, nets=1: 2.0 * macs * nb * nets
+    table = {
+        "conv1_fwd": ("tensor", nb * 35280 + 2 * 4 * 256 * 32, f(MAC["conv1"], 2)),
+        "conv2_fwd": ("tensor", 0, f(MAC["conv2"], 2)), "conv3_fwd": ("tensor", 0, f(MAC["conv3"], 2)),
+        "fc1_fwd": ("tensor", 0, f(MAC["fc1"], 2)), "fc1_wgrad": ("tensor", 0, f(MAC["fc1"])),
+        "fc1_dgrad": ("tensor", 0, f(MAC["fc1"])), "conv3_wgrad": ("tensor", 0, f(MAC["conv3"])),
+        "conv3_dgrad": ("tensor", 0, f(MAC["conv3"])), "conv2_wgrad": ("tensor", 0, f(MAC["conv2"])),
+        "conv2_dgrad": ("tensor", 0, f(MAC["conv2"])), "conv1_wgrad": ("tensor", nb * 35280, f(MAC["conv1"])),
+        "optimizer": ("hbm", 5 * 4 * N_PARAMS, 0.0),
+        "gather": ("hbm", nb * (35280 + 2 * 28224), 0.0),
+    }
+    return table.get(label, ("hbm", 0, 0.0))
+
+
+def run_b200(a, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from simple_dqn_b200 import DeepQNetwork, ReplayMemory, _lib as L
+
+    torch.cuda.set_device(local_rank)
+    dev = local_rank
+    if world > 1:
+        dist.init_process_group("cpu:gloo,cuda:nccl", rank=rank, world_size=world)
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    args = make_args(a.batch)
+    args.device_id = dev
+    base, actions, rewards, terminals = synthetic_meta(a.replay)
+    gbatch = a.batch * world
+
+    def new_mem(**kw):
+        margs = make_args(gbatch)
+        m = ReplayMemory(a.replay, margs, device=dev, stream=stream, **kw)
+        for s in range(0, a.replay, BLOCK):
+            e = min(a.replay, s + BLOCK)
+            m.add_batch(actions[s:e], rewards[s:e], base[:e - s], terminals[s:e])
+        m.set_cursor(a.replay, 123456 % a.replay)
+        return m
+
+    mem = new_mem(rng="device")
+    net = DeepQNetwork(NUM_ACTIONS, args, device=dev, math_mode=a.math, stream=stream)
+    net.update_target_network()
+    if world > 1:
+        uid = [DeepQNetwork.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        net.comm_init(uid[0], rank, world)
+    random.seed(1)
+    mem.seed_device_rng(random)
+
+    # ---- value: fused device path, inputs resident in HBM
+    net.train_fused(mem, a.warmup)
+    barrier()
+    sampler = ClockSampler(dev)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_wall0 = time.time()
+    ev0.record(stream)
+    net.train_fused(mem, a.steps)
+    ev1.record(stream)
+    barrier()
+    t_wall1 = time.time()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64)
+    if world > 1:
+        msd = ms.cuda()
+        dist.all_reduce(msd, op=dist.ReduceOp.MAX)
+        ms = msd.cpu()
+    ms_total = float(ms[0])
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    cost_tail = net.last_costs(min(a.steps, 8))
+    assert np.isfinite(cost_tail).all(), cost_tail
+    launches = net.launches_per_step() * a.steps
+
+    # ---- roofline: per-kernel CUDA-event durations over a slice of the same loop
+    prof_steps = min(a.steps, 200)
+    barrier()
+    L.profile_begin(dev, L.stream_ptr(stream))
+    net.train_fused(mem, prof_steps)
+    prof = L.profile_end()
+    per = {}
+    for name, t in prof:
+        per.setdefault(name, []).append(t)
+    per_kernel = {k: float(np.mean(v)) for k, v in per.items()}        # ms per launch
+    pk = peaks()
+    top = max(per_kernel, key=lambda k: per_kernel[k])
+    tot_prof = sum(per_kernel.values())
+    bound, abytes, aflops = kernel_model(top, a.batch, None)
+    if bound == "tensor":
+        ach = aflops / (per_kernel[top] * 1e-3) / 1e12
+        roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": pk["tf_sustained"] or pk["tf_burst"],
+                "unit": "TFLOP/s"}
+    else:
+        ach = abytes / (per_kernel[top] * 1e-3) / 1e9
+        roof = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s"}
+    roof["frac"] = roof["achieved"] / roof["peak"]
+    roof["traffic"] = None
+    roof["peak_source"] = pk["source"] + (", sustained figure (kernel timed inside a long step)"
+                                           if bound == "tensor" else "")
+    roof["us_per_launch"] = per_kernel[top] * 1e3
+    roof["share_of_step"] = per_kernel[top] / tot_prof
+    roof["per_kernel_us"] = {k: round(v * 1e3, 3) for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1])}
+    conv_flops = 2.0 * a.batch * (4 * (MAC["conv1"] + MAC["conv2"] + MAC["conv3"]) - MAC["conv1"])
+    conv_ms = sum(v for k, v in per_kernel.items() if k.startswith("conv"))
+    roof["conv_stack"] = {"achieved_tflops": conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms else None,
+                          "frac_of_peak": (conv_flops / (conv_ms * 1e-3) / 1e12) / (pk["tf_sustained"] or pk["tf_burst"])
+                          if conv_ms else None}
+    whole_step_flops = 2.0 * a.batch * (4 * sum(MAC.values()) - MAC["conv1"])
+    roof["whole_step"] = {"gflop": whole_step_flops / 1e9,
+                          "achieved_tflops": whole_step_flops / (ms_total / a.steps * 1e-3) / 1e12,
+                          "gather_gbs": a.batch * 35280 / (ms_total / a.steps * 1e-3) / 1e9}
+
+    # ---- e2e: the drop-in public API from HOST buffers (agent.py:100-114 without env / predict):
+    # 4 x mem.add(host frame) [train_frequency 4], getMinibatch() with the HOST random stream
+    # (MT state up + down), train(), cost read back for the stats callback.
+    del mem
+    mem2 = new_mem(rng="python", device_minibatch=True)
+    random.seed(1)
+    costs = []
+    net.callback = types.SimpleNamespace(on_train=lambda c: costs.append(c))
+    frames = [np.ascontiguousarray(base[i]) for i in range(64)]
+    e2e_steps = max(50, min(a.steps, 1000))
+
+    def e2e_loop(n):
+        for i in range(n):
+            for j in range(4):
+                mem2.add(int(actions[j]), int(rewards[j]), frames[(4 * i + j) % 64], bool(terminals[j]))
+            net.train(mem2.getMinibatch(), 0)
+
+    e2e_loop(10)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_loop(e2e_steps)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    dts = torch.tensor([dt], dtype=torch.float64)
+    if world > 1:
+        d = dts.cuda()
+        dist.all_reduce(d, op=dist.ReduceOp.MAX)
+        dts = d.cpu()
+    e2e = {"value": world * e2e_steps / float(dts[0]), "unit": UNIT,
+           "h2d_bytes_per_step": 4 * 7056 + 625 * 4, "d2h_bytes_per_step": 625 * 4 + 4 * 1024 + 4,
+           "steps": e2e_steps,
+           "what": "per step: 4x ReplayMemory.add(host frame) + getMinibatch() with the host `random` stream "
+                   "(MT19937 state up/down) + DeepQNetwork.train() + cost to the callback"}
+    assert len(costs) == e2e_steps + 10 and np.isfinite(costs).all()
+    net.callback = None
+
+    if rank != 0:
+        return
+    line = {"metric": METRIC, "value": world * a.steps / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_total / a.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if a.math == "fp32" else "f16x3-split (fp32 accumulate)", "data": "synthetic",
+            "config": workload_config(a, world), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+            "roofline": roof, "last_costs": [float(c) for c in cost_tail]}
+    if world > 1:
+        line["config"]["global_updates_per_s"] = a.steps / (ms_total * 1e-3)
+    if world == 1 and not a.no_cpu:
+        cb, _, _ = cpu_arm(10 ** 9, 3, a.replay, a.batch, max_seconds=a.cpu_seconds)
+        line["cpu_baseline"] = cb
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3000)
+    ap.add_argument("--warmup", type=int, default=100)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--math", default=os.environ.get("B200DQN_MATH", "fp32"), choices=["fp32", "tcgen05"])
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--replay", type=int, default=1_000_000)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    a = ap.parse_args()
+    assert a.warmup >= 3, "timing rules: at least 3 warm-up steps"
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.impl == "reference":
+        if a.steps > 5000:
+            a.steps = 5000
+        return run_reference(a, rank, world)
+    run_b200(a, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,107 @@
+// capi.cu — library-wide entry points: error text, version, device probe.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace b200 {
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+bool g_prof_on = false;
+namespace {
+constexpr int kProfCap = 8192;
+struct Prof {
+  cudaEvent_t ev[kProfCap + 1];
+  const char* label[kProfCap + 1];
+  int n = 0;
+  int created = 0;
+  int device = 0;
+} g_prof;
+}  // namespace
+
+void prof_mark(const char* label, cudaStream_t st) {
+  if (g_prof.n >= kProfCap) return;
+  const int i = ++g_prof.n;
+  if (i >= g_prof.created) {
+    cudaEventCreate(&g_prof.ev[i]);
+    g_prof.created = i + 1;
+  }
+  g_prof.label[i] = label;
+  cudaEventRecord(g_prof.ev[i], st);
+}
+}  // namespace b200
+
+extern "C" int b200dqn_profile_begin(int device, void* stream) {
+  using namespace b200;
+  DeviceGuard g(device);
+  if (g_prof.created == 0) {
+    B2_CHECK_CUDA(cudaEventCreate(&g_prof.ev[0]));
+    g_prof.created = 1;
+  }
+  g_prof.n = 0;
+  g_prof.device = device;
+  B2_CHECK_CUDA(cudaEventRecord(g_prof.ev[0], as_stream(stream)));
+  g_prof_on = true;
+  return B200DQN_OK;
+}
+
+extern "C" int b200dqn_profile_end(int max_entries, char* names32, float* ms, int* count) {
+  using namespace b200;
+  B2_REQUIRE(names32 && ms && count && max_entries > 0, B200DQN_EINVAL, "profile_end: bad argument");
+  g_prof_on = false;
+  DeviceGuard g(g_prof.device);
+  B2_CHECK_CUDA(cudaDeviceSynchronize());
+  const int n = g_prof.n < max_entries ? g_prof.n : max_entries;
+  for (int i = 1; i <= n; ++i) {
+    float t = 0.f;
+    B2_CHECK_CUDA(cudaEventElapsedTime(&t, g_prof.ev[i - 1], g_prof.ev[i]));
+    ms[i - 1] = t;
+    strncpy(names32 + (i - 1) * 32, g_prof.label[i], 31);
+    names32[(i - 1) * 32 + 31] = 0;
+  }
+  *count = n;
+  return B200DQN_OK;
+}
+
+extern "C" const char* b200dqn_last_error(void) { return b200::g_err; }
+extern "C" int b200dqn_version(void) { return B200DQN_VERSION; }
+
+extern "C" int b200dqn_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, size_t* free_bytes,
+                                   size_t* total_bytes) {
+  cudaDeviceProp prop;
+  B2_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (sm_count) *sm_count = prop.multiProcessorCount;
+  if (cc_major) *cc_major = prop.major;
+  if (cc_minor) *cc_minor = prop.minor;
+  b200::DeviceGuard g(device);
+  size_t f = 0, t = 0;
+  B2_CHECK_CUDA(cudaMemGetInfo(&f, &t));
+  if (free_bytes) *free_bytes = f;
+  if (total_bytes) *total_bytes = t;
+  B2_REQUIRE(prop.major == 10, B200DQN_ECUDA,
+             "device %d is sm_%d%d; libb200dqn.so is built for sm_100a (B200) only", device, prop.major, prop.minor);
+  return B200DQN_OK;
+}
+
+extern "C" int b200dqn_copy_to_host(int device, void* host_dst, const void* dev_src, size_t bytes, void* stream) {
+  B2_REQUIRE(host_dst && dev_src, B200DQN_EINVAL, "copy_to_host: null argument");
+  b200::DeviceGuard g(device);
+  cudaStream_t st = b200::as_stream(stream);
+  B2_CHECK_CUDA(cudaMemcpyAsync(host_dst, dev_src, bytes, cudaMemcpyDeviceToHost, st));
+  B2_CHECK_CUDA(cudaStreamSynchronize(st));
+  return B200DQN_OK;
+}
+
+extern "C" int b200dqn_copy_to_device(int device, void* dev_dst, const void* host_src, size_t bytes, void* stream) {
+  B2_REQUIRE(dev_dst && host_src, B200DQN_EINVAL, "copy_to_device: null argument");
+  b200::DeviceGuard g(device);
+  cudaStream_t st = b200::as_stream(stream);
+  B2_CHECK_CUDA(cudaMemcpyAsync(dev_dst, host_src, bytes, cudaMemcpyHostToDevice, st));
+  B2_CHECK_CUDA(cudaStreamSynchronize(st));
+  return B200DQN_OK;
+}

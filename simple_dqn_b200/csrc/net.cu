@@ -1,0 +1,718 @@
+// net.cu — Nature-DQN train / predict on the device behind DeepQNetwork's call surface
+// (src/deepqnetwork.py:15-192 of the reference; per-entry citations in include/b200dqn.h).
+#include <new>
+#include <vector>
+
+#include "net.cuh"
+#include "net_umma.cuh"
+
+namespace b200 {
+
+// ------------------------------------------------------------------------------------------
+// K2e: finish fc1 (sum split-K partials, Rectlin) and run fc2 (Affine nout=A, no activation).
+// grid = (rows, nets), block = 512 (one thread per hidden unit).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kHidden)
+k_fc2_fwd(const float* __restrict__ part, int splits, int rows, float* h4_online, float* h4_target,
+          const float* __restrict__ w5_online, const float* __restrict__ w5_target, float* q_online,
+          float* q_target, int A) {
+  __shared__ float red[kHidden / 32][kMaxActions];
+  const int b = blockIdx.x, z = blockIdx.y, t = threadIdx.x;
+  float h = 0.f;
+  for (int s = 0; s < splits; ++s) h += part[((z * splits + s) * rows + b) * kHidden + t];
+  h = fmaxf(h, 0.f);
+  (z ? h4_target : h4_online)[b * kHidden + t] = h;
+  const float* w5 = z ? w5_target : w5_online;
+  for (int a = 0; a < A; ++a) {
+    float v = h * w5[t * A + a];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((t & 31) == 0) red[t >> 5][a] = v;
+  }
+  __syncthreads();
+  if (t < A) {
+    float v = 0.f;
+#pragma unroll
+    for (int wI = 0; wI < kHidden / 32; ++wI) v += red[wI][t];
+    (z ? q_target : q_online)[b * A + t] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K3: TD target, delta, cost, clip — src/deepqnetwork.py:124-159.  The reference forms the target
+// on the host in Python floats (double) and stores it into a float32 array; we do the same
+// arithmetic in fp64 and round once.  cost is the batch mean of 0.5*sum_a delta^2 BEFORE the clip.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_td(const float* __restrict__ q_pre, const float* __restrict__ q_post, const uint8_t* __restrict__ actions,
+     const int64_t* __restrict__ rewards, const uint8_t* __restrict__ terminals,
+     const int32_t* __restrict__ midx, int rows, int A, double discount, int min_reward, int max_reward,
+     float clip, float* __restrict__ delta, float* __restrict__ cost_ring, uint32_t* __restrict__ step) {
+  __shared__ float s_cost[256];
+  const int b = threadIdx.x;
+  float c = 0.f;
+  for (int bb = b; bb < rows; bb += blockDim.x) {
+    const int64_t mi = midx[bb];
+    const int a = actions[mi];
+    int64_t r = rewards[mi];
+    r = r < min_reward ? min_reward : (r > max_reward ? max_reward : r);   // np.clip (:136)
+    float maxq = q_post[bb * A];
+    for (int j = 1; j < A; ++j) maxq = fmaxf(maxq, q_post[bb * A + j]);     // be.max(postq, axis=0) (:124)
+    const double y = terminals[mi] ? double(r) : double(r) + discount * double(maxq);  // :140-143
+    const float target = static_cast<float>(y);
+    const float pre = q_pre[bb * A + a];
+    float d = pre - target;                                                  // SumSquared gradient (:149)
+    c += 0.5f * d * d;                                                       // :154, before the clip
+    if (clip > 0.f) d = fminf(fmaxf(d, -clip), clip);                        // :158-159
+    for (int j = 0; j < A; ++j) delta[bb * A + j] = (j == a) ? d : 0.f;
+  }
+  s_cost[b] = c;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (b < o) s_cost[b] += s_cost[b + o];
+    __syncthreads();
+  }
+  if (b == 0) {
+    const uint32_t s = *step;
+    cost_ring[s % kCostRing] = s_cost[0] / float(rows);
+    *step = s + 1;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K4a/K5a: fc2 backward.  blocks [0,rows): dZ4[b][k] = (sum_a delta[b][a] W5[k][a]) * (H4[b][k] > 0);
+// blocks [rows, rows+A): dW5[k][a] = sum_b H4[b][k] * delta[b][a].
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kHidden)
+k_fc2_bwd(const float* __restrict__ delta, const float* __restrict__ w5, const float* __restrict__ h4, int rows,
+          int A, float* __restrict__ dz4, float* __restrict__ dw5) {
+  const int k = threadIdx.x;
+  if (blockIdx.x < rows) {
+    const int b = blockIdx.x;
+    float v = 0.f;
+    for (int a = 0; a < A; ++a) v = fmaf(delta[b * A + a], w5[k * A + a], v);
+    dz4[b * kHidden + k] = h4[b * kHidden + k] > 0.f ? v : 0.f;
+  } else {
+    const int a = blockIdx.x - rows;
+    float v = 0.f;
+    for (int b = 0; b < rows; ++b) v = fmaf(h4[b * kHidden + k], delta[b * A + a], v);
+    dw5[k * A + a] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K6: gradient reduction + Neon RMSProp (src/deepqnetwork.py:51-53,165):
+//   g = dW / bsz;  s = decay*s + g*g*(1-decay);  W = W - (g*lr) / (sqrt(s + eps) + eps)
+// The split-K partials of every layer are summed here in fixed order (deterministic), so the
+// wgrad kernels never need atomics.  mode bit0: sum partials (else read g_buf); bit1: write the
+// summed gradient to g_buf (all-reduce input / get_grads); bit2: apply the update.
+// Explicit _rn intrinsics keep the compiler from contracting into FMAs, so given identical
+// gradients the update is bit-identical to the numpy oracle.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_optimizer(const LayerTable lt, const float* __restrict__ part, float* __restrict__ g_buf, float* __restrict__ w,
+            float* __restrict__ s, int64_t n4, int mode, float inv_bsz, float lr, float decay, float one_m_decay,
+            float eps) {
+  const int64_t i4 = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (i4 >= n4) return;
+  const int64_t i = i4 * 4;
+  float4 g;
+  if (mode & 1) {
+    int l = 0;
+#pragma unroll
+    for (int j = 1; j < kLayers; ++j) l += (i >= lt.off[j]) ? 1 : 0;
+    const int64_t lsize = lt.off[l + 1] - lt.off[l];
+    const float* p = part + lt.part_off[l] + (i - lt.off[l]);
+    g = *reinterpret_cast<const float4*>(p);
+    for (int sp = 1; sp < lt.splits[l]; ++sp) {
+      const float4 v = *reinterpret_cast<const float4*>(p + sp * lsize);
+      g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w;
+    }
+  } else {
+    g = *reinterpret_cast<const float4*>(g_buf + i);
+  }
+  if (mode & 2) *reinterpret_cast<float4*>(g_buf + i) = g;
+  if (mode & 4) {
+    float4 wv = *reinterpret_cast<float4*>(w + i);
+    float4 sv = *reinterpret_cast<float4*>(s + i);
+    float* gp = reinterpret_cast<float*>(&g);
+    float* wp = reinterpret_cast<float*>(&wv);
+    float* sp = reinterpret_cast<float*>(&sv);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float gg = __fmul_rn(gp[j], inv_bsz);
+      const float ns = __fadd_rn(__fmul_rn(decay, sp[j]), __fmul_rn(__fmul_rn(gg, gg), one_m_decay));
+      const float den = __fadd_rn(__fsqrt_rn(__fadd_rn(ns, eps)), eps);
+      wp[j] = __fsub_rn(wp[j], __fdiv_rn(__fmul_rn(gg, lr), den));
+      sp[j] = ns;
+    }
+    *reinterpret_cast<float4*>(w + i) = wv;
+    *reinterpret_cast<float4*>(s + i) = sv;
+  }
+}
+
+__global__ void k_iota(int32_t* a, int32_t* b, int n, int mult) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    a[i] = i;
+    b[i] = i * mult;
+  }
+}
+
+__global__ void k_zero_rows(float* q, int from, int to, int A) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < (to - from) * A) q[from * A + i] = 0.f;
+}
+
+static inline unsigned cdiv(int64_t a, int64_t b) { return unsigned((a + b - 1) / b); }
+static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+template <class P, int BM, int BN, int BK, int TM, int TN>
+static int launch_gemm(const char* label, const P& p, int M, int N, int Z, cudaStream_t st) {
+  dim3 grid(cdiv(M, BM), cdiv(N, BN), Z);
+  k_simt_gemm<P, BM, BN, BK, TM, TN><<<grid, (BM / TM) * (BN / TN), 0, st>>>(p);
+  B2_LAUNCH_CHECK();
+  B2_PROF(label, st);
+  return B200DQN_OK;
+}
+
+// Where the first conv layer reads its frames: in place from the ring (fused) or from staged states.
+struct FrameSource {
+  const uint8_t* src[2];
+  const int32_t* idx[2];
+  int shift[2];
+};
+
+// Model.fprop for `nets` networks (z = 0 online, z = 1 target) on `rows` samples.
+static int forward(b200dqn_net* n, const FrameSource& fs, int nets, int rows, cudaStream_t st) {
+  const LayerTable& lt = n->lt;
+  const float* w[2] = {n->d_w, n->d_tw};
+  int rc;
+  if (n->cfg.math_mode == B200DQN_MATH_TCGEN05) {
+    rc = umma_forward(n, fs.src, fs.idx, fs.shift, nets, rows, st);
+    if (rc) return rc;
+  } else {
+    {
+      Conv1Fwd p;
+      for (int z = 0; z < 2; ++z) {
+        p.src[z] = fs.src[z]; p.idx[z] = fs.idx[z]; p.shift[z] = fs.shift[z];
+        p.w[z] = w[z] + lt.off[0]; p.out[z] = n->d_h1[z];
+      }
+      p.nb = rows;
+      if ((rc = launch_gemm<Conv1Fwd, 64, 32, 16, 4, 2>("conv1_fwd", p, rows * kP1 * kP1, kC1, nets, st))) return rc;
+    }
+    {
+      using P = ConvFwd<kP1, kC1, 4, 2, kC2>;
+      P p;
+      for (int z = 0; z < 2; ++z) { p.in[z] = n->d_h1[z]; p.w[z] = w[z] + lt.off[1]; p.out[z] = n->d_h2[z]; }
+      p.nb = rows;
+      if ((rc = launch_gemm<P, 32, 64, 16, 2, 4>("conv2_fwd", p, rows * kP2 * kP2, kC2, nets, st))) return rc;
+    }
+    {
+      using P = ConvFwd<kP2, kC2, 3, 1, kC3>;
+      P p;
+      for (int z = 0; z < 2; ++z) { p.in[z] = n->d_h2[z]; p.w[z] = w[z] + lt.off[2]; p.out[z] = n->d_h3[z]; }
+      p.nb = rows;
+      if ((rc = launch_gemm<P, 32, 64, 16, 2, 4>("conv3_fwd", p, rows * kP3 * kP3, kC3, nets, st))) return rc;
+    }
+    {
+      Fc1Fwd p;
+      for (int z = 0; z < 2; ++z) { p.in[z] = n->d_h3[z]; p.w[z] = w[z] + lt.off[3]; }
+      p.part = n->d_fc1part; p.nb = rows; p.splits = kFc1Splits; p.kchunk = kFc1Chunk;
+      if ((rc = launch_gemm<Fc1Fwd, 32, 64, 16, 2, 4>("fc1_fwd", p, rows, kHidden, nets * kFc1Splits, st))) return rc;
+    }
+  }
+  k_fc2_fwd<<<dim3(rows, nets), kHidden, 0, st>>>(n->d_fc1part, kFc1Splits, rows, n->d_h4[0], n->d_h4[1],
+                                                  w[0] + lt.off[4], w[1] + lt.off[4], n->d_q[0], n->d_q[1], n->A);
+  B2_LAUNCH_CHECK();
+  B2_PROF("fc2_fwd", st);
+  return B200DQN_OK;
+}
+
+static int wgrad_chunk(int kred, int base) {
+  int c = (kred + 31) / 32;
+  if (c < base) c = base;
+  return round_up(c, 16);
+}
+
+// Model.bprop + optimizer.optimize for the online network (src/deepqnetwork.py:162-165).
+static int backward_and_update(b200dqn_net* n, const FrameSource& fs, int rows, cudaStream_t st, bool update) {
+  const LayerTable& lt = n->lt;
+  const float* w = n->d_w;
+  int rc;
+  k_fc2_bwd<<<rows + n->A, kHidden, 0, st>>>(n->d_delta, w + lt.off[4], n->d_h4[0], rows, n->A, n->d_dz4,
+                                             n->d_part + lt.part_off[4]);
+  B2_LAUNCH_CHECK();
+  B2_PROF("fc2_bwd", st);
+  if (n->cfg.math_mode == B200DQN_MATH_TCGEN05 && umma_has_backward()) {
+    if ((rc = umma_backward(n, fs.src[0], fs.idx[0], fs.shift[0], rows, st))) return rc;
+  } else {
+    {
+      Fc1Wgrad p{n->d_h3[0], n->d_dz4, n->d_part + lt.part_off[3], rows};
+      if ((rc = launch_gemm<Fc1Wgrad, 64, 64, 16, 4, 4>("fc1_wgrad", p, kFlat, kHidden, 1, st))) return rc;
+    }
+    {
+      Fc1Dgrad p{n->d_dz4, w + lt.off[3], n->d_h3[0], n->d_dz3, rows};
+      if ((rc = launch_gemm<Fc1Dgrad, 32, 32, 16, 2, 2>("fc1_dgrad", p, rows, kFlat, 1, st))) return rc;
+    }
+    {
+      using P = ConvWgrad<kP2, kC2, 3, 1, kC3>;
+      const int kred = rows * kP3 * kP3;
+      P p{n->d_h2[0], n->d_dz3, n->d_part + lt.part_off[2], rows, wgrad_chunk(kred, 112)};
+      if ((rc = launch_gemm<P, 64, 64, 16, 4, 4>("conv3_wgrad", p, P::KW, kC3, lt.splits[2], st))) return rc;
+    }
+    {
+      using P = ConvDgrad<kP2, kC2, 3, 1, kC3>;
+      P p{n->d_dz3, w + lt.off[2], n->d_h2[0], n->d_dz2, rows};
+      if ((rc = launch_gemm<P, 32, 64, 16, 2, 4>("conv3_dgrad", p, rows * P::HC * P::HC, kC2, 1, st))) return rc;
+    }
+    {
+      using P = ConvWgrad<kP1, kC1, 4, 2, kC2>;
+      const int kred = rows * kP2 * kP2;
+      P p{n->d_h1[0], n->d_dz2, n->d_part + lt.part_off[1], rows, wgrad_chunk(kred, 96)};
+      if ((rc = launch_gemm<P, 64, 64, 16, 4, 4>("conv2_wgrad", p, P::KW, kC2, lt.splits[1], st))) return rc;
+    }
+    {
+      using P = ConvDgrad<kP1, kC1, 4, 2, kC2>;
+      P p{n->d_dz2, w + lt.off[1], n->d_h1[0], n->d_dz1, rows};
+      if ((rc = launch_gemm<P, 64, 32, 16, 4, 2>("conv2_dgrad", p, rows * P::HC * P::HC, kC1, 4, st))) return rc;
+    }
+    {
+      const int kred = rows * kP1 * kP1;
+      Conv1Wgrad p{fs.src[0], fs.idx[0], fs.shift[0], n->d_dz1, n->d_part + lt.part_off[0], rows,
+                   wgrad_chunk(kred, 512)};
+      if ((rc = launch_gemm<Conv1Wgrad, 64, 32, 16, 4, 2>("conv1_wgrad", p, kK1, kC1, lt.splits[0], st))) return rc;
+    }
+  }
+  if (!update) return B200DQN_OK;
+  const int64_t n4 = n->n_params / 4;
+  const float inv_bsz = 1.0f / float(rows * n->world);
+  const float lr = float(n->cfg.learning_rate), decay = float(n->cfg.decay_rate);
+  const float omd = float(1.0 - n->cfg.decay_rate), eps = 1e-6f;
+  if (n->world > 1) {
+    k_optimizer<<<cdiv(n4, 256), 256, 0, st>>>(lt, n->d_part, n->d_g, n->d_w, n->d_s, n4, 1 | 2, inv_bsz, lr, decay,
+                                               omd, eps);
+    B2_LAUNCH_CHECK();
+    B2_PROF("grad_reduce", st);
+    if ((rc = comm_allreduce_grads(n, st))) return rc;
+    B2_PROF("allreduce", st);
+    k_optimizer<<<cdiv(n4, 256), 256, 0, st>>>(lt, n->d_part, n->d_g, n->d_w, n->d_s, n4, 4, inv_bsz, lr, decay, omd,
+                                               eps);
+  } else {
+    k_optimizer<<<cdiv(n4, 256), 256, 0, st>>>(lt, n->d_part, n->d_g, n->d_w, n->d_s, n4, 1 | 4, inv_bsz, lr, decay,
+                                               omd, eps);
+  }
+  B2_LAUNCH_CHECK();
+  B2_PROF("optimizer", st);
+  return B200DQN_OK;
+}
+
+// One DeepQNetwork.train on device-resident inputs.
+static int train_step(b200dqn_net* n, const FrameSource& fs, const uint8_t* actions, const int64_t* rewards,
+                      const uint8_t* terminals, const int32_t* midx, cudaStream_t st) {
+  const int rows = n->nb;
+  int rc;
+  if ((rc = forward(n, fs, 2, rows, st))) return rc;
+  k_td<<<1, 256, 0, st>>>(n->d_q[0], n->d_q[1], actions, rewards, terminals, midx, rows, n->A,
+                          n->cfg.discount_rate, n->cfg.min_reward, n->cfg.max_reward, float(n->cfg.clip_error),
+                          n->d_delta, n->d_cost, n->d_step);
+  B2_LAUNCH_CHECK();
+  B2_PROF("td", st);
+  if ((rc = backward_and_update(n, fs, rows, st, true))) return rc;
+  n->train_iterations += 1;  // :168
+  return B200DQN_OK;
+}
+
+// ---------------------------------------------------------------- layout conversion (host)
+// Neon layout <-> internal layout index map for one layer; returns internal linear index.
+static inline int64_t neon_to_internal(int layer, int64_t i, int A) {
+  switch (layer) {
+    case 0: return i;  // (c,r,s) x K: identical
+    case 1: {          // neon rows (c,r,s), C=32,R=4 -> internal rows (r,s,c)
+      const int64_t k = i % kC2, row = i / kC2;
+      const int c = int(row / 16), r = int(row / 4) % 4, s = int(row % 4);
+      return ((int64_t(r) * 4 + s) * kC1 + c) * kC2 + k;
+    }
+    case 2: {          // C=64, R=3
+      const int64_t k = i % kC3, row = i / kC3;
+      const int c = int(row / 9), r = int(row / 3) % 3, s = int(row % 3);
+      return ((int64_t(r) * 3 + s) * kC2 + c) * kC3 + k;
+    }
+    case 3: {          // neon W[n][(c,p,q)] -> internal W[(p,q,c)][n]
+      const int64_t nn = i / kFlat, col = i % kFlat;
+      const int c = int(col / 49), p = int(col / 7) % 7, q = int(col % 7);
+      return ((int64_t(p) * 7 + q) * kC3 + c) * kHidden + nn;
+    }
+    default: {         // neon W[a][k] -> internal W[k][a]
+      const int64_t a = i / kHidden, k = i % kHidden;
+      return k * A + a;
+    }
+  }
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+// ============================================================================ C ABI: network
+extern "C" int b200dqn_net_config_default(b200dqn_net_config* cfg, int num_actions) {
+  B2_REQUIRE(cfg, B200DQN_EINVAL, "null cfg");
+  memset(cfg, 0, sizeof(*cfg));
+  cfg->num_actions = num_actions;
+  cfg->batch_size = 32;          // main.py:39
+  cfg->history_length = 4;       // main.py:34
+  cfg->screen_h = cfg->screen_w = 84;  // main.py:27-28
+  cfg->discount_rate = 0.99;     // main.py:38
+  cfg->learning_rate = 0.00025;  // main.py:37
+  cfg->decay_rate = 0.95;        // main.py:41
+  cfg->clip_error = 1.0;         // main.py:42
+  cfg->min_reward = -1;          // main.py:43
+  cfg->max_reward = 1;           // main.py:44
+  cfg->target_steps = 10000;     // main.py:63
+  cfg->math_mode = B200DQN_MATH_FP32_SIMT;
+  return B200DQN_OK;
+}
+
+extern "C" int b200dqn_net_create(int device, const b200dqn_net_config* cfg, b200dqn_net** out) {
+  B2_REQUIRE(cfg && out, B200DQN_EINVAL, "net_create: null argument");
+  B2_REQUIRE(cfg->num_actions >= 1 && cfg->num_actions <= kMaxActions, B200DQN_EINVAL,
+             "net_create: num_actions %d not in [1,%d]", cfg->num_actions, kMaxActions);
+  B2_REQUIRE(cfg->batch_size >= 1 && cfg->batch_size <= 4096, B200DQN_EINVAL, "net_create: batch_size");
+  B2_REQUIRE(cfg->screen_h == kFrameH && cfg->screen_w == kFrameW && cfg->history_length == kHist,
+             B200DQN_ENOTIMPL,
+             "net_create: only the reference's 84x84x4 Nature-DQN geometry is implemented (got %dx%dx%d)",
+             cfg->screen_h, cfg->screen_w, cfg->history_length);
+  B2_REQUIRE(cfg->math_mode == B200DQN_MATH_FP32_SIMT || cfg->math_mode == B200DQN_MATH_TCGEN05, B200DQN_EINVAL,
+             "net_create: unknown math_mode %d", cfg->math_mode);
+  DeviceGuard g(device);
+  auto* n = new (std::nothrow) b200dqn_net();
+  B2_REQUIRE(n, B200DQN_EINVAL, "out of host memory");
+  n->device = device;
+  n->cfg = *cfg;
+  n->nb = cfg->batch_size;
+  n->A = cfg->num_actions;
+  const int nb = n->nb, A = n->A;
+  LayerTable& lt = n->lt;
+  const int rows_[kLayers] = {kK1, kK2, kK3, kFlat, kHidden};
+  const int cols_[kLayers] = {kC1, kC2, kC3, kHidden, A};
+  lt.off[0] = 0;
+  for (int l = 0; l < kLayers; ++l) {
+    lt.rows[l] = rows_[l];
+    lt.cols[l] = cols_[l];
+    lt.off[l + 1] = lt.off[l] + int64_t(rows_[l]) * cols_[l];
+  }
+  n->n_params = lt.off[kLayers];
+  B2_REQUIRE(n->n_params % 4 == 0, B200DQN_EINVAL, "parameter count must be a multiple of 4");
+  const int kred[3] = {nb * kP1 * kP1, nb * kP2 * kP2, nb * kP3 * kP3};
+  const int base[3] = {512, 96, 112};
+  int64_t po = 0;
+  for (int l = 0; l < kLayers; ++l) {
+    lt.splits[l] = l < 3 ? int(cdiv(kred[l], wgrad_chunk(kred[l], base[l]))) : 1;
+    lt.part_off[l] = po;
+    po += int64_t(lt.splits[l]) * (lt.off[l + 1] - lt.off[l]);
+  }
+  n->part_elems = po;
+
+  auto fmalloc = [&](float** p, size_t elems) -> cudaError_t {
+    cudaError_t e = cudaMalloc(p, elems * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemset(*p, 0, elems * sizeof(float));
+    return e;
+  };
+  B2_CHECK_CUDA(fmalloc(&n->d_w, n->n_params));
+  B2_CHECK_CUDA(fmalloc(&n->d_s, n->n_params));
+  if (cfg->target_steps) {
+    B2_CHECK_CUDA(fmalloc(&n->d_tw, n->n_params));
+    B2_CHECK_CUDA(fmalloc(&n->d_ts, n->n_params));
+  } else {
+    n->d_tw = n->d_w;  // deepqnetwork.py:72-73: the target model IS the online model
+    n->d_ts = n->d_s;
+  }
+  B2_CHECK_CUDA(fmalloc(&n->d_g, n->n_params));
+  B2_CHECK_CUDA(fmalloc(&n->d_part, n->part_elems));
+  for (int z = 0; z < 2; ++z) {
+    B2_CHECK_CUDA(fmalloc(&n->d_h1[z], size_t(nb) * kP1 * kP1 * kC1));
+    B2_CHECK_CUDA(fmalloc(&n->d_h2[z], size_t(nb) * kP2 * kP2 * kC2));
+    B2_CHECK_CUDA(fmalloc(&n->d_h3[z], size_t(nb) * kFlat));
+    B2_CHECK_CUDA(fmalloc(&n->d_h4[z], size_t(nb) * kHidden));
+    B2_CHECK_CUDA(fmalloc(&n->d_q[z], size_t(nb) * A));
+  }
+  B2_CHECK_CUDA(fmalloc(&n->d_fc1part, size_t(2) * kFc1Splits * nb * kHidden));
+  B2_CHECK_CUDA(fmalloc(&n->d_delta, size_t(nb) * A));
+  B2_CHECK_CUDA(fmalloc(&n->d_dz4, size_t(nb) * kHidden));
+  B2_CHECK_CUDA(fmalloc(&n->d_dz3, size_t(nb) * kFlat));
+  B2_CHECK_CUDA(fmalloc(&n->d_dz2, size_t(nb) * kP2 * kP2 * kC2));
+  B2_CHECK_CUDA(fmalloc(&n->d_dz1, size_t(nb) * kP1 * kP1 * kC1));
+  B2_CHECK_CUDA(fmalloc(&n->d_cost, kCostRing));
+  B2_CHECK_CUDA(cudaMalloc(&n->d_step, sizeof(uint32_t)));
+  B2_CHECK_CUDA(cudaMemset(n->d_step, 0, sizeof(uint32_t)));
+  const size_t state_bytes = size_t(nb) * kHist * kFrameBytes;
+  B2_CHECK_CUDA(cudaMalloc(&n->d_pre, state_bytes + 256));
+  B2_CHECK_CUDA(cudaMalloc(&n->d_post, state_bytes + 256));
+  B2_CHECK_CUDA(cudaMalloc(&n->d_act, nb));
+  B2_CHECK_CUDA(cudaMalloc(&n->d_term, nb));
+  B2_CHECK_CUDA(cudaMalloc(&n->d_rew, nb * sizeof(int64_t)));
+  B2_CHECK_CUDA(cudaMalloc(&n->d_iota1, nb * sizeof(int32_t)));
+  B2_CHECK_CUDA(cudaMalloc(&n->d_iota4, nb * sizeof(int32_t)));
+  k_iota<<<cdiv(nb, 128), 128>>>(n->d_iota1, n->d_iota4, nb, kHist);
+  B2_LAUNCH_CHECK();
+  n->pin_bytes = 2 * state_bytes + size_t(nb) * 16 + size_t(nb) * A * sizeof(float) + 256;
+  B2_CHECK_CUDA(cudaMallocHost(&n->h_pin, n->pin_bytes));
+  int rc = umma_net_init(n);
+  if (rc) return rc;
+  B2_CHECK_CUDA(cudaDeviceSynchronize());
+  *out = n;
+  return B200DQN_OK;
+}
+
+extern "C" int b200dqn_net_destroy(b200dqn_net* n) {
+  if (!n) return B200DQN_OK;
+  DeviceGuard g(n->device);
+  cudaDeviceSynchronize();
+  comm_destroy(n);
+  umma_net_destroy(n);
+  if (n->d_tw != n->d_w) { cudaFree(n->d_tw); cudaFree(n->d_ts); }
+  cudaFree(n->d_w); cudaFree(n->d_s); cudaFree(n->d_g); cudaFree(n->d_part);
+  for (int z = 0; z < 2; ++z) {
+    cudaFree(n->d_h1[z]); cudaFree(n->d_h2[z]); cudaFree(n->d_h3[z]); cudaFree(n->d_h4[z]); cudaFree(n->d_q[z]);
+  }
+  cudaFree(n->d_fc1part); cudaFree(n->d_delta); cudaFree(n->d_dz4); cudaFree(n->d_dz3); cudaFree(n->d_dz2);
+  cudaFree(n->d_dz1); cudaFree(n->d_cost); cudaFree(n->d_step); cudaFree(n->d_pre); cudaFree(n->d_post);
+  cudaFree(n->d_act); cudaFree(n->d_term); cudaFree(n->d_rew); cudaFree(n->d_iota1); cudaFree(n->d_iota4);
+  cudaFreeHost(n->h_pin);
+  delete n;
+  return B200DQN_OK;
+}
+
+extern "C" int b200dqn_net_layer_shape(const b200dqn_net* n, int layer, int* rows, int* cols) {
+  B2_REQUIRE(n && layer >= 0 && layer < kLayers, B200DQN_EINVAL, "net_layer_shape: bad layer");
+  // NEON shapes: conv (C*R*S, K); linear (nout, nin)
+  const int r[kLayers] = {kK1, kK2, kK3, kHidden, n->A};
+  const int c[kLayers] = {kC1, kC2, kC3, kFlat, kHidden};
+  if (rows) *rows = r[layer];
+  if (cols) *cols = c[layer];
+  return B200DQN_OK;
+}
+
+static int xfer_params(b200dqn_net* n, float* dev_base, int layer, float* host, bool to_device, cudaStream_t st) {
+  const int64_t off = n->lt.off[layer], cnt = n->lt.off[layer + 1] - off;
+  std::vector<float> tmp(cnt);
+  if (to_device) {
+    for (int64_t i = 0; i < cnt; ++i) tmp[neon_to_internal(layer, i, n->A)] = host[i];
+    B2_CHECK_CUDA(cudaMemcpyAsync(dev_base + off, tmp.data(), cnt * sizeof(float), cudaMemcpyHostToDevice, st));
+    B2_CHECK_CUDA(cudaStreamSynchronize(st));
+  } else {
+    B2_CHECK_CUDA(cudaMemcpyAsync(tmp.data(), dev_base + off, cnt * sizeof(float), cudaMemcpyDeviceToHost, st));
+    B2_CHECK_CUDA(cudaStreamSynchronize(st));
+    for (int64_t i = 0; i < cnt; ++i) host[i] = tmp[neon_to_internal(layer, i, n->A)];
+  }
+  return B200DQN_OK;
+}
+
+extern "C" int b200dqn_net_set_weights(b200dqn_net* n, int which, int layer, const float* host_W,
+                                       const float* host_S, void* stream) {
+  B2_REQUIRE(n && host_W && layer >= 0 && layer < kLayers && (which == 0 || which == 1), B200DQN_EINVAL,
+             "net_set_weights: bad argument");
+  DeviceGuard g(n->device);
+  cudaStream_t st = as_stream(stream);
+  int rc = xfer_params(n, which ? n->d_tw : n->d_w, layer, const_cast<float*>(host_W), true, st);
+  if (rc) return rc;
+  if (host_S && (rc = xfer_params(n, which ? n->d_ts : n->d_s, layer, const_cast<float*>(host_S), true, st))) return rc;
+  return umma_weights_changed(n, st);
+}
+
+extern "C" int b200dqn_net_get_weights(b200dqn_net* n, int which, int layer, float* host_W, float* host_S,
+                                       void* stream) {
+  B2_REQUIRE(n && layer >= 0 && layer < kLayers && (which == 0 || which == 1), B200DQN_EINVAL,
+             "net_get_weights: bad argument");
+  DeviceGuard g(n->device);
+  cudaStream_t st = as_stream(stream);
+  int rc;
+  if (host_W && (rc = xfer_params(n, which ? n->d_tw : n->d_w, layer, host_W, false, st))) return rc;
+  if (host_S && (rc = xfer_params(n, which ? n->d_ts : n->d_s, layer, host_S, false, st))) return rc;
+  return B200DQN_OK;
+}
+
+extern "C" int b200dqn_net_sync_target(b200dqn_net* n, void* stream) {
+  B2_REQUIRE(n, B200DQN_EINVAL, "null net");
+  if (n->d_tw == n->d_w) return B200DQN_OK;  // target_steps == 0: alias
+  DeviceGuard g(n->device);
+  cudaStream_t st = as_stream(stream);
+  B2_CHECK_CUDA(cudaMemcpyAsync(n->d_tw, n->d_w, n->n_params * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  B2_CHECK_CUDA(cudaMemcpyAsync(n->d_ts, n->d_s, n->n_params * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return umma_target_synced(n, st);
+}
+
+extern "C" int b200dqn_net_predict_device(b200dqn_net* n, const uint8_t* dev_states, int live_rows, float* dev_q,
+                                          void* stream) {
+  B2_REQUIRE(n && dev_states && dev_q && live_rows >= 1 && live_rows <= n->nb, B200DQN_EINVAL,
+             "net_predict_device: bad argument");
+  DeviceGuard g(n->device);
+  cudaStream_t st = as_stream(stream);
+  FrameSource fs{{dev_states, dev_states}, {n->d_iota4, n->d_iota4}, {0, 0}};
+  int rc = forward(n, fs, 1, live_rows, st);
+  if (rc) return rc;
+  if (dev_q != n->d_q[0])
+    B2_CHECK_CUDA(cudaMemcpyAsync(dev_q, n->d_q[0], size_t(live_rows) * n->A * sizeof(float),
+                                  cudaMemcpyDeviceToDevice, st));
+  if (live_rows < n->nb) {
+    k_zero_rows<<<cdiv((n->nb - live_rows) * n->A, 128), 128, 0, st>>>(dev_q, live_rows, n->nb, n->A);
+    B2_LAUNCH_CHECK();
+  }
+  return B200DQN_OK;
+}
+
+extern "C" int b200dqn_net_predict(b200dqn_net* n, const uint8_t* host_states, float* host_q, void* stream) {
+  B2_REQUIRE(n && host_states && host_q, B200DQN_EINVAL, "net_predict: null argument");
+  DeviceGuard g(n->device);
+  cudaStream_t st = as_stream(stream);
+  const size_t state_bytes = size_t(n->nb) * kHist * kFrameBytes;
+  memcpy(n->h_pin, host_states, state_bytes);
+  B2_CHECK_CUDA(cudaMemcpyAsync(n->d_pre, n->h_pin, state_bytes, cudaMemcpyHostToDevice, st));
+  int rc = b200dqn_net_predict_device(n, n->d_pre, n->nb, n->d_q[0], stream);
+  if (rc) return rc;
+  float* hq = reinterpret_cast<float*>(n->h_pin + 2 * state_bytes + size_t(n->nb) * 16);
+  B2_CHECK_CUDA(cudaMemcpyAsync(hq, n->d_q[0], size_t(n->nb) * n->A * sizeof(float), cudaMemcpyDeviceToHost, st));
+  B2_CHECK_CUDA(cudaStreamSynchronize(st));
+  memcpy(host_q, hq, size_t(n->nb) * n->A * sizeof(float));
+  return B200DQN_OK;
+}
+
+extern "C" int b200dqn_net_train_device(b200dqn_net* n, const uint8_t* dev_pre, const uint8_t* dev_actions,
+                                        const int64_t* dev_rewards, const uint8_t* dev_post,
+                                        const uint8_t* dev_terminals, void* stream) {
+  B2_REQUIRE(n && dev_pre && dev_actions && dev_rewards && dev_post && dev_terminals, B200DQN_EINVAL,
+             "net_train_device: null argument");
+  DeviceGuard g(n->device);
+  FrameSource fs{{dev_pre, dev_post}, {n->d_iota4, n->d_iota4}, {0, 0}};
+  return train_step(n, fs, dev_actions, dev_rewards, dev_terminals, n->d_iota1, as_stream(stream));
+}
+
+extern "C" int b200dqn_net_train(b200dqn_net* n, const uint8_t* host_pre, const uint8_t* host_actions,
+                                 const int64_t* host_rewards, const uint8_t* host_post, const uint8_t* host_terminals,
+                                 float* host_cost, void* stream) {
+  B2_REQUIRE(n && host_pre && host_actions && host_rewards && host_post && host_terminals, B200DQN_EINVAL,
+             "net_train: null argument");
+  for (int i = 0; i < n->nb; ++i)
+    B2_REQUIRE(host_actions[i] < n->A, B200DQN_EINVAL, "net_train: action %d >= num_actions %d", host_actions[i], n->A);
+  DeviceGuard g(n->device);
+  cudaStream_t st = as_stream(stream);
+  const size_t sb = size_t(n->nb) * kHist * kFrameBytes;
+  uint8_t* p = n->h_pin;
+  memcpy(p, host_pre, sb);
+  memcpy(p + sb, host_post, sb);
+  uint8_t* meta = p + 2 * sb;
+  memcpy(meta, host_rewards, n->nb * 8);
+  memcpy(meta + n->nb * 8, host_actions, n->nb);
+  memcpy(meta + n->nb * 9, host_terminals, n->nb);
+  B2_CHECK_CUDA(cudaMemcpyAsync(n->d_pre, p, sb, cudaMemcpyHostToDevice, st));
+  B2_CHECK_CUDA(cudaMemcpyAsync(n->d_post, p + sb, sb, cudaMemcpyHostToDevice, st));
+  B2_CHECK_CUDA(cudaMemcpyAsync(n->d_rew, meta, n->nb * 8, cudaMemcpyHostToDevice, st));
+  B2_CHECK_CUDA(cudaMemcpyAsync(n->d_act, meta + n->nb * 8, n->nb, cudaMemcpyHostToDevice, st));
+  B2_CHECK_CUDA(cudaMemcpyAsync(n->d_term, meta + n->nb * 9, n->nb, cudaMemcpyHostToDevice, st));
+  int rc = b200dqn_net_train_device(n, n->d_pre, n->d_act, n->d_rew, n->d_post, n->d_term, stream);
+  if (rc) return rc;
+  if (host_cost) return b200dqn_net_read_costs(n, 1, host_cost, stream);
+  B2_CHECK_CUDA(cudaStreamSynchronize(st));
+  return B200DQN_OK;
+}
+
+static int check_fusable(b200dqn_net* n, b200dqn_replay* r) {
+  B2_REQUIRE(r->device == n->device, B200DQN_EINVAL, "train_fused: replay and net live on different devices");
+  B2_REQUIRE(r->h == kFrameH && r->w == kFrameW && r->hist == kHist, B200DQN_EINVAL,
+             "train_fused: replay geometry differs from the network's");
+  B2_REQUIRE(r->batch == n->nb * n->world, B200DQN_EINVAL,
+             "train_fused: replay batch (%d) must equal the global minibatch %d x %d", r->batch, n->nb, n->world);
+  return B200DQN_OK;
+}
+
+static int train_on_ring(b200dqn_net* n, b200dqn_replay* r, cudaStream_t st) {
+  const int32_t* my_idx = r->d_idx + n->rank * n->nb;  // this rank's slice of the global minibatch
+  // prestates = frames index-4 .. index-1, poststates = index-3 .. index (src/replay_memory.py:71-72)
+  FrameSource fs{{r->d_screens, r->d_screens}, {my_idx, my_idx}, {-kHist, -kHist + 1}};
+  return train_step(n, fs, r->d_actions, r->d_rewards, r->d_terminals, my_idx, st);
+}
+
+extern "C" int b200dqn_net_train_sampled(b200dqn_net* n, b200dqn_replay* r, void* stream) {
+  B2_REQUIRE(n && r, B200DQN_EINVAL, "net_train_sampled: null argument");
+  int rc = check_fusable(n, r);
+  if (rc) return rc;
+  DeviceGuard g(n->device);
+  return train_on_ring(n, r, as_stream(stream));
+}
+
+extern "C" int b200dqn_net_train_fused(b200dqn_net* n, b200dqn_replay* r, int nsteps, void* stream) {
+  B2_REQUIRE(n && r && nsteps >= 1, B200DQN_EINVAL, "net_train_fused: bad argument");
+  int rc = check_fusable(n, r);
+  if (rc) return rc;
+  B2_REQUIRE(r->count > r->hist, B200DQN_ESTATE, "getMinibatch: count must exceed history_length");
+  B2_REQUIRE(r->rng_set, B200DQN_ESTATE, "net_train_fused: call b200dqn_replay_set_rng first");
+  DeviceGuard g(n->device);
+  cudaStream_t st = as_stream(stream);
+  for (int i = 0; i < nsteps; ++i) {
+    if ((rc = launch_sample(r, st))) return rc;
+    if ((rc = train_on_ring(n, r, st))) return rc;
+  }
+  return B200DQN_OK;
+}
+
+extern "C" int b200dqn_net_read_costs(b200dqn_net* n, int count, float* host_costs, void* stream) {
+  B2_REQUIRE(n && host_costs && count >= 1 && count <= kCostRing, B200DQN_EINVAL, "net_read_costs: bad argument");
+  DeviceGuard g(n->device);
+  cudaStream_t st = as_stream(stream);
+  float* ring = reinterpret_cast<float*>(n->h_pin);
+  uint32_t step = 0;
+  // the pinned block is reused: wait for anything in flight first
+  B2_CHECK_CUDA(cudaStreamSynchronize(st));
+  B2_CHECK_CUDA(cudaMemcpyAsync(ring, n->d_cost, kCostRing * sizeof(float), cudaMemcpyDeviceToHost, st));
+  B2_CHECK_CUDA(cudaMemcpyAsync(&step, n->d_step, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  B2_CHECK_CUDA(cudaStreamSynchronize(st));
+  B2_REQUIRE(uint32_t(count) <= step, B200DQN_ESTATE, "net_read_costs: only %u steps have run", step);
+  for (int i = 0; i < count; ++i) host_costs[i] = ring[(step - count + i) % kCostRing];
+  return B200DQN_OK;
+}
+
+extern "C" int b200dqn_net_train_iterations(const b200dqn_net* n, int64_t* iters) {
+  B2_REQUIRE(n && iters, B200DQN_EINVAL, "null argument");
+  *iters = n->train_iterations;
+  return B200DQN_OK;
+}
+
+extern "C" int b200dqn_net_device_ptr(b200dqn_net* n, int which, void** dev_ptr, size_t* bytes) {
+  B2_REQUIRE(n && dev_ptr, B200DQN_EINVAL, "net_device_ptr: null argument");
+  void* p = nullptr;
+  size_t b = 0;
+  switch (which) {
+    case B200DQN_NET_PTR_Q_ONLINE: p = n->d_q[0]; b = size_t(n->nb) * n->A * 4; break;
+    case B200DQN_NET_PTR_Q_TARGET: p = n->d_q[1]; b = size_t(n->nb) * n->A * 4; break;
+    case B200DQN_NET_PTR_DELTAS: p = n->d_delta; b = size_t(n->nb) * n->A * 4; break;
+    case B200DQN_NET_PTR_GRADS: p = n->d_g; b = n->n_params * 4; break;
+    case B200DQN_NET_PTR_WEIGHTS: p = n->d_w; b = n->n_params * 4; break;
+    case B200DQN_NET_PTR_COST: p = n->d_cost; b = kCostRing * 4; break;
+    default: B2_REQUIRE(false, B200DQN_EINVAL, "net_device_ptr: unknown selector %d", which);
+  }
+  *dev_ptr = p;
+  if (bytes) *bytes = b;
+  return B200DQN_OK;
+}
+
+extern "C" int b200dqn_net_get_grads(b200dqn_net* n, int layer, float* host_dW, void* stream) {
+  B2_REQUIRE(n && host_dW && layer >= 0 && layer < kLayers, B200DQN_EINVAL, "net_get_grads: bad argument");
+  DeviceGuard g(n->device);
+  cudaStream_t st = as_stream(stream);
+  const int64_t n4 = n->n_params / 4;
+  if (n->world == 1) {  // partials of the last step are still in scratch; sum them into d_g
+    k_optimizer<<<cdiv(n4, 256), 256, 0, st>>>(n->lt, n->d_part, n->d_g, n->d_w, n->d_s, n4, 1 | 2, 0.f, 0.f, 0.f, 0.f,
+                                               0.f);
+    B2_LAUNCH_CHECK();
+  }
+  return xfer_params(n, n->d_g, layer, host_dW, false, st);
+}
+
+extern "C" int b200dqn_net_launches_per_step(const b200dqn_net* n, int* launches) {
+  B2_REQUIRE(n && launches, B200DQN_EINVAL, "null argument");
+  // sample + forward (4 GEMM-shaped + fc2) + td + fc2_bwd + 7 backward GEMMs + optimizer (+2 in a communicator)
+  int fwd = (n->cfg.math_mode == B200DQN_MATH_TCGEN05) ? umma_forward_launches() : 4;
+  int bwd = (n->cfg.math_mode == B200DQN_MATH_TCGEN05 && umma_has_backward()) ? umma_backward_launches() : 7;
+  *launches = 1 + fwd + 1 + 1 + 1 + bwd + (n->world > 1 ? 2 : 1);
+  return B200DQN_OK;
+}

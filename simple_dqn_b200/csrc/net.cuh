@@ -1,0 +1,64 @@
+// net.cuh — the Q-network object: fp32 master weights (online + target), RMSProp state,
+// activations, gradient partials, all resident in HBM.
+#pragma once
+#include "common.cuh"
+#include "net_simt.cuh"
+#include "replay.cuh"
+
+namespace b200 {
+
+constexpr int kLayers = 5;
+constexpr int kMaxActions = 32;
+constexpr int kCostRing = 1024;
+constexpr int kFc1Splits = 14;            // 3136 / 14 = 224 = 14 * 16
+constexpr int kFc1Chunk = kFlat / kFc1Splits;
+
+struct LayerTable {
+  int64_t off[kLayers + 1];   // element offsets into the all-layer parameter vector
+  int rows[kLayers], cols[kLayers];  // internal [K][N] shape
+  int64_t part_off[kLayers];  // element offsets into the split-K partial scratch
+  int splits[kLayers];
+};
+
+}  // namespace b200
+
+struct b200dqn_net {
+  int device = 0;
+  b200dqn_net_config cfg{};
+  int nb = 0;  // per-rank minibatch
+  int A = 0;
+  b200::LayerTable lt{};
+  int64_t n_params = 0;
+
+  // parameters (internal layout, all layers contiguous)
+  float* d_w = nullptr;   // online weights
+  float* d_s = nullptr;   // online RMSProp state
+  float* d_tw = nullptr;  // target weights (== d_w when target_steps == 0)
+  float* d_ts = nullptr;  // target optimizer state (copied for fidelity with :102-105)
+  float* d_g = nullptr;   // summed gradients (all-reduce buffer / get_grads)
+  float* d_part = nullptr;  // split-K partials
+  int64_t part_elems = 0;
+
+  // activations: [0] online, [1] target
+  float* d_h1[2] = {}, *d_h2[2] = {}, *d_h3[2] = {}, *d_h4[2] = {};
+  float* d_fc1part = nullptr;  // [2*splits][nb][512]
+  float* d_q[2] = {};          // [nb][A]
+  float* d_delta = nullptr;    // [nb][A] clipped
+  float* d_dz4 = nullptr, *d_dz3 = nullptr, *d_dz2 = nullptr, *d_dz1 = nullptr;
+  float* d_cost = nullptr;     // cost ring [kCostRing]
+  uint32_t* d_step = nullptr;  // device step counter (cost ring cursor)
+
+  // unfused-mode staging (host minibatch -> device)
+  uint8_t* d_pre = nullptr, *d_post = nullptr, *d_act = nullptr, *d_term = nullptr;
+  int64_t* d_rew = nullptr;
+  int32_t* d_iota1 = nullptr;  // b
+  int32_t* d_iota4 = nullptr;  // hist * b
+  uint8_t* h_pin = nullptr;    // pinned staging for predict/train host entry points
+  size_t pin_bytes = 0;
+
+  int64_t train_iterations = 0;
+
+  // multi-GPU
+  void* nccl_comm = nullptr;
+  int rank = 0, world = 1;
+};

@@ -1,0 +1,26 @@
+// net_umma.cuh — entry points of the tcgen05 (math_mode TCGEN05) engine and of the NCCL glue,
+// called from net.cu.
+#pragma once
+#include "common.cuh"
+
+struct b200dqn_net;
+
+namespace b200 {
+
+// tcgen05 engine (net_umma.cu)
+int umma_net_init(b200dqn_net* n);                      // allocate operand images etc. (no-op in SIMT mode)
+void umma_net_destroy(b200dqn_net* n);
+int umma_weights_changed(b200dqn_net* n, cudaStream_t st);  // fp32 master weights were overwritten by the host
+int umma_target_synced(b200dqn_net* n, cudaStream_t st);    // target <- online
+int umma_forward(b200dqn_net* n, const uint8_t* const src[2], const int32_t* const idx[2], const int shift[2],
+                 int nets, int rows, cudaStream_t st);
+bool umma_has_backward();
+int umma_backward(b200dqn_net* n, const uint8_t* src, const int32_t* idx, int shift, int rows, cudaStream_t st);
+int umma_forward_launches();
+int umma_backward_launches();
+
+// NCCL glue (comm.cu)
+int comm_allreduce_grads(b200dqn_net* n, cudaStream_t st);
+void comm_destroy(b200dqn_net* n);
+
+}  // namespace b200

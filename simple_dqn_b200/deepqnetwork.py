@@ -1,0 +1,237 @@
+"""DeepQNetwork with the reference's call surface (/root/reference/src/deepqnetwork.py:15-192):
+the Neon model/train/predict replaced by hand-written sm_100a kernels (csrc/net*.cu)."""
+import ctypes as C
+import logging
+import pickle
+
+import numpy as np
+
+from . import _lib as L
+from .replay_memory import DeviceMinibatch
+from .state_buffer import DeviceStates
+
+logger = logging.getLogger(__name__)
+
+# (R, S, K, stride) of deepqnetwork.py:83-87
+_CONV = [(8, 8, 32, 4), (4, 4, 64, 2), (3, 3, 64, 1)]
+
+
+def _arg(args, name, default):
+    return getattr(args, name, default)
+
+
+class DeepQNetwork:
+    def __init__(self, num_actions, args, device=None, math_mode=None, stream=None):
+        # remember parameters (:17-26)
+        self.num_actions = num_actions
+        self.batch_size = args.batch_size
+        self.discount_rate = args.discount_rate
+        self.history_length = args.history_length
+        self.screen_dim = (args.screen_height, args.screen_width)
+        self.clip_error = args.clip_error
+        self.min_reward = args.min_reward
+        self.max_reward = args.max_reward
+        self.batch_norm = _arg(args, "batch_norm", False)
+        # flags of the reference this build accepts but does not implement (SURVEY §8 a17 note)
+        if self.batch_norm:
+            raise NotImplementedError("--batch_norm is not implemented on the B200 path")
+        if _arg(args, "optimizer", "rmsprop") != "rmsprop":
+            raise NotImplementedError("only --optimizer rmsprop is implemented on the B200 path")
+        if np.dtype(_arg(args, "datatype", "float32")) != np.float32:
+            raise NotImplementedError("only --datatype float32 is implemented on the B200 path")
+        if _arg(args, "stochastic_round", False):
+            raise NotImplementedError("--stochastic_round is not implemented on the B200 path")
+        self.device = _arg(args, "device_id", 0) if device is None else device
+        self._stream = L.stream_ptr(stream)
+
+        cfg = L.NetConfig()
+        L.call("b200dqn_net_config_default", C.byref(cfg), num_actions)
+        cfg.batch_size = args.batch_size
+        cfg.history_length = args.history_length
+        cfg.screen_h, cfg.screen_w = self.screen_dim
+        cfg.discount_rate = args.discount_rate
+        cfg.learning_rate = args.learning_rate
+        cfg.decay_rate = args.decay_rate
+        cfg.clip_error = float(args.clip_error or 0)
+        cfg.min_reward = int(args.min_reward)
+        cfg.max_reward = int(args.max_reward)
+        cfg.target_steps = int(args.target_steps or 0)
+        if math_mode is None:
+            math_mode = _arg(args, "math_mode", "fp32")
+        cfg.math_mode = {"fp32": L.MATH_FP32_SIMT, "tcgen05": L.MATH_TCGEN05}[math_mode]
+        self.math_mode = math_mode
+        h = C.c_void_p()
+        L.call("b200dqn_net_create", self.device, C.byref(cfg), C.byref(h))
+        self._h = h
+
+        # model.initialize (:49, :70): Xavier draws from one numpy RandomState(random_seed) —
+        # online layers first, then the separately-initialised target model.
+        rng = np.random.RandomState(_arg(args, "random_seed", None))
+        for which in ((0, 1) if cfg.target_steps else (0,)):
+            for layer, shp in enumerate(self.layer_shapes()):
+                fan_in = shp[0] if layer < 3 else shp[1]               # Xavier(local=True / False) (:79-80)
+                scale = np.sqrt(3.0 / fan_in)
+                w = rng.uniform(-scale, scale, shp).astype(np.float32)
+                self._set_layer(which, layer, w, np.zeros_like(w))
+        self.train_iterations = 0
+        self.save_weights_prefix = _arg(args, "save_weights_prefix", None)
+        self.callback = None
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                L.load().b200dqn_net_destroy(h)
+            except Exception:
+                pass
+
+    # ---- weights in Neon layout
+    def layer_shapes(self):
+        out = []
+        for layer in range(5):
+            r, c = C.c_int(), C.c_int()
+            L.call("b200dqn_net_layer_shape", self._h, layer, C.byref(r), C.byref(c))
+            out.append((r.value, c.value))
+        return out
+
+    def _set_layer(self, which, layer, w, s=None):
+        w = np.ascontiguousarray(w, dtype=np.float32)
+        s = None if s is None else np.ascontiguousarray(s, dtype=np.float32)
+        assert w.shape == self.layer_shapes()[layer], (w.shape, self.layer_shapes()[layer])
+        L.call("b200dqn_net_set_weights", self._h, which, layer, L.np_ptr(w), L.np_ptr(s), self._stream)
+
+    def set_weights(self, weights, states=None, which=0):
+        for layer, w in enumerate(weights):
+            self._set_layer(which, layer, w, None if states is None else states[layer])
+
+    def get_weights(self, which=0, with_states=True):
+        ws, ss = [], []
+        for layer, shp in enumerate(self.layer_shapes()):
+            w = np.empty(shp, dtype=np.float32)
+            s = np.empty(shp, dtype=np.float32) if with_states else None
+            L.call("b200dqn_net_get_weights", self._h, which, layer, L.np_ptr(w), L.np_ptr(s), self._stream)
+            ws.append(w)
+            ss.append(s)
+        return (ws, ss) if with_states else ws
+
+    def get_grads(self):
+        out = []
+        for layer, shp in enumerate(self.layer_shapes()):
+            g = np.empty(shp, dtype=np.float32)
+            L.call("b200dqn_net_get_grads", self._h, layer, L.np_ptr(g), self._stream)
+            out.append(g)
+        return out
+
+    def device_view(self, which, shape):
+        p, b = C.c_void_p(), C.c_size_t()
+        L.call("b200dqn_net_device_ptr", self._h, which, C.byref(p), C.byref(b))
+        return L.DeviceArray(p.value, shape, "<f4", owner=self)
+
+    def _read_f32(self, which, shape):
+        return L.download(self.device, self.device_view(which, shape).ptr, shape, np.float32, self._stream)
+
+    def last_q(self):
+        """(preq, postq) of the last train() as (batch, A) arrays (deepqnetwork.py:120,129)."""
+        shp = (self.batch_size, self.num_actions)
+        return self._read_f32(L.NET_PTR_Q_ONLINE, shp), self._read_f32(L.NET_PTR_Q_TARGET, shp)
+
+    def last_deltas(self):
+        return self._read_f32(L.NET_PTR_DELTAS, (self.batch_size, self.num_actions))
+
+    # ---- reference methods
+    def update_target_network(self):
+        L.call("b200dqn_net_sync_target", self._h, self._stream)        # :102-105
+
+    def train(self, minibatch, epoch=0):
+        """deepqnetwork.py:107-172.  A pristine DeviceMinibatch is trained in place from the ring."""
+        if isinstance(minibatch, DeviceMinibatch) and not minibatch.materialised:
+            L.call("b200dqn_net_train_sampled", self._h, minibatch._mem._h, self._stream)
+            self.train_iterations += 1
+            if self.callback:
+                self.callback.on_train(self.last_costs(1)[0])
+            return
+        prestates, actions, rewards, poststates, terminals = minibatch
+        assert len(prestates.shape) == 4                                # :110-116
+        assert len(poststates.shape) == 4
+        assert len(actions.shape) == 1
+        assert len(rewards.shape) == 1
+        assert len(terminals.shape) == 1
+        assert prestates.shape == poststates.shape
+        assert prestates.shape[0] == actions.shape[0] == rewards.shape[0] == poststates.shape[0] == terminals.shape[0]
+        assert prestates.shape == (self.batch_size, self.history_length) + self.screen_dim
+        pre = np.ascontiguousarray(prestates, dtype=np.uint8)
+        post = np.ascontiguousarray(poststates, dtype=np.uint8)
+        act = np.ascontiguousarray(actions, dtype=np.uint8)
+        rew = np.ascontiguousarray(rewards, dtype=np.int64)
+        term = np.ascontiguousarray(terminals, dtype=np.uint8)
+        cost = C.c_float()
+        L.call("b200dqn_net_train", self._h, L.np_ptr(pre), L.np_ptr(act), L.np_ptr(rew), L.np_ptr(post),
+               L.np_ptr(term), C.byref(cost), self._stream)
+        self.train_iterations += 1                                      # :168
+        if self.callback:
+            self.callback.on_train(cost.value)                          # :171-172
+
+    def train_fused(self, mem, nsteps=1):
+        """`nsteps` x (mem.getMinibatch(); self.train(...)) of agent.py:112-114 with no host round trip
+        (device-resident MT19937 stream).  Costs stay on the device — see :meth:`last_costs`."""
+        if not mem._rng_on_device:
+            mem.seed_device_rng()
+        L.call("b200dqn_net_train_fused", self._h, mem._h, int(nsteps), self._stream)
+        self.train_iterations += nsteps
+        mem._sample_ticket += nsteps
+
+    def last_costs(self, count=1):
+        out = np.empty(count, dtype=np.float32)
+        L.call("b200dqn_net_read_costs", self._h, int(count), L.np_ptr(out), self._stream)
+        return out
+
+    def predict(self, states):
+        # :176 — the minibatch is full size
+        assert tuple(states.shape) == ((self.batch_size, self.history_length,) + self.screen_dim)
+        q = np.empty((self.batch_size, self.num_actions), dtype=np.float32)
+        if isinstance(states, DeviceStates):
+            p, b = C.c_void_p(), C.c_size_t()
+            L.call("b200dqn_net_device_ptr", self._h, L.NET_PTR_Q_ONLINE, C.byref(p), C.byref(b))
+            L.call("b200dqn_net_predict_device", self._h, C.c_void_p(states.device_ptr()), states.live_rows, p,
+                   self._stream)
+            return self._read_f32(L.NET_PTR_Q_ONLINE, q.shape)
+        st = np.ascontiguousarray(states, dtype=np.uint8)
+        L.call("b200dqn_net_predict", self._h, L.np_ptr(st), L.np_ptr(q), self._stream)
+        return q                                                        # (batch, A) == qvalues.T (:186)
+
+    def load_weights(self, load_path):
+        """Model.load_params (:188-189): both pickle layouts found in the reference's snapshots/."""
+        with open(load_path, "rb") as f:
+            d = pickle.load(f, encoding="latin1")
+        if "layer_params_states" in d:                                  # pre-1.0 layout (convert_weights.py:10-12)
+            ls = d["layer_params_states"]
+        else:                                                           # neon 1.3.0 layout
+            ls = [l for l in d["model"]["config"]["layers"] if "params" in l]
+        ws = [np.asarray(l["params"]["W"], dtype=np.float32) for l in ls]
+        ss = [np.asarray(l["states"][0], dtype=np.float32) if l.get("states") else np.zeros_like(w)
+              for l, w in zip(ls, ws)]
+        self.set_weights(ws, ss)
+
+    def save_weights(self, save_path):
+        """Model.save_params (:191-192), written in the pre-1.0 layout the loader above reads."""
+        ws, ss = self.get_weights()
+        d = {"epoch_index": 0,
+             "layer_params_states": [{"params": {"W": w}, "states": [s]} for w, s in zip(ws, ss)]}
+        with open(save_path, "wb") as f:
+            pickle.dump(d, f, protocol=2)
+
+    # ---- multi-GPU (new capability)
+    def comm_init(self, unique_id, rank, world_size):
+        buf = (C.c_char * 128).from_buffer_copy(bytes(unique_id))
+        L.call("b200dqn_net_comm_init", self._h, buf, rank, world_size)
+
+    @staticmethod
+    def comm_unique_id():
+        buf = (C.c_char * 128)()
+        L.call("b200dqn_comm_unique_id", buf)
+        return bytes(buf)
+
+    def launches_per_step(self):
+        n = C.c_int()
+        L.call("b200dqn_net_launches_per_step", self._h, C.byref(n))
+        return n.value
