@@ -214,7 +214,11 @@ enum {
   B200DQN_NET_PTR_DELTAS,       /* clipped deltas (batch,A) f32 — :159                                 */
   B200DQN_NET_PTR_GRADS,        /* summed dW, internal layout, all layers contiguous                   */
   B200DQN_NET_PTR_WEIGHTS,      /* online fp32 master weights, internal layout                         */
-  B200DQN_NET_PTR_COST          /* device cost ring                                                    */
+  B200DQN_NET_PTR_COST,         /* device cost ring                                                    */
+  B200DQN_NET_PTR_H1,           /* online activations of the last forward, NHWC fp32: (batch,20,20,32) */
+  B200DQN_NET_PTR_H2,           /* (batch,9,9,64)                                                      */
+  B200DQN_NET_PTR_H3,           /* (batch,7,7,64)                                                      */
+  B200DQN_NET_PTR_H4            /* (batch,512)                                                         */
 };
 int b200dqn_net_device_ptr(b200dqn_net* n, int which, void** dev_ptr, size_t* bytes);
 /* Last summed gradient of `layer` converted to NEON layout (tests).  Synchronises. */

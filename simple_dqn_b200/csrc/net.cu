@@ -222,7 +222,8 @@ static int forward(b200dqn_net* n, const FrameSource& fs, int nets, int rows, cu
       if ((rc = launch_gemm<Fc1Fwd, 32, 64, 16, 2, 4>("fc1_fwd", p, rows, kHidden, nets * kFc1Splits, st))) return rc;
     }
   }
-  k_fc2_fwd<<<dim3(rows, nets), kHidden, 0, st>>>(n->d_fc1part, kFc1Splits, rows, n->d_h4[0], n->d_h4[1],
+  const int fc1_splits = n->cfg.math_mode == B200DQN_MATH_TCGEN05 ? umma_fc1_splits() : kFc1Splits;
+  k_fc2_fwd<<<dim3(rows, nets), kHidden, 0, st>>>(n->d_fc1part, fc1_splits, rows, n->d_h4[0], n->d_h4[1],
                                                   w[0] + lt.off[4], w[1] + lt.off[4], n->d_q[0], n->d_q[1], n->A);
   B2_LAUNCH_CHECK();
   B2_PROF("fc2_fwd", st);
@@ -688,6 +689,10 @@ extern "C" int b200dqn_net_device_ptr(b200dqn_net* n, int which, void** dev_ptr,
     case B200DQN_NET_PTR_GRADS: p = n->d_g; b = n->n_params * 4; break;
     case B200DQN_NET_PTR_WEIGHTS: p = n->d_w; b = n->n_params * 4; break;
     case B200DQN_NET_PTR_COST: p = n->d_cost; b = kCostRing * 4; break;
+    case B200DQN_NET_PTR_H1: p = n->d_h1[0]; b = size_t(n->nb) * kP1 * kP1 * kC1 * 4; break;
+    case B200DQN_NET_PTR_H2: p = n->d_h2[0]; b = size_t(n->nb) * kP2 * kP2 * kC2 * 4; break;
+    case B200DQN_NET_PTR_H3: p = n->d_h3[0]; b = size_t(n->nb) * kFlat * 4; break;
+    case B200DQN_NET_PTR_H4: p = n->d_h4[0]; b = size_t(n->nb) * kHidden * 4; break;
     default: B2_REQUIRE(false, B200DQN_EINVAL, "net_device_ptr: unknown selector %d", which);
   }
   *dev_ptr = p;

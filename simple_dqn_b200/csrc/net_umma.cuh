@@ -14,6 +14,7 @@ int umma_weights_changed(b200dqn_net* n, cudaStream_t st);  // fp32 master weigh
 int umma_target_synced(b200dqn_net* n, cudaStream_t st);    // target <- online
 int umma_forward(b200dqn_net* n, const uint8_t* const src[2], const int32_t* const idx[2], const int shift[2],
                  int nets, int rows, cudaStream_t st);
+int umma_fc1_splits();
 bool umma_has_backward();
 int umma_backward(b200dqn_net* n, const uint8_t* src, const int32_t* idx, int shift, int rows, cudaStream_t st);
 int umma_forward_launches();

@@ -135,6 +135,15 @@ class DeepQNetwork:
         shp = (self.batch_size, self.num_actions)
         return self._read_f32(L.NET_PTR_Q_ONLINE, shp), self._read_f32(L.NET_PTR_Q_TARGET, shp)
 
+    def last_activations(self):
+        """Online-network activations of the last forward as NCHW arrays like the oracle's."""
+        b = self.batch_size
+        h1 = self._read_f32(L.NET_PTR_H1, (b, 20, 20, 32)).transpose(0, 3, 1, 2)
+        h2 = self._read_f32(L.NET_PTR_H2, (b, 9, 9, 64)).transpose(0, 3, 1, 2)
+        h3 = self._read_f32(L.NET_PTR_H3, (b, 7, 7, 64)).transpose(0, 3, 1, 2)
+        h4 = self._read_f32(L.NET_PTR_H4, (b, 512))
+        return h1, h2, h3, h4
+
     def last_deltas(self):
         return self._read_f32(L.NET_PTR_DELTAS, (self.batch_size, self.num_actions))
 

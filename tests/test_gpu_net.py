@@ -72,6 +72,18 @@ def test_predict_parity(mode, num_actions):
 
 
 @pytest.mark.parametrize("mode", MODES)
+def test_forward_activations_layer_by_layer(mode):
+    net, orc = _paired(4, mode)
+    states = random_minibatch(32, 4, 8)[0]
+    net.predict(states)
+    _, acts = O.forward(orc.weights, states, keep=True)
+    for name, dev in zip(("h1", "h2", "h3", "h4"), net.last_activations()):
+        ref = acts[name]
+        err = np.abs(dev - ref).max() / np.abs(ref).max()
+        assert err <= 1e-4, (name, err)
+
+
+@pytest.mark.parametrize("mode", MODES)
 def test_train_step_parity(mode):
     net, orc = _paired(4, mode)
     costs = []
