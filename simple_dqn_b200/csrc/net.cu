@@ -408,7 +408,10 @@ extern "C" int b200dqn_net_create(int device, const b200dqn_net_config* cfg, b20
   const int base[3] = {512, 96, 112};
   int64_t po = 0;
   for (int l = 0; l < kLayers; ++l) {
-    lt.splits[l] = l < 3 ? int(cdiv(kred[l], wgrad_chunk(kred[l], base[l]))) : 1;
+    if (cfg->math_mode == B200DQN_MATH_TCGEN05)
+      lt.splits[l] = l < 3 ? umma_wgrad_splits(l, nb) : 1;
+    else
+      lt.splits[l] = l < 3 ? int(cdiv(kred[l], wgrad_chunk(kred[l], base[l]))) : 1;
     lt.part_off[l] = po;
     po += int64_t(lt.splits[l]) * (lt.off[l + 1] - lt.off[l]);
   }

@@ -15,6 +15,7 @@ int umma_target_synced(b200dqn_net* n, cudaStream_t st);    // target <- online
 int umma_forward(b200dqn_net* n, const uint8_t* const src[2], const int32_t* const idx[2], const int shift[2],
                  int nets, int rows, cudaStream_t st);
 int umma_fc1_splits();
+int umma_wgrad_splits(int layer, int rows);   // split-K factor of the conv wgrad of `layer` (0..2)
 bool umma_has_backward();
 int umma_backward(b200dqn_net* n, const uint8_t* src, const int32_t* idx, int shift, int rows, cudaStream_t st);
 int umma_forward_launches();
