@@ -205,7 +205,8 @@ def run_b200(a, rank, world, local_rank):
     dev = local_rank
     if world > 1:
         dist.init_process_group("cpu:gloo,cuda:nccl", rank=rank, world_size=world)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()          # non-default: enables CUDA-graph replay + side-stream branches
+    torch.cuda.set_stream(stream)
 
     def barrier():
         if world > 1:

@@ -59,6 +59,13 @@ int b200dqn_device_info(int device, int* sm_count, int* cc_major, int* cc_minor,
 int b200dqn_copy_to_host(int device, void* host_dst, const void* dev_src, size_t bytes, void* stream);
 int b200dqn_copy_to_device(int device, void* dev_dst, const void* host_src, size_t bytes, void* stream);
 
+/* A non-default (non-blocking) CUDA stream owned by the library, for callers that do not bring their
+ * own (torch.cuda.Stream().cuda_stream works too).  The fused train path only uses CUDA-graph
+ * replay and side-stream branches when it is given a non-default stream. */
+int b200dqn_stream_create(int device, void** out_stream);
+int b200dqn_stream_destroy(int device, void* stream);
+int b200dqn_stream_synchronize(int device, void* stream);
+
 /* Per-launch timing with CUDA events (bench.py's roofline leg): between begin and end every kernel
  * the library launches is followed by an event on its stream.  end synchronises the device and
  * returns, in launch order, a 32-byte label and the elapsed ms since the previous event. */

@@ -6,5 +6,6 @@ fallback (``_lib.load`` raises if ``libb200dqn.so`` has not been built)."""
 from .replay_memory import ReplayMemory, DeviceMinibatch      # noqa: F401
 from .state_buffer import StateBuffer, DeviceStates           # noqa: F401
 from .deepqnetwork import DeepQNetwork                        # noqa: F401
+from ._lib import Stream                                      # noqa: F401
 
-__all__ = ["ReplayMemory", "DeviceMinibatch", "StateBuffer", "DeviceStates", "DeepQNetwork"]
+__all__ = ["ReplayMemory", "DeviceMinibatch", "StateBuffer", "DeviceStates", "DeepQNetwork", "Stream"]

@@ -42,6 +42,9 @@ SIGNATURES = {
                             C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)],
     "b200dqn_copy_to_host": [C.c_int, _P, _P, C.c_size_t, _P],
     "b200dqn_copy_to_device": [C.c_int, _P, _P, C.c_size_t, _P],
+    "b200dqn_stream_create": [C.c_int, C.POINTER(_P)],
+    "b200dqn_stream_destroy": [C.c_int, _P],
+    "b200dqn_stream_synchronize": [C.c_int, _P],
     "b200dqn_profile_begin": [C.c_int, _P],
     "b200dqn_profile_end": [C.c_int, _P, _P, C.POINTER(C.c_int)],
     "b200dqn_replay_create": [C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_P)],
@@ -178,3 +181,24 @@ def profile_end(max_entries=8192):
     call("b200dqn_profile_end", max_entries, names, np_ptr(ms), C.byref(n))
     raw = names.raw
     return [(raw[i * 32:(i + 1) * 32].split(b"\0")[0].decode(), float(ms[i])) for i in range(n.value)]
+
+
+class Stream:
+    """A library-owned non-blocking CUDA stream (``.cuda_stream`` like torch.cuda.Stream)."""
+
+    def __init__(self, device=0):
+        h = C.c_void_p()
+        call("b200dqn_stream_create", device, C.byref(h))
+        self.device = device
+        self.cuda_stream = h.value
+
+    def synchronize(self):
+        call("b200dqn_stream_synchronize", self.device, C.c_void_p(self.cuda_stream))
+
+    def __del__(self):
+        h, self.cuda_stream = getattr(self, "cuda_stream", None), None
+        if h:
+            try:
+                load().b200dqn_stream_destroy(self.device, C.c_void_p(h))
+            except Exception:
+                pass

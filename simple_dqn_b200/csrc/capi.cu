@@ -105,3 +105,24 @@ extern "C" int b200dqn_copy_to_device(int device, void* dev_dst, const void* hos
   B2_CHECK_CUDA(cudaStreamSynchronize(st));
   return B200DQN_OK;
 }
+
+extern "C" int b200dqn_stream_create(int device, void** out_stream) {
+  B2_REQUIRE(out_stream, B200DQN_EINVAL, "stream_create: null argument");
+  b200::DeviceGuard g(device);
+  cudaStream_t st;
+  B2_CHECK_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  *out_stream = st;
+  return B200DQN_OK;
+}
+
+extern "C" int b200dqn_stream_destroy(int device, void* stream) {
+  b200::DeviceGuard g(device);
+  if (stream) B2_CHECK_CUDA(cudaStreamDestroy(b200::as_stream(stream)));
+  return B200DQN_OK;
+}
+
+extern "C" int b200dqn_stream_synchronize(int device, void* stream) {
+  b200::DeviceGuard g(device);
+  B2_CHECK_CUDA(cudaStreamSynchronize(b200::as_stream(stream)));
+  return B200DQN_OK;
+}

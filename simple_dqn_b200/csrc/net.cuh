@@ -58,6 +58,16 @@ struct b200dqn_net {
 
   int64_t train_iterations = 0;
 
+  // step scheduling: side streams / events for the independent wgrad + optimizer branches, and the
+  // captured CUDA graph of one fused step
+  cudaStream_t side[3] = {};
+  cudaEvent_t ev[7] = {};
+  bool use_graph = true, use_branches = true;
+  cudaGraphExec_t graph_exec = nullptr;
+  b200dqn_replay* graph_replay = nullptr;
+  cudaStream_t graph_stream = nullptr;
+  int graph_world = 0;
+
   // multi-GPU
   void* nccl_comm = nullptr;
   int rank = 0, world = 1;

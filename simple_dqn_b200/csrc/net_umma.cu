@@ -361,43 +361,44 @@ int umma_forward(b200dqn_net* n, const uint8_t* const src[2], const int32_t* con
   return B200DQN_OK;
 }
 
-int umma_backward(b200dqn_net* n, const uint8_t* src, const int32_t* idx, int shift, int rows, cudaStream_t st) {
+int umma_backward_op(b200dqn_net* n, int op, const uint8_t* src, const int32_t* idx, int shift, int rows,
+                     cudaStream_t st) {
   const LayerTable& lt = n->lt;
   const float* w = n->d_w;
-  int rc;
-  {
-    UFc1Wgrad p{n->d_h3[0], n->d_dz4, n->d_part + lt.part_off[3], rows};
-    if ((rc = umma::launch_umma("fc1_wgrad", p, kFlat, kHidden, 1, st))) return rc;
+  switch (op) {
+    case 0: {
+      UFc1Wgrad p{n->d_h3[0], n->d_dz4, n->d_part + lt.part_off[3], rows};
+      return umma::launch_umma("fc1_wgrad", p, kFlat, kHidden, 1, st);
+    }
+    case 1: {
+      UFc1Dgrad p{w + lt.off[3], n->d_dz4, n->d_h3[0], n->d_dz3, rows};
+      return umma::launch_umma("fc1_dgrad", p, kFlat, rows, 1, st);
+    }
+    case 2: {
+      using P = UConvWgrad<kP2, kC2, 3, 1, kC3>;
+      P p{n->d_h2[0], n->d_dz3, n->d_part + lt.part_off[2], rows, kUWgradKb};
+      return umma::launch_umma("conv3_wgrad", p, P::KW, kC3, lt.splits[2], st);
+    }
+    case 3: {
+      using P = UConvDgrad<kP2, kC2, 3, 1, kC3>;
+      P p{n->d_dz3, w + lt.off[2], n->d_h2[0], n->d_dz2, rows};
+      return umma::launch_umma("conv3_dgrad", p, rows * P::HC * P::HC, kC2, 1, st);
+    }
+    case 4: {
+      using P = UConvWgrad<kP1, kC1, 4, 2, kC2>;
+      P p{n->d_h1[0], n->d_dz2, n->d_part + lt.part_off[1], rows, kUWgradKb};
+      return umma::launch_umma("conv2_wgrad", p, P::KW, kC2, lt.splits[1], st);
+    }
+    case 5: {
+      using P = UConvDgrad<kP1, kC1, 4, 2, kC2>;
+      P p{n->d_dz2, w + lt.off[1], n->d_h1[0], n->d_dz1, rows};
+      return umma::launch_umma("conv2_dgrad", p, rows * P::HC * P::HC, kC1, 4, st);
+    }
+    default: {
+      UConv1Wgrad p{src, idx, shift, n->d_dz1, n->d_part + lt.part_off[0], rows, kUWgradKb};
+      return umma::launch_umma("conv1_wgrad", p, kK1, kC1, lt.splits[0], st);
+    }
   }
-  {
-    UFc1Dgrad p{w + lt.off[3], n->d_dz4, n->d_h3[0], n->d_dz3, rows};
-    if ((rc = umma::launch_umma("fc1_dgrad", p, kFlat, rows, 1, st))) return rc;
-  }
-  {
-    using P = UConvWgrad<kP2, kC2, 3, 1, kC3>;
-    P p{n->d_h2[0], n->d_dz3, n->d_part + lt.part_off[2], rows, kUWgradKb};
-    if ((rc = umma::launch_umma("conv3_wgrad", p, P::KW, kC3, lt.splits[2], st))) return rc;
-  }
-  {
-    using P = UConvDgrad<kP2, kC2, 3, 1, kC3>;
-    P p{n->d_dz3, w + lt.off[2], n->d_h2[0], n->d_dz2, rows};
-    if ((rc = umma::launch_umma("conv3_dgrad", p, rows * P::HC * P::HC, kC2, 1, st))) return rc;
-  }
-  {
-    using P = UConvWgrad<kP1, kC1, 4, 2, kC2>;
-    P p{n->d_h1[0], n->d_dz2, n->d_part + lt.part_off[1], rows, kUWgradKb};
-    if ((rc = umma::launch_umma("conv2_wgrad", p, P::KW, kC2, lt.splits[1], st))) return rc;
-  }
-  {
-    using P = UConvDgrad<kP1, kC1, 4, 2, kC2>;
-    P p{n->d_dz2, w + lt.off[1], n->d_h1[0], n->d_dz1, rows};
-    if ((rc = umma::launch_umma("conv2_dgrad", p, rows * P::HC * P::HC, kC1, 4, st))) return rc;
-  }
-  {
-    UConv1Wgrad p{src, idx, shift, n->d_dz1, n->d_part + lt.part_off[0], rows, kUWgradKb};
-    if ((rc = umma::launch_umma("conv1_wgrad", p, kK1, kC1, lt.splits[0], st))) return rc;
-  }
-  return B200DQN_OK;
 }
 
 int umma_fc1_splits() { return kUFc1Splits; }

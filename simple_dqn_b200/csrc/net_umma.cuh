@@ -17,7 +17,9 @@ int umma_forward(b200dqn_net* n, const uint8_t* const src[2], const int32_t* con
 int umma_fc1_splits();
 int umma_wgrad_splits(int layer, int rows);   // split-K factor of the conv wgrad of `layer` (0..2)
 bool umma_has_backward();
-int umma_backward(b200dqn_net* n, const uint8_t* src, const int32_t* idx, int shift, int rows, cudaStream_t st);
+// op: 0 fc1_wgrad, 1 fc1_dgrad, 2 conv3_wgrad, 3 conv3_dgrad, 4 conv2_wgrad, 5 conv2_dgrad, 6 conv1_wgrad
+int umma_backward_op(b200dqn_net* n, int op, const uint8_t* src, const int32_t* idx, int shift, int rows,
+                     cudaStream_t st);
 int umma_forward_launches();
 int umma_backward_launches();
 

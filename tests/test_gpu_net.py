@@ -25,17 +25,17 @@ pytestmark = pytest.mark.gpu
 MODES = ["fp32", "tcgen05"]
 
 
-def _net(num_actions, mode, **kw):
+def _net(num_actions, mode, stream=None, **kw):
     from simple_dqn_b200 import DeepQNetwork
     try:
-        return DeepQNetwork(num_actions, make_args(**kw), math_mode=mode)
+        return DeepQNetwork(num_actions, make_args(**kw), math_mode=mode, stream=stream)
     except NotImplementedError as e:
         pytest.skip(str(e))
 
 
-def _paired(num_actions, mode, seed=3, batch=32):
+def _paired(num_actions, mode, seed=3, batch=32, stream=None):
     """A device net and an oracle net holding identical fp32 weights (trained-looking scale)."""
-    net = _net(num_actions, mode, batch_size=batch, random_seed=seed)
+    net = _net(num_actions, mode, stream=stream, batch_size=batch, random_seed=seed)
     ws, ss = net.get_weights()
     # Xavier weights give Q ~ 1e-2; scale the last layers so Q ~ O(1) like a trained net
     ws[3] = ws[3] * np.float32(3.0)
@@ -167,20 +167,24 @@ def test_trajectory_20_steps_with_target_sync(mode):
 def test_fused_ring_training_equals_host_minibatch_training(mode):
     """agent.py:112-114 fused (sample -> frames read in place from the ring -> train) must do
     exactly what getMinibatch() + train(minibatch) does: same indexes, same weights."""
-    from simple_dqn_b200 import ReplayMemory
+    from simple_dqn_b200 import ReplayMemory, Stream
     size, batch = 4000, 32
     orc_ring = ReplayOracle(size, batch_size=batch)
     synthetic_ring(orc_ring, seed=4, block=200, terminal_p=0.02)
     nets = []
     for fused in (True, False):
-        mem = ReplayMemory(size, make_args(), rng="device")
+        # fused: non-default stream => CUDA-graph replay + side-stream branches;
+        # unfused: legacy default stream => plain serial launches of the same kernels
+        stream = Stream() if fused else None
+        mem = ReplayMemory(size, make_args(), rng="device", stream=stream)
         mem.add_batch(orc_ring.actions, orc_ring.rewards, orc_ring.screens, orc_ring.terminals)
         mem.set_cursor(orc_ring.count, orc_ring.current)
-        net, _ = _paired(4, mode)
+        net, _ = _paired(4, mode, stream=stream)
         random.seed(77)
         mem.seed_device_rng(random)
         if fused:
-            net.train_fused(mem, nsteps=5)
+            net.train_fused(mem, nsteps=2)
+            net.train_fused(mem, nsteps=3)                      # second call replays the cached graph
         else:
             for _ in range(5):
                 net.train(mem.getMinibatch(), 0)
