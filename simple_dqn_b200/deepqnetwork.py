@@ -42,6 +42,7 @@ class DeepQNetwork:
         if _arg(args, "stochastic_round", False):
             raise NotImplementedError("--stochastic_round is not implemented on the B200 path")
         self.device = _arg(args, "device_id", 0) if device is None else device
+        self._stream_obj = stream            # keep the stream alive as long as this object uses it
         self._stream = L.stream_ptr(stream)
 
         cfg = L.NetConfig()

@@ -66,6 +66,7 @@ class ReplayMemory:
         self.device = device
         self.rng_mode = rng
         self.device_minibatch = device_minibatch
+        self._stream_obj = stream            # keep the stream alive as long as this object uses it
         self._stream = L.stream_ptr(stream)
         assert rng in ("python", "device")
         h = C.c_void_p()

@@ -35,6 +35,7 @@ class StateBuffer:
         self.dims = (args.screen_height, args.screen_width)
         self.batch_size = args.batch_size
         self.device = device
+        self._stream_obj = stream            # keep the stream alive as long as this object uses it
         self._stream = L.stream_ptr(stream)
         h = C.c_void_p()
         L.call("b200dqn_statebuf_create", device, self.dims[0], self.dims[1], self.history_length, self.batch_size,
