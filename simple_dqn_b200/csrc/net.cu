@@ -5,20 +5,47 @@
 #include <new>
 #include <vector>
 
+#include <cuda_fp16.h>
+
 #include "net.cuh"
 #include "net_umma.cuh"
 
 namespace b200 {
 
 // ------------------------------------------------------------------------------------------
-// K2e: finish fc1 (sum split-K partials, Rectlin) and run fc2 (Affine nout=A, no activation).
-// grid = (rows, nets), block = 512 (one thread per hidden unit).
+// K2e + K3 + K4a/K5a ("head"): finish fc1 (sum split-K partials, Rectlin), run fc2 (Affine
+// nout=A, no activation) for both networks, and — in the last CTA to finish (ticket counter) —
+// the TD target / delta / cost / clip of src/deepqnetwork.py:124-159 and the fc2 backward:
+//   dZ4[b][k] = (sum_a delta[b][a] W5[k][a]) * (H4[b][k] > 0),  dW5[k][a] = sum_b H4[b][k] delta[b][a].
+// The reference forms the target on the host in Python floats (double) and stores it into a
+// float32 array; we do the same arithmetic in fp64 and round once.  cost is the batch mean of
+// 0.5*sum_a delta^2 BEFORE the clip.  grid = (rows, nets), block = 512 (one thread per hidden unit).
 // ------------------------------------------------------------------------------------------
+struct HeadTrainArgs {
+  int enable;
+  const uint8_t* actions;
+  const int64_t* rewards;
+  const uint8_t* terminals;
+  const int32_t* midx;
+  double discount;
+  int min_reward, max_reward;
+  float clip;
+  float* delta;       // [rows][A]
+  float* cost_ring;
+  uint32_t* step;
+  uint32_t* ticket;
+  float* dz4;         // [rows][512]
+  float* dw5;         // [512][A]
+  __half* dz4_hi;     // fp16 hi / scaled-lo planes of dZ4 for the tcgen05 dgrad (nullptr in fp32 mode)
+  int64_t dz4_lo_off;
+};
+
 __global__ void __launch_bounds__(kHidden)
-k_fc2_fwd(const float* __restrict__ part, int splits, int rows, float* h4_online, float* h4_target,
-          const float* __restrict__ w5_online, const float* __restrict__ w5_target, float* q_online,
-          float* q_target, int A) {
+k_head(const float* __restrict__ part, int splits, int rows, float* h4_online, float* h4_target,
+       const float* __restrict__ w5_online, const float* __restrict__ w5_target, float* q_online,
+       float* q_target, int A, const HeadTrainArgs td) {
   __shared__ float red[kHidden / 32][kMaxActions];
+  __shared__ int s_last;
   const int b = blockIdx.x, z = blockIdx.y, t = threadIdx.x;
   float h = 0.f;
   for (int s = 0; s < splits; ++s) h += part[((z * splits + s) * rows + b) * kHidden + t];
@@ -38,68 +65,62 @@ k_fc2_fwd(const float* __restrict__ part, int splits, int rows, float* h4_online
     for (int wI = 0; wI < kHidden / 32; ++wI) v += red[wI][t];
     (z ? q_target : q_online)[b * A + t] = v;
   }
-}
+  if (!td.enable) return;
 
-// ------------------------------------------------------------------------------------------
-// K3: TD target, delta, cost, clip — src/deepqnetwork.py:124-159.  The reference forms the target
-// on the host in Python floats (double) and stores it into a float32 array; we do the same
-// arithmetic in fp64 and round once.  cost is the batch mean of 0.5*sum_a delta^2 BEFORE the clip.
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-k_td(const float* __restrict__ q_pre, const float* __restrict__ q_post, const uint8_t* __restrict__ actions,
-     const int64_t* __restrict__ rewards, const uint8_t* __restrict__ terminals,
-     const int32_t* __restrict__ midx, int rows, int A, double discount, int min_reward, int max_reward,
-     float clip, float* __restrict__ delta, float* __restrict__ cost_ring, uint32_t* __restrict__ step) {
-  __shared__ float s_cost[256];
-  const int b = threadIdx.x;
-  float c = 0.f;
-  for (int bb = b; bb < rows; bb += blockDim.x) {
-    const int64_t mi = midx[bb];
-    const int a = actions[mi];
-    int64_t r = rewards[mi];
-    r = r < min_reward ? min_reward : (r > max_reward ? max_reward : r);   // np.clip (:136)
-    float maxq = q_post[bb * A];
-    for (int j = 1; j < A; ++j) maxq = fmaxf(maxq, q_post[bb * A + j]);     // be.max(postq, axis=0) (:124)
-    const double y = terminals[mi] ? double(r) : double(r) + discount * double(maxq);  // :140-143
-    const float target = static_cast<float>(y);
-    const float pre = q_pre[bb * A + a];
-    float d = pre - target;                                                  // SumSquared gradient (:149)
-    c += 0.5f * d * d;                                                       // :154, before the clip
-    if (clip > 0.f) d = fminf(fmaxf(d, -clip), clip);                        // :158-159
-    for (int j = 0; j < A; ++j) delta[bb * A + j] = (j == a) ? d : 0.f;
-  }
-  s_cost[b] = c;
+  // ---- last CTA standing does the (tiny) TD + fc2 backward
+  __threadfence();
   __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if (b < o) s_cost[b] += s_cost[b + o];
-    __syncthreads();
+  if (t == 0) s_last = (atomicAdd(td.ticket, 1u) == gridDim.x * gridDim.y - 1) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  float c = 0.f;
+  for (int bb = t; bb < rows; bb += kHidden) {
+    const int64_t mi = td.midx[bb];
+    const int a = td.actions[mi];
+    int64_t r = td.rewards[mi];
+    r = r < td.min_reward ? td.min_reward : (r > td.max_reward ? td.max_reward : r);     // np.clip (:136)
+    float maxq = __ldcg(q_target + bb * A);
+    for (int j = 1; j < A; ++j) maxq = fmaxf(maxq, __ldcg(q_target + bb * A + j));       // be.max(postq) (:124)
+    const double y = td.terminals[mi] ? double(r) : double(r) + td.discount * double(maxq);  // :140-143
+    const float target = static_cast<float>(y);
+    float d = __ldcg(q_online + bb * A + a) - target;                                     // SumSquared grad (:149)
+    c += 0.5f * d * d;                                                                    // :154, before the clip
+    if (td.clip > 0.f) d = fminf(fmaxf(d, -td.clip), td.clip);                            // :158-159
+    for (int j = 0; j < A; ++j) td.delta[bb * A + j] = (j == a) ? d : 0.f;
   }
-  if (b == 0) {
-    const uint32_t s = *step;
-    cost_ring[s % kCostRing] = s_cost[0] / float(rows);
-    *step = s + 1;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((t & 31) == 0) red[t >> 5][0] = c;
+  __syncthreads();   // also orders the delta[] writes before the reads below (same CTA)
+  if (t == 0) {
+    float tot = 0.f;
+    for (int wI = 0; wI < kHidden / 32; ++wI) tot += red[wI][0];
+    const uint32_t sidx = *td.step;
+    td.cost_ring[sidx % kCostRing] = tot / float(rows);
+    *td.step = sidx + 1;
+    *td.ticket = 0;   // re-arm for the next launch
   }
-}
-
-// ------------------------------------------------------------------------------------------
-// K4a/K5a: fc2 backward.  blocks [0,rows): dZ4[b][k] = (sum_a delta[b][a] W5[k][a]) * (H4[b][k] > 0);
-// blocks [rows, rows+A): dW5[k][a] = sum_b H4[b][k] * delta[b][a].
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kHidden)
-k_fc2_bwd(const float* __restrict__ delta, const float* __restrict__ w5, const float* __restrict__ h4, int rows,
-          int A, float* __restrict__ dz4, float* __restrict__ dw5) {
-  const int k = threadIdx.x;
-  if (blockIdx.x < rows) {
-    const int b = blockIdx.x;
+  float dw[kMaxActions];
+#pragma unroll
+  for (int a = 0; a < kMaxActions; ++a) dw[a] = 0.f;
+  for (int bb = 0; bb < rows; ++bb) {
+    const float hv = __ldcg(h4_online + bb * kHidden + t);
     float v = 0.f;
-    for (int a = 0; a < A; ++a) v = fmaf(delta[b * A + a], w5[k * A + a], v);
-    dz4[b * kHidden + k] = h4[b * kHidden + k] > 0.f ? v : 0.f;
-  } else {
-    const int a = blockIdx.x - rows;
-    float v = 0.f;
-    for (int b = 0; b < rows; ++b) v = fmaf(h4[b * kHidden + k], delta[b * A + a], v);
-    dw5[k * A + a] = v;
+    for (int a = 0; a < A; ++a) {
+      const float d = td.delta[bb * A + a];
+      v = fmaf(d, w5_online[t * A + a], v);
+      dw[a] = fmaf(hv, d, dw[a]);
+    }
+    const float o = hv > 0.f ? v : 0.f;
+    td.dz4[bb * kHidden + t] = o;
+    if (td.dz4_hi) {
+      const __half h = __float2half_rn(o);
+      td.dz4_hi[bb * kHidden + t] = h;
+      td.dz4_hi[td.dz4_lo_off + bb * kHidden + t] = __float2half_rn((o - __half2float(h)) * 2048.0f);
+    }
   }
+  for (int a = 0; a < A; ++a) td.dw5[t * A + a] = dw[a];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -186,7 +207,8 @@ struct FrameSource {
 };
 
 // Model.fprop for `nets` networks (z = 0 online, z = 1 target) on `rows` samples.
-static int forward(b200dqn_net* n, const FrameSource& fs, int nets, int rows, cudaStream_t st) {
+static int forward(b200dqn_net* n, const FrameSource& fs, int nets, int rows, cudaStream_t st,
+                   const HeadTrainArgs& td) {
   const LayerTable& lt = n->lt;
   const float* w[2] = {n->d_w, n->d_tw};
   int rc;
@@ -225,10 +247,10 @@ static int forward(b200dqn_net* n, const FrameSource& fs, int nets, int rows, cu
     }
   }
   const int fc1_splits = n->cfg.math_mode == B200DQN_MATH_TCGEN05 ? umma_fc1_splits() : kFc1Splits;
-  k_fc2_fwd<<<dim3(rows, nets), kHidden, 0, st>>>(n->d_fc1part, fc1_splits, rows, n->d_h4[0], n->d_h4[1],
-                                                  w[0] + lt.off[4], w[1] + lt.off[4], n->d_q[0], n->d_q[1], n->A);
+  k_head<<<dim3(rows, nets), kHidden, 0, st>>>(n->d_fc1part, fc1_splits, rows, n->d_h4[0], n->d_h4[1],
+                                               w[0] + lt.off[4], w[1] + lt.off[4], n->d_q[0], n->d_q[1], n->A, td);
   B2_LAUNCH_CHECK();
-  B2_PROF("fc2_fwd", st);
+  B2_PROF(td.enable ? "head(fc2+td+fc2_bwd)" : "fc2_fwd", st);
   return B200DQN_OK;
 }
 
@@ -294,6 +316,7 @@ static int optimizer_range(b200dqn_net* n, int l0, int l1, int mode, int rows, c
                                                   decay, omd, eps);
   B2_LAUNCH_CHECK();
   B2_PROF(label, st);
+  if (mode & 4) return umma_pack_layers(n, 0, l0, l1, st);   // refresh the fp16 tile images of the updated layers
   return B200DQN_OK;
 }
 
@@ -309,18 +332,13 @@ static int optimizer_range(b200dqn_net* n, int l0, int l1, int mode, int rows, c
 // own layer, and every per-layer RMSProp update only needs that layer's wgrad plus the guarantee
 // that the dgrad reading the old weights has finished.  On a single GPU those independent pieces
 // run on three side streams (graph branches under capture):
-//   main : fc2_bwd . fc1_dgrad . conv3_dgrad . conv2_dgrad . conv1_wgrad . opt(conv1)
+//   main : head . fc1_dgrad . conv3_dgrad . conv2_dgrad . conv1_wgrad . opt(conv1)
 //   sA   :          fc1_wgrad ......... [after fc1_dgrad]   opt(fc1, fc2)
 //   sB   :                    conv3_wgrad .. [after conv3_dgrad] opt(conv3)
 //   sC   :                               conv2_wgrad .. [after conv2_dgrad] opt(conv2)
 // In a communicator the update follows one all-reduce of the whole gradient, so the simple
 // serial order is kept.
 static int backward_and_update(b200dqn_net* n, const FrameSource& fs, int rows, cudaStream_t st, bool update) {
-  const LayerTable& lt = n->lt;
-  k_fc2_bwd<<<rows + n->A, kHidden, 0, st>>>(n->d_delta, n->d_w + lt.off[4], n->d_h4[0], rows, n->A, n->d_dz4,
-                                             n->d_part + lt.part_off[4]);
-  B2_LAUNCH_CHECK();
-  B2_PROF("fc2_bwd", st);
   const bool branches = update && n->world == 1 && !g_prof_on && n->use_branches && st != nullptr;
   if (!branches) {
     for (int op = kFc1Wgrad; op <= kConv1Wgrad; ++op) B2_TRY(bwd_op(n, fs, rows, BwdOp(op), st));
@@ -371,12 +389,11 @@ static int backward_and_update(b200dqn_net* n, const FrameSource& fs, int rows, 
 static int train_step(b200dqn_net* n, const FrameSource& fs, const uint8_t* actions, const int64_t* rewards,
                       const uint8_t* terminals, const int32_t* midx, cudaStream_t st) {
   const int rows = n->nb;
-  B2_TRY(forward(n, fs, 2, rows, st));
-  k_td<<<1, 256, 0, st>>>(n->d_q[0], n->d_q[1], actions, rewards, terminals, midx, rows, n->A,
-                          n->cfg.discount_rate, n->cfg.min_reward, n->cfg.max_reward, float(n->cfg.clip_error),
-                          n->d_delta, n->d_cost, n->d_step);
-  B2_LAUNCH_CHECK();
-  B2_PROF("td", st);
+  HeadTrainArgs td{1, actions, rewards, terminals, midx, n->cfg.discount_rate, n->cfg.min_reward, n->cfg.max_reward,
+                   float(n->cfg.clip_error), n->d_delta, n->d_cost, n->d_step, n->d_ticket, n->d_dz4,
+                   n->d_part + n->lt.part_off[4], nullptr, 0};
+  umma_dz4_planes(n, &td.dz4_hi, &td.dz4_lo_off);
+  B2_TRY(forward(n, fs, 2, rows, st, td));
   return backward_and_update(n, fs, rows, st, true);
 }
 
@@ -505,6 +522,8 @@ extern "C" int b200dqn_net_create(int device, const b200dqn_net_config* cfg, b20
   B2_CHECK_CUDA(fmalloc(&n->d_cost, kCostRing));
   B2_CHECK_CUDA(cudaMalloc(&n->d_step, sizeof(uint32_t)));
   B2_CHECK_CUDA(cudaMemset(n->d_step, 0, sizeof(uint32_t)));
+  B2_CHECK_CUDA(cudaMalloc(&n->d_ticket, sizeof(uint32_t)));
+  B2_CHECK_CUDA(cudaMemset(n->d_ticket, 0, sizeof(uint32_t)));
   const size_t state_bytes = size_t(nb) * kHist * kFrameBytes;
   B2_CHECK_CUDA(cudaMalloc(&n->d_pre, state_bytes + 256));
   B2_CHECK_CUDA(cudaMalloc(&n->d_post, state_bytes + 256));
@@ -543,7 +562,7 @@ extern "C" int b200dqn_net_destroy(b200dqn_net* n) {
     cudaFree(n->d_h1[z]); cudaFree(n->d_h2[z]); cudaFree(n->d_h3[z]); cudaFree(n->d_h4[z]); cudaFree(n->d_q[z]);
   }
   cudaFree(n->d_fc1part); cudaFree(n->d_delta); cudaFree(n->d_dz4); cudaFree(n->d_dz3); cudaFree(n->d_dz2);
-  cudaFree(n->d_dz1); cudaFree(n->d_cost); cudaFree(n->d_step); cudaFree(n->d_pre); cudaFree(n->d_post);
+  cudaFree(n->d_dz1); cudaFree(n->d_cost); cudaFree(n->d_step); cudaFree(n->d_ticket); cudaFree(n->d_pre); cudaFree(n->d_post);
   cudaFree(n->d_act); cudaFree(n->d_term); cudaFree(n->d_rew); cudaFree(n->d_iota1); cudaFree(n->d_iota4);
   cudaFreeHost(n->h_pin);
   delete n;
@@ -616,7 +635,8 @@ extern "C" int b200dqn_net_predict_device(b200dqn_net* n, const uint8_t* dev_sta
   DeviceGuard g(n->device);
   cudaStream_t st = as_stream(stream);
   FrameSource fs{{dev_states, dev_states}, {n->d_iota4, n->d_iota4}, {0, 0}};
-  int rc = forward(n, fs, 1, live_rows, st);
+  HeadTrainArgs no_td{};
+  int rc = forward(n, fs, 1, live_rows, st, no_td);
   if (rc) return rc;
   if (dev_q != n->d_q[0])
     B2_CHECK_CUDA(cudaMemcpyAsync(dev_q, n->d_q[0], size_t(live_rows) * n->A * sizeof(float),
@@ -806,9 +826,11 @@ extern "C" int b200dqn_net_get_grads(b200dqn_net* n, int layer, float* host_dW, 
 
 extern "C" int b200dqn_net_launches_per_step(const b200dqn_net* n, int* launches) {
   B2_REQUIRE(n && launches, B200DQN_EINVAL, "null argument");
-  // sample + forward (4 GEMM-shaped + fc2) + td + fc2_bwd + 7 backward GEMMs + optimizer (+2 in a communicator)
+  // sample + forward (4 GEMM-shaped) + head (fc2 + td + fc2_bwd) + 7 backward GEMMs + optimizer launches
+  // (5 per-layer-group launches on one GPU; reduce + update around the all-reduce in a communicator)
   int fwd = (n->cfg.math_mode == B200DQN_MATH_TCGEN05) ? umma_forward_launches() : 4;
   int bwd = (n->cfg.math_mode == B200DQN_MATH_TCGEN05 && umma_has_backward()) ? umma_backward_launches() : 7;
-  *launches = 1 + fwd + 1 + 1 + 1 + bwd + (n->world > 1 ? 2 : 1);
+  const bool branches = n->world == 1 && n->use_branches;
+  *launches = 1 + fwd + 1 + bwd + (n->world > 1 ? 2 : (branches ? 4 : 1));
   return B200DQN_OK;
 }

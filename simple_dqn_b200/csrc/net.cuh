@@ -47,6 +47,7 @@ struct b200dqn_net {
   float* d_dz4 = nullptr, *d_dz3 = nullptr, *d_dz2 = nullptr, *d_dz1 = nullptr;
   float* d_cost = nullptr;     // cost ring [kCostRing]
   uint32_t* d_step = nullptr;  // device step counter (cost ring cursor)
+  uint32_t* d_ticket = nullptr;  // last-CTA-standing counter of the head kernel
 
   // unfused-mode staging (host minibatch -> device)
   uint8_t* d_pre = nullptr, *d_post = nullptr, *d_act = nullptr, *d_term = nullptr;
@@ -67,6 +68,8 @@ struct b200dqn_net {
   b200dqn_replay* graph_replay = nullptr;
   cudaStream_t graph_stream = nullptr;
   int graph_world = 0;
+
+  void* umma_state = nullptr;  // tcgen05 engine: fp16 operand planes + weight tile images (net_umma.cu)
 
   // multi-GPU
   void* nccl_comm = nullptr;

@@ -5,6 +5,7 @@
 #include "net.cuh"
 #include "net_umma.cuh"
 #include "umma.cuh"
+#include "umma2.cuh"
 
 namespace b200 {
 
@@ -307,6 +308,306 @@ struct UConv1Wgrad {
   }
 };
 
+// ==========================================================================================
+// Engine v2 (umma2.cuh): pre-split fp16 hi/lo operand planes + weight tile images.
+// ==========================================================================================
+struct UmmaState {
+  // activation planes per net: [hi plane | lo plane], NHWC fp16
+  __half* h16[3][2] = {};     // H1, H2, H3  x  (online, target)
+  int64_t h_elems[3] = {};
+  __half* dz16[3] = {};       // dZ4, dZ3, dZ2 (online)
+  int64_t dz_elems[3] = {};
+  // weight tile images ([hi | lo] per (tile, k-block))
+  uint8_t* img_fwd[2][4] = {};  // conv1, conv2, conv3, fc1  x  (online, target)
+  int64_t img_fwd_bytes[4] = {};
+  uint8_t* img_dgr[3] = {};     // fc1_dgrad (A operand), conv3_dgrad (B), conv2_dgrad (B, 4 parity classes)
+};
+static inline UmmaState* ust(b200dqn_net* n) { return static_cast<UmmaState*>(n->umma_state); }
+
+struct PlanePair {
+  __half* hi;
+  int64_t lo_off;   // lo plane = hi + lo_off
+};
+
+__device__ __forceinline__ void store_f32_and_planes(float* f32, const PlanePair& pl, int64_t i, const float v[8]) {
+  if (f32) st8(f32 + i, v);
+  umma2::split8_planes(v, pl.hi + i, pl.hi + pl.lo_off + i);
+}
+
+// ---- forward -----------------------------------------------------------------------------
+struct V2Conv1Fwd {
+  static constexpr int kBN = 32;
+  static constexpr bool kAExact = true, kARowMajorThreads = true, kBRowMajorThreads = false;
+  static constexpr int kAMode = umma2::kReg, kBMode = umma2::kBulk;
+  const uint8_t* src[2];
+  const int32_t* idx[2];
+  int shift[2];
+  const uint8_t* wimg[2];   // [4 kb][hi 32x128 | lo 32x128]
+  float* out[2];
+  PlanePair out16[2];
+  int rows;
+  __device__ int M(int) const { return rows * kP1 * kP1; }
+  __device__ int N(int) const { return kC1; }
+  __device__ void krange(int, int& kb, int& ke) const { kb = 0; ke = kK1 / 64; }
+  __device__ void a8(int z, int m, int k0, float v[8]) const {
+    if (m >= rows * kP1 * kP1) { zero8(v); return; }
+    const int n = m / (kP1 * kP1), pq = m % (kP1 * kP1), p = pq / kP1, q = pq % kP1;
+    const int c = k0 >> 6, r = (k0 >> 3) & 7;
+    const int64_t f = static_cast<int64_t>((z ? idx[1] : idx[0])[n]) + (z ? shift[1] : shift[0]) + c;
+    const uint8_t* ptr = (z ? src[1] : src[0]) + f * kFrameBytes + (p * 4 + r) * kFrameW + q * 4;
+    const uint32_t lo = *reinterpret_cast<const uint32_t*>(ptr), hi = *reinterpret_cast<const uint32_t*>(ptr + 4);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v[j] = float((lo >> (8 * j)) & 0xffu);
+      v[4 + j] = float((hi >> (8 * j)) & 0xffu);
+    }
+  }
+  __device__ const uint8_t* b_tile(int z, int, int kb) const { return (z ? wimg[1] : wimg[0]) + kb * (kC1 * 256); }
+  __device__ void store8(int z, int m, int n0, const float v[8]) const {
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = fmaxf(v[j] * (1.0f / 255.0f), 0.f);
+    store_f32_and_planes(z ? out[1] : out[0], z ? out16[1] : out16[0], int64_t(m) * kC1 + n0, o);
+  }
+};
+
+template <int H, int C, int R, int ST, int KO>
+struct V2ConvFwd {
+  static constexpr int P = (H - R) / ST + 1, K = R * R * C;
+  static_assert(K % 64 == 0 && C % 8 == 0, "k-blocks of 64, chunks of 8 channels");
+  static constexpr int kBN = KO;
+  static constexpr bool kAExact = false, kARowMajorThreads = true, kBRowMajorThreads = false;
+  static constexpr int kAMode = umma2::kAsync, kBMode = umma2::kBulk;
+  PlanePair in16[2];
+  const uint8_t* wimg[2];   // [K/64][hi KOx128 | lo KOx128]
+  float* out[2];
+  PlanePair out16[2];
+  int rows;
+  __device__ int M(int) const { return rows * P * P; }
+  __device__ int N(int) const { return KO; }
+  __device__ void krange(int, int& kb, int& ke) const { kb = 0; ke = K / 64; }
+  __device__ bool a_src(int z, int m, int k0, const __half*& hi, const __half*& lo) const {
+    const PlanePair& pl = z ? in16[1] : in16[0];
+    hi = pl.hi; lo = pl.hi + pl.lo_off;
+    if (m >= rows * P * P) return false;
+    const int n = m / (P * P), pq = m % (P * P), p = pq / P, q = pq % P;
+    const int r = k0 / (R * C), sc = k0 % (R * C);
+    const int64_t off = (int64_t(n * H + p * ST + r) * H + q * ST) * C + sc;
+    hi += off; lo += off;
+    return true;
+  }
+  __device__ const uint8_t* b_tile(int z, int, int kb) const { return (z ? wimg[1] : wimg[0]) + kb * (KO * 256); }
+  __device__ void store8(int z, int m, int n0, const float v[8]) const {
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = fmaxf(v[j], 0.f);
+    store_f32_and_planes(z ? out[1] : out[0], z ? out16[1] : out16[0], int64_t(m) * KO + n0, o);
+  }
+};
+
+struct V2Fc1Fwd {
+  static constexpr int kBN = 32;
+  static constexpr bool kAExact = false, kARowMajorThreads = false, kBRowMajorThreads = true;
+  static constexpr int kAMode = umma2::kBulk, kBMode = umma2::kAsync;
+  PlanePair in16[2];        // H3 planes [rows][3136]
+  const uint8_t* wimg[2];   // [4 mtiles][49 kb][hi 128x128 | lo 128x128]
+  float* part;              // [2*splits][rows][512]
+  int rows, splits;
+  __device__ int M(int) const { return kHidden; }
+  __device__ int N(int) const { return rows; }
+  __device__ void krange(int z, int& kb, int& ke) const {
+    const int per = (kFlat / 64 + splits - 1) / splits;
+    kb = (z % splits) * per;
+    ke = min(kb + per, kFlat / 64);
+  }
+  __device__ const uint8_t* a_tile(int z, int mtile, int kb) const {
+    return ((z / splits) ? wimg[1] : wimg[0]) + (int64_t(mtile) * (kFlat / 64) + kb) * (128 * 256);
+  }
+  __device__ bool b_src(int z, int n, int k0, const __half*& hi, const __half*& lo) const {
+    const PlanePair& pl = (z / splits) ? in16[1] : in16[0];
+    hi = pl.hi; lo = pl.hi + pl.lo_off;
+    if (n >= rows) return false;
+    hi += int64_t(n) * kFlat + k0; lo += int64_t(n) * kFlat + k0;
+    return true;
+  }
+  __device__ void store8(int z, int m, int n0, const float v[8]) const {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (n0 + j < rows) part[(z * rows + n0 + j) * kHidden + m] = v[j];
+  }
+};
+
+// ---- dgrad -------------------------------------------------------------------------------
+struct V2Fc1Dgrad {
+  static constexpr int kBN = 32;
+  static constexpr bool kAExact = false, kARowMajorThreads = true, kBRowMajorThreads = true;
+  static constexpr int kAMode = umma2::kBulk, kBMode = umma2::kAsync;
+  const uint8_t* wimg;   // [25 mtiles][8 kb][hi | lo]   rows m = flat index (p,q,c), K = hidden unit
+  PlanePair dz4;         // [rows][512]
+  const float* h3;       // [rows][3136] (mask)
+  float* dz3;
+  PlanePair dz3_16;
+  int rows;
+  __device__ int M(int) const { return kFlat; }
+  __device__ int N(int) const { return rows; }
+  __device__ void krange(int, int& kb, int& ke) const { kb = 0; ke = kHidden / 64; }
+  __device__ const uint8_t* a_tile(int, int mtile, int kb) const {
+    return wimg + (int64_t(mtile) * (kHidden / 64) + kb) * (128 * 256);
+  }
+  __device__ bool b_src(int, int n, int k0, const __half*& hi, const __half*& lo) const {
+    hi = dz4.hi; lo = dz4.hi + dz4.lo_off;
+    if (n >= rows) return false;
+    hi += int64_t(n) * kHidden + k0; lo += int64_t(n) * kHidden + k0;
+    return true;
+  }
+  __device__ void store8(int, int m, int n0, const float v[8]) const {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (n0 + j < rows) {
+        const int64_t i = int64_t(n0 + j) * kFlat + m;
+        const float o = h3[i] > 0.f ? v[j] : 0.f;
+        dz3[i] = o;
+        __half h, l;
+        umma2::split1(o, h, l);
+        dz3_16.hi[i] = h;
+        dz3_16.hi[dz3_16.lo_off + i] = l;
+      }
+  }
+};
+
+template <int H, int C, int R, int ST, int KO>
+struct V2ConvDgrad {
+  static constexpr int P = (H - R) / ST + 1, RT = R / ST, HC = (H + ST - 1) / ST, K = RT * RT * KO;
+  static_assert(K % 64 == 0 && KO % 8 == 0, "k-blocks of 64");
+  static constexpr int kBN = C;
+  static constexpr bool kAExact = false, kARowMajorThreads = true, kBRowMajorThreads = true;
+  static constexpr int kAMode = umma2::kAsync, kBMode = umma2::kBulk;
+  PlanePair dz;          // [rows][P][P][KO]
+  const uint8_t* wimg;   // [ST*ST classes][K/64][hi Cx128 | lo Cx128]
+  const float* x;        // forward activation (mask)
+  float* dx;
+  PlanePair dx16;        // hi == nullptr -> not needed
+  int rows;
+  __device__ int M(int) const { return rows * HC * HC; }
+  __device__ int N(int) const { return C; }
+  __device__ void krange(int, int& kb, int& ke) const { kb = 0; ke = K / 64; }
+  __device__ bool a_src(int z, int m, int k0, const __half*& hi, const __half*& lo) const {
+    hi = dz.hi; lo = dz.hi + dz.lo_off;
+    if (m >= rows * HC * HC) return false;
+    const int n = m / (HC * HC), yx = m % (HC * HC), yy = yx / HC, xx = yx % HC;
+    const int rp = k0 / (RT * KO), sp = (k0 / KO) % RT, ko = k0 % KO;
+    if (yy * ST + z / ST >= H || xx * ST + z % ST >= H) return false;
+    const int p = yy - rp, q = xx - sp;
+    if (p < 0 || p >= P || q < 0 || q >= P) return false;
+    const int64_t off = (int64_t(n * P + p) * P + q) * KO + ko;
+    hi += off; lo += off;
+    return true;
+  }
+  __device__ const uint8_t* b_tile(int z, int, int kb) const { return wimg + (int64_t(z) * (K / 64) + kb) * (C * 256); }
+  __device__ void store8(int z, int m, int c0, const float v[8]) const {
+    const int n = m / (HC * HC), yx = m % (HC * HC), yy = yx / HC, xx = yx % HC;
+    const int y = yy * ST + z / ST, xq = xx * ST + z % ST;
+    if (y >= H || xq >= H) return;
+    const int64_t i = (int64_t(n * H + y) * H + xq) * C + c0;
+    float xv[8], o[8];
+    ld8(x + i, xv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = xv[j] > 0.f ? v[j] : 0.f;
+    st8(dx + i, o);
+    if (dx16.hi) umma2::split8_planes(o, dx16.hi + i, dx16.hi + dx16.lo_off + i);
+  }
+};
+
+// ---- weight tile-image sources (k_pack_image) --------------------------------------------------
+template <int K, int N>
+struct PackFwdConv {   // B operand of a forward conv: rows = output channel n, K = filter taps
+  static constexpr bool kRowMajorThreads = false;
+  const float* w;      // [K][N]
+  __host__ __device__ int tiles() const { return 1; }
+  __host__ __device__ int rows() const { return N; }
+  __host__ __device__ int kblocks() const { return K / 64; }
+  __device__ void src8(int, int r, int k0, float v[8]) const {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = w[(k0 + j) * N + r];
+  }
+};
+struct PackFc1Fwd {    // A operand of the swapped fc1 forward: rows = hidden unit m, K = flat index
+  static constexpr bool kRowMajorThreads = false;
+  const float* w;      // W4 [3136][512]
+  __host__ __device__ int tiles() const { return kHidden / 128; }
+  __host__ __device__ int rows() const { return 128; }
+  __host__ __device__ int kblocks() const { return kFlat / 64; }
+  __device__ void src8(int tile, int r, int k0, float v[8]) const {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = w[(k0 + j) * kHidden + tile * 128 + r];
+  }
+};
+struct PackFc1Dgrad {  // A operand of fc1 dgrad: rows = flat index m, K = hidden unit
+  static constexpr bool kRowMajorThreads = true;
+  const float* w;
+  __host__ __device__ int tiles() const { return (kFlat + 127) / 128; }
+  __host__ __device__ int rows() const { return 128; }
+  __host__ __device__ int kblocks() const { return kHidden / 64; }
+  __device__ void src8(int tile, int r, int k0, float v[8]) const {
+    const int m = tile * 128 + r;
+    if (m >= kFlat) { zero8(v); return; }
+    ld8(w + m * kHidden + k0, v);
+  }
+};
+template <int H, int C, int R, int ST, int KO>
+struct PackConvDgrad { // B operand of a conv dgrad, one tile per output-parity class
+  static constexpr int RT = R / ST, K = RT * RT * KO;
+  static constexpr bool kRowMajorThreads = true;
+  const float* w;      // [(r,s,c)][KO]
+  __host__ __device__ int tiles() const { return ST * ST; }
+  __host__ __device__ int rows() const { return C; }
+  __host__ __device__ int kblocks() const { return K / 64; }
+  __device__ void src8(int z, int c, int k0, float v[8]) const {
+    const int rp = k0 / (RT * KO), sp = (k0 / KO) % RT, ko = k0 % KO;
+    const int r = rp * ST + z / ST, s = sp * ST + z % ST;
+    ld8(w + ((r * R + s) * C + c) * KO + ko, v);
+  }
+};
+
+static int64_t fwd_image_bytes(int layer) {
+  switch (layer) {
+    case 0: return int64_t(kK1 / 64) * kC1 * 256;
+    case 1: return int64_t(kK2 / 64) * kC2 * 256;
+    case 2: return int64_t(kK3 / 64) * kC3 * 256;
+    default: return int64_t(kHidden / 128) * (kFlat / 64) * 128 * 256;
+  }
+}
+
+// (re)build the tile images of layers [l0, l1] of network `which` from its fp32 master weights
+int umma_pack_layers(b200dqn_net* n, int which, int l0, int l1, cudaStream_t st) {
+  if (n->cfg.math_mode != B200DQN_MATH_TCGEN05) return B200DQN_OK;
+  UmmaState* u = ust(n);
+  const LayerTable& lt = n->lt;
+  const float* w = which ? n->d_tw : n->d_w;
+  int rc = 0;
+  for (int l = l0; l <= l1 && !rc; ++l) {
+    switch (l) {
+      case 0: rc = umma2::launch_pack("pack", PackFwdConv<kK1, kC1>{w + lt.off[0]}, u->img_fwd[which][0], st); break;
+      case 1:
+        rc = umma2::launch_pack("pack", PackFwdConv<kK2, kC2>{w + lt.off[1]}, u->img_fwd[which][1], st);
+        if (!rc && !which)
+          rc = umma2::launch_pack("pack", PackConvDgrad<kP1, kC1, 4, 2, kC2>{w + lt.off[1]}, u->img_dgr[2], st);
+        break;
+      case 2:
+        rc = umma2::launch_pack("pack", PackFwdConv<kK3, kC3>{w + lt.off[2]}, u->img_fwd[which][2], st);
+        if (!rc && !which)
+          rc = umma2::launch_pack("pack", PackConvDgrad<kP2, kC2, 3, 1, kC3>{w + lt.off[2]}, u->img_dgr[1], st);
+        break;
+      case 3:
+        rc = umma2::launch_pack("pack", PackFc1Fwd{w + lt.off[3]}, u->img_fwd[which][3], st);
+        if (!rc && !which) rc = umma2::launch_pack("pack", PackFc1Dgrad{w + lt.off[3]}, u->img_dgr[0], st);
+        break;
+      default: break;  // fc2 runs on CUDA cores (N = A <= 18)
+    }
+  }
+  return rc;
+}
+
 constexpr int kUFc1Splits = 7;    // 49 k-blocks of 64 -> 7 per CTA; 4 M-tiles x 7 x 2 nets = 56 CTAs
 constexpr int kUWgradKb = 4;      // k-blocks (256 pixels) per wgrad split
 
@@ -317,46 +618,115 @@ int umma_wgrad_splits(int layer, int rows) {
 }
 
 int umma_net_init(b200dqn_net* n) {
-  (void)n;
+  if (n->cfg.math_mode != B200DQN_MATH_TCGEN05) return B200DQN_OK;
+  auto* u = new UmmaState();
+  n->umma_state = u;
+  const int nb = n->nb;
+  u->h_elems[0] = int64_t(nb) * kP1 * kP1 * kC1;
+  u->h_elems[1] = int64_t(nb) * kP2 * kP2 * kC2;
+  u->h_elems[2] = int64_t(nb) * kFlat;
+  u->dz_elems[0] = int64_t(nb) * kHidden;
+  u->dz_elems[1] = int64_t(nb) * kFlat;
+  u->dz_elems[2] = int64_t(nb) * kP2 * kP2 * kC2;
+  for (int i = 0; i < 3; ++i) {
+    for (int z = 0; z < 2; ++z) {
+      B2_CHECK_CUDA(cudaMalloc(&u->h16[i][z], 2 * u->h_elems[i] * sizeof(__half)));
+      B2_CHECK_CUDA(cudaMemset(u->h16[i][z], 0, 2 * u->h_elems[i] * sizeof(__half)));
+    }
+    B2_CHECK_CUDA(cudaMalloc(&u->dz16[i], 2 * u->dz_elems[i] * sizeof(__half)));
+    B2_CHECK_CUDA(cudaMemset(u->dz16[i], 0, 2 * u->dz_elems[i] * sizeof(__half)));
+  }
+  for (int l = 0; l < 4; ++l) {
+    u->img_fwd_bytes[l] = fwd_image_bytes(l);
+    for (int z = 0; z < 2; ++z) {
+      if (z == 1 && n->d_tw == n->d_w) { u->img_fwd[1][l] = u->img_fwd[0][l]; continue; }
+      B2_CHECK_CUDA(cudaMalloc(&u->img_fwd[z][l], u->img_fwd_bytes[l]));
+      B2_CHECK_CUDA(cudaMemset(u->img_fwd[z][l], 0, u->img_fwd_bytes[l]));
+    }
+  }
+  const int64_t dgr_bytes[3] = {int64_t((kFlat + 127) / 128) * (kHidden / 64) * 128 * 256,
+                                int64_t(kK3 / 64) * kC2 * 256, int64_t(4) * (256 / 64) * kC1 * 256};
+  for (int i = 0; i < 3; ++i) {
+    B2_CHECK_CUDA(cudaMalloc(&u->img_dgr[i], dgr_bytes[i]));
+    B2_CHECK_CUDA(cudaMemset(u->img_dgr[i], 0, dgr_bytes[i]));
+  }
   return B200DQN_OK;
 }
-void umma_net_destroy(b200dqn_net*) {}
-int umma_weights_changed(b200dqn_net*, cudaStream_t) { return B200DQN_OK; }
-int umma_target_synced(b200dqn_net*, cudaStream_t) { return B200DQN_OK; }
+
+void umma_net_destroy(b200dqn_net* n) {
+  UmmaState* u = ust(n);
+  if (!u) return;
+  for (int i = 0; i < 3; ++i) {
+    for (int z = 0; z < 2; ++z) cudaFree(u->h16[i][z]);
+    cudaFree(u->dz16[i]);
+    cudaFree(u->img_dgr[i]);
+  }
+  for (int l = 0; l < 4; ++l) {
+    if (u->img_fwd[1][l] != u->img_fwd[0][l]) cudaFree(u->img_fwd[1][l]);
+    cudaFree(u->img_fwd[0][l]);
+  }
+  delete u;
+  n->umma_state = nullptr;
+}
+
+int umma_weights_changed(b200dqn_net* n, cudaStream_t st) {
+  if (n->cfg.math_mode != B200DQN_MATH_TCGEN05) return B200DQN_OK;
+  int rc = umma_pack_layers(n, 0, 0, 3, st);
+  if (!rc && n->d_tw != n->d_w) rc = umma_pack_layers(n, 1, 0, 3, st);
+  return rc;
+}
+
+int umma_target_synced(b200dqn_net* n, cudaStream_t st) {
+  if (n->cfg.math_mode != B200DQN_MATH_TCGEN05 || n->d_tw == n->d_w) return B200DQN_OK;
+  UmmaState* u = ust(n);
+  for (int l = 0; l < 4; ++l)
+    B2_CHECK_CUDA(cudaMemcpyAsync(u->img_fwd[1][l], u->img_fwd[0][l], u->img_fwd_bytes[l], cudaMemcpyDeviceToDevice, st));
+  return B200DQN_OK;
+}
+
+void umma_dz4_planes(b200dqn_net* n, __half** hi, int64_t* lo_off) {
+  UmmaState* u = ust(n);
+  *hi = u ? u->dz16[0] : nullptr;
+  *lo_off = u ? u->dz_elems[0] : 0;
+}
 
 int umma_forward(b200dqn_net* n, const uint8_t* const src[2], const int32_t* const idx[2], const int shift[2],
                  int nets, int rows, cudaStream_t st) {
-  const LayerTable& lt = n->lt;
-  const float* w[2] = {n->d_w, n->d_tw};
+  UmmaState* u = ust(n);
   int rc;
+  auto planes = [&](int i, int z) { return PlanePair{u->h16[i][z], u->h_elems[i]}; };
   {
-    UConv1Fwd p;
+    V2Conv1Fwd p;
     for (int z = 0; z < 2; ++z) {
       p.src[z] = src[z]; p.idx[z] = idx[z]; p.shift[z] = shift[z];
-      p.w[z] = w[z] + lt.off[0]; p.out[z] = n->d_h1[z];
+      p.wimg[z] = u->img_fwd[z][0]; p.out[z] = n->d_h1[z]; p.out16[z] = planes(0, z);
     }
     p.rows = rows;
-    if ((rc = umma::launch_umma("conv1_fwd", p, rows * kP1 * kP1, kC1, nets, st))) return rc;
+    if ((rc = umma2::launch_umma2("conv1_fwd", p, rows * kP1 * kP1, kC1, nets, st))) return rc;
   }
   {
-    using P = UConvFwd<kP1, kC1, 4, 2, kC2>;
+    using P = V2ConvFwd<kP1, kC1, 4, 2, kC2>;
     P p;
-    for (int z = 0; z < 2; ++z) { p.in[z] = n->d_h1[z]; p.w[z] = w[z] + lt.off[1]; p.out[z] = n->d_h2[z]; }
+    for (int z = 0; z < 2; ++z) {
+      p.in16[z] = planes(0, z); p.wimg[z] = u->img_fwd[z][1]; p.out[z] = n->d_h2[z]; p.out16[z] = planes(1, z);
+    }
     p.rows = rows;
-    if ((rc = umma::launch_umma("conv2_fwd", p, rows * kP2 * kP2, kC2, nets, st))) return rc;
+    if ((rc = umma2::launch_umma2("conv2_fwd", p, rows * kP2 * kP2, kC2, nets, st))) return rc;
   }
   {
-    using P = UConvFwd<kP2, kC2, 3, 1, kC3>;
+    using P = V2ConvFwd<kP2, kC2, 3, 1, kC3>;
     P p;
-    for (int z = 0; z < 2; ++z) { p.in[z] = n->d_h2[z]; p.w[z] = w[z] + lt.off[2]; p.out[z] = n->d_h3[z]; }
+    for (int z = 0; z < 2; ++z) {
+      p.in16[z] = planes(1, z); p.wimg[z] = u->img_fwd[z][2]; p.out[z] = n->d_h3[z]; p.out16[z] = planes(2, z);
+    }
     p.rows = rows;
-    if ((rc = umma::launch_umma("conv3_fwd", p, rows * kP3 * kP3, kC3, nets, st))) return rc;
+    if ((rc = umma2::launch_umma2("conv3_fwd", p, rows * kP3 * kP3, kC3, nets, st))) return rc;
   }
   {
-    UFc1Fwd p;
-    for (int z = 0; z < 2; ++z) { p.in[z] = n->d_h3[z]; p.w[z] = w[z] + lt.off[3]; }
+    V2Fc1Fwd p;
+    for (int z = 0; z < 2; ++z) { p.in16[z] = planes(2, z); p.wimg[z] = u->img_fwd[z][3]; }
     p.part = n->d_fc1part; p.rows = rows; p.splits = kUFc1Splits;
-    if ((rc = umma::launch_umma("fc1_fwd", p, kHidden, rows, nets * kUFc1Splits, st))) return rc;
+    if ((rc = umma2::launch_umma2("fc1_fwd", p, kHidden, rows, nets * kUFc1Splits, st))) return rc;
   }
   return B200DQN_OK;
 }
@@ -371,8 +741,10 @@ int umma_backward_op(b200dqn_net* n, int op, const uint8_t* src, const int32_t* 
       return umma::launch_umma("fc1_wgrad", p, kFlat, kHidden, 1, st);
     }
     case 1: {
-      UFc1Dgrad p{w + lt.off[3], n->d_dz4, n->d_h3[0], n->d_dz3, rows};
-      return umma::launch_umma("fc1_dgrad", p, kFlat, rows, 1, st);
+      UmmaState* u = ust(n);
+      V2Fc1Dgrad p{u->img_dgr[0], PlanePair{u->dz16[0], u->dz_elems[0]}, n->d_h3[0], n->d_dz3,
+                   PlanePair{u->dz16[1], u->dz_elems[1]}, rows};
+      return umma2::launch_umma2("fc1_dgrad", p, kFlat, rows, 1, st);
     }
     case 2: {
       using P = UConvWgrad<kP2, kC2, 3, 1, kC3>;
@@ -380,9 +752,11 @@ int umma_backward_op(b200dqn_net* n, int op, const uint8_t* src, const int32_t* 
       return umma::launch_umma("conv3_wgrad", p, P::KW, kC3, lt.splits[2], st);
     }
     case 3: {
-      using P = UConvDgrad<kP2, kC2, 3, 1, kC3>;
-      P p{n->d_dz3, w + lt.off[2], n->d_h2[0], n->d_dz2, rows};
-      return umma::launch_umma("conv3_dgrad", p, rows * P::HC * P::HC, kC2, 1, st);
+      UmmaState* u = ust(n);
+      using P = V2ConvDgrad<kP2, kC2, 3, 1, kC3>;
+      P p{PlanePair{u->dz16[1], u->dz_elems[1]}, u->img_dgr[1], n->d_h2[0], n->d_dz2,
+          PlanePair{u->dz16[2], u->dz_elems[2]}, rows};
+      return umma2::launch_umma2("conv3_dgrad", p, rows * P::HC * P::HC, kC2, 1, st);
     }
     case 4: {
       using P = UConvWgrad<kP1, kC1, 4, 2, kC2>;
@@ -390,9 +764,10 @@ int umma_backward_op(b200dqn_net* n, int op, const uint8_t* src, const int32_t* 
       return umma::launch_umma("conv2_wgrad", p, P::KW, kC2, lt.splits[1], st);
     }
     case 5: {
-      using P = UConvDgrad<kP1, kC1, 4, 2, kC2>;
-      P p{n->d_dz2, w + lt.off[1], n->d_h1[0], n->d_dz1, rows};
-      return umma::launch_umma("conv2_dgrad", p, rows * P::HC * P::HC, kC1, 4, st);
+      UmmaState* u = ust(n);
+      using P = V2ConvDgrad<kP1, kC1, 4, 2, kC2>;
+      P p{PlanePair{u->dz16[2], u->dz_elems[2]}, u->img_dgr[2], n->d_h1[0], n->d_dz1, PlanePair{nullptr, 0}, rows};
+      return umma2::launch_umma2("conv2_dgrad", p, rows * P::HC * P::HC, kC1, 4, st);
     }
     default: {
       UConv1Wgrad p{src, idx, shift, n->d_dz1, n->d_part + lt.part_off[0], rows, kUWgradKb};

@@ -1,6 +1,8 @@
 // net_umma.cuh — entry points of the tcgen05 (math_mode TCGEN05) engine and of the NCCL glue,
 // called from net.cu.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 struct b200dqn_net;
@@ -15,6 +17,10 @@ int umma_target_synced(b200dqn_net* n, cudaStream_t st);    // target <- online
 int umma_forward(b200dqn_net* n, const uint8_t* const src[2], const int32_t* const idx[2], const int shift[2],
                  int nets, int rows, cudaStream_t st);
 int umma_fc1_splits();
+// rebuild the fp16 hi/lo tile images of layers [l0, l1] of network `which` (0 online, 1 target)
+int umma_pack_layers(b200dqn_net* n, int which, int l0, int l1, cudaStream_t st);
+// fp16 hi plane of dZ4 and the offset of its lo plane (nullptr when math_mode != TCGEN05)
+void umma_dz4_planes(b200dqn_net* n, __half** hi, int64_t* lo_off);
 int umma_wgrad_splits(int layer, int rows);   // split-K factor of the conv wgrad of `layer` (0..2)
 bool umma_has_backward();
 // op: 0 fc1_wgrad, 1 fc1_dgrad, 2 conv3_wgrad, 3 conv3_dgrad, 4 conv2_wgrad, 5 conv2_dgrad, 6 conv1_wgrad

@@ -1,0 +1,303 @@
+// umma2.cuh — tcgen05 implicit-GEMM kernel, engine v2: operands arrive PRE-SPLIT (fp16 hi / scaled
+// fp16 lo planes written once by their producer), so the mainloop is pure data movement:
+//
+//   kAsync : activations / gradients live in HBM as NHWC fp16 hi+lo planes; every 16-byte chunk of
+//            the canonical K-major SWIZZLE_128B tile is one cp.async (LDGSTS) straight from global to
+//            its swizzled shared-memory slot — the im2col gather costs no registers and no math.
+//   kBulk  : weights live in HBM as ready-made tile images (the exact shared-memory byte image of a
+//            [rows x 64] hi tile followed by the lo tile); one elected thread fetches a whole tile
+//            with ONE TMA bulk copy (cp.async.bulk, SASS UBLKCP) that completes on an mbarrier.
+//   kReg   : the u8 frame window of conv1 is converted in registers (u8 -> fp16 is exact, no lo part).
+//
+// 4-stage ring: loads for k-block i+3 are in flight while the tensor core works on k-block i.
+// Accumulation scheme (3 MMAs / k-step, fp32 in TMEM) as in umma.cuh.
+#pragma once
+#include "umma.cuh"
+
+namespace b200 {
+namespace umma2 {
+
+using umma::kBK;
+using umma::kBM;
+using umma::kThreads;
+
+enum OperandMode { kReg = 0, kAsync = 1, kBulk = 2 };
+
+__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gsrc, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// fp32 -> (hi, lo') with the "positive stays positive" rule: a strictly positive value whose fp16
+// rounding is 0 keeps the smallest subnormal in hi, so (hi > 0) is exactly the Rectlin mask.
+__device__ __forceinline__ void split1(float x, __half& hi, __half& lo) {
+  __half h = __float2half_rn(x);
+  if (x > 0.f && __half_as_ushort(h) == 0) h = __ushort_as_half(1);
+  hi = h;
+  lo = __float2half_rn((x - __half2float(h)) * umma::kLoScale);
+}
+__device__ __forceinline__ void split8_planes(const float v[8], __half* hi_dst, __half* lo_dst) {
+  __align__(16) __half h[8];
+  __align__(16) __half l[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) split1(v[j], h[j], l[j]);
+  *reinterpret_cast<uint4*>(hi_dst) = *reinterpret_cast<const uint4*>(h);
+  *reinterpret_cast<uint4*>(lo_dst) = *reinterpret_cast<const uint4*>(l);
+}
+
+// Problem P (see net_umma.cu):
+//   static constexpr int kBN; static constexpr bool kAExact;
+//   static constexpr int kAMode, kBMode;                         (OperandMode)
+//   static constexpr bool kARowMajorThreads, kBRowMajorThreads;  (thread -> chunk mapping, as in umma.cuh)
+//   int M(z), N(z); void krange(z, kb0, kb1);
+//   kReg  : void a8(z, m, k0, float v[8])                                   (A only)
+//   kAsync: bool a_src(z, m, k0, const __half*& hi, const __half*& lo)      false -> zero fill
+//           bool b_src(z, n, k0, const __half*& hi, const __half*& lo)
+//   kBulk : const uint8_t* a_tile(z, mtile, kb) / b_tile(z, ntile, kb)      -> [hi image | lo image]
+//   void store8(z, m, n0, const float v[8])
+template <class P>
+struct Cfg2 {
+  static constexpr int BN = P::kBN;
+  static constexpr uint32_t kABytes = kBM * 128;
+  static constexpr uint32_t kBBytes = BN * 128;
+  static constexpr uint32_t kAStage = (P::kAExact ? 1 : 2) * kABytes;
+  static constexpr uint32_t kStageBytes = kAStage + 2 * kBBytes;
+  static constexpr int kStages = (4 * kStageBytes <= 200 * 1024) ? 4 : 3;
+  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024;
+  static constexpr uint32_t kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
+                                        : (2 * BN <= 256) ? 256 : 512;
+  static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N for M=128 must be a multiple of 16 in [16,256]");
+  static_assert(!(P::kAMode == kBulk && P::kAExact), "bulk A images always carry hi+lo");
+};
+
+template <class P>
+__global__ void __launch_bounds__(kThreads, 1) k_umma2(const P p) {
+  using C = Cfg2<P>;
+  constexpr int BN = C::BN;
+  constexpr int S = C::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint32_t s_tmem;
+  __shared__ __align__(8) uint64_t s_full[S];    // TMA bulk tiles landed
+  __shared__ __align__(8) uint64_t s_empty[S];   // MMAs reading the stage completed
+  __shared__ __align__(8) uint64_t s_done;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int z = blockIdx.z;
+  const int M = p.M(z), N = p.N(z);
+  const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * BN;
+  if (m0 >= M || n0 >= N) return;
+  int kb0, kb1;
+  p.krange(z, kb0, kb1);
+  const int nkb = kb1 - kb0;
+
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+
+  if (warp == 0) umma::tmem_alloc(&s_tmem, C::kTmemCols);
+  if (tid == 32) {
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_empty[s], 1);
+    }
+    mbar_init(&s_done, 1);
+    mbar_fence_init();
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tmem = s_tmem;
+  constexpr uint32_t idesc = umma::make_idesc_f16(kBM, BN);
+  constexpr bool kAnyBulk = (P::kAMode == kBulk) || (P::kBMode == kBulk);
+  constexpr uint32_t kBulkBytes = (P::kAMode == kBulk ? 2 * C::kABytes : 0) + (P::kBMode == kBulk ? 2 * C::kBBytes : 0);
+
+  // ---- producer: everything needed for k-block (kb0 + j) goes into stage j % S
+  auto issue_loads = [&](int j) {
+    const int s = j % S, kb = kb0 + j, k0 = kb * kBK;
+    const uint32_t st_addr = smem_base + s * C::kStageBytes;
+    uint8_t* st_gen = smem_gen + s * C::kStageBytes;
+    const uint32_t a_hi = st_addr, a_lo = st_addr + C::kABytes, b_hi = st_addr + C::kAStage, b_lo = b_hi + C::kBBytes;
+    if (kAnyBulk && tid == 0) {
+      mbar_arrive_expect_tx(&s_full[s], kBulkBytes);
+      if constexpr (P::kAMode == kBulk)
+        tma_bulk_g2s(st_gen, p.a_tile(z, blockIdx.x, kb), 2 * C::kABytes, &s_full[s]);
+      if constexpr (P::kBMode == kBulk)
+        tma_bulk_g2s(st_gen + C::kAStage, p.b_tile(z, blockIdx.y, kb), 2 * C::kBBytes, &s_full[s]);
+    }
+    if constexpr (P::kAMode == kAsync) {
+#pragma unroll
+      for (int i = 0; i < kBM * 8 / kThreads; ++i) {
+        const int id = tid + i * kThreads;
+        const int r = P::kARowMajorThreads ? (id >> 3) : (id % kBM);
+        const int c = P::kARowMajorThreads ? (id & 7) : (id / kBM);
+        const __half *hi, *lo;
+        const uint32_t bytes = p.a_src(z, m0 + r, k0 + c * 8, hi, lo) ? 16u : 0u;
+        const uint32_t off = umma::sw128_off(r, c);
+        cp_async16(a_hi + off, hi, bytes);
+        if (!P::kAExact) cp_async16(a_lo + off, lo, bytes);
+      }
+    } else if constexpr (P::kAMode == kReg) {
+      constexpr int kCh = kBM * 8 / kThreads;
+      float av[kCh][8];
+#pragma unroll
+      for (int i = 0; i < kCh; ++i) {
+        const int id = tid + i * kThreads;
+        const int r = P::kARowMajorThreads ? (id >> 3) : (id % kBM);
+        const int c = P::kARowMajorThreads ? (id & 7) : (id / kBM);
+        p.a8(z, m0 + r, k0 + c * 8, av[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < kCh; ++i) {
+        const int id = tid + i * kThreads;
+        const int r = P::kARowMajorThreads ? (id >> 3) : (id % kBM);
+        const int c = P::kARowMajorThreads ? (id & 7) : (id / kBM);
+        uint4 hi, lo;
+        umma::split8(av[i], hi, lo);
+        *reinterpret_cast<uint4*>(st_gen + umma::sw128_off(r, c)) = hi;
+        if (!P::kAExact) *reinterpret_cast<uint4*>(st_gen + C::kABytes + umma::sw128_off(r, c)) = lo;
+      }
+    }
+    if constexpr (P::kBMode == kAsync) {
+#pragma unroll
+      for (int i = 0; i < (BN * 8 + kThreads - 1) / kThreads; ++i) {
+        const int id = tid + i * kThreads;
+        if (id < BN * 8) {
+          const int r = P::kBRowMajorThreads ? (id >> 3) : (id % BN);
+          const int c = P::kBRowMajorThreads ? (id & 7) : (id / BN);
+          const __half *hi, *lo;
+          const uint32_t bytes = p.b_src(z, n0 + r, k0 + c * 8, hi, lo) ? 16u : 0u;
+          const uint32_t off = umma::sw128_off(r, c);
+          cp_async16(b_hi + off, hi, bytes);
+          cp_async16(b_lo + off, lo, bytes);
+        }
+      }
+    }
+  };
+
+  // ---- prologue: fill S-1 stages
+#pragma unroll
+  for (int j = 0; j < S - 1; ++j) {
+    if (j < nkb) issue_loads(j);
+    cp_async_commit();
+  }
+
+  for (int it = 0; it < nkb; ++it) {
+    const int s = it % S;
+    cp_async_wait<S - 2>();          // this thread's copies for k-block `it` have landed
+    fence_proxy_async_smem();        // generic/LDGSTS writes -> visible to the tensor core's async proxy
+    __syncthreads();                 // ... for every thread's copies
+    if (tid == 0) {
+      if (kAnyBulk) mbar_wait(&s_full[s], (it / S) & 1);
+      umma::fence_after_sync();
+      const uint32_t sa = smem_base + s * C::kStageBytes;
+      const uint64_t da_hi = umma::make_desc_sw128(sa);
+      const uint64_t da_lo = umma::make_desc_sw128(sa + C::kABytes);
+      const uint64_t db_hi = umma::make_desc_sw128(sa + C::kAStage);
+      const uint64_t db_lo = umma::make_desc_sw128(sa + C::kAStage + C::kBBytes);
+#pragma unroll
+      for (int k = 0; k < kBK / 16; ++k) {
+        const uint32_t acc = (it > 0 || k > 0) ? 1u : 0u;
+        umma::mma_f16(tmem, da_hi + 2 * k, db_hi + 2 * k, idesc, acc);
+        if (!P::kAExact) {
+          umma::mma_f16(tmem + BN, da_lo + 2 * k, db_hi + 2 * k, idesc, acc);
+          umma::mma_f16(tmem + BN, da_hi + 2 * k, db_lo + 2 * k, idesc, 1u);
+        } else {
+          umma::mma_f16(tmem + BN, da_hi + 2 * k, db_lo + 2 * k, idesc, acc);
+        }
+      }
+      umma::mma_commit(&s_empty[s]);
+      if (it == nkb - 1) umma::mma_commit(&s_done);
+    }
+    // refill the stage that k-block it-1 used (its MMAs were issued one iteration ago)
+    const int nxt = it + S - 1;
+    if (nxt < nkb) {
+      if (nxt >= S) mbar_wait(&s_empty[nxt % S], ((nxt / S) - 1) & 1);
+      issue_loads(nxt);
+    }
+    cp_async_commit();
+  }
+
+  // ---- epilogue
+  mbar_wait(&s_done, 0);
+  umma::fence_after_sync();
+  {
+    const int q = warp & 3, half = warp >> 2;
+    const int m = m0 + q * 32 + lane;
+    const uint32_t lane_addr = tmem + (uint32_t(q * 32) << 16);
+    constexpr int kColsPerHalf = BN / 2;
+#pragma unroll
+    for (int c = 0; c < kColsPerHalf; c += 8) {
+      const int col = half * kColsPerHalf + c;
+      float a0[8], a1[8];
+      umma::tmem_ld8(lane_addr + col, a0);
+      umma::tmem_ld8(lane_addr + BN + col, a1);
+      umma::tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a0[j] = fmaf(a1[j], umma::kLoInv, a0[j]);
+      if (m < M && n0 + col < N) p.store8(z, m, n0 + col, a0);
+    }
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) {
+    umma::fence_after_sync();
+    umma::tmem_dealloc(tmem, C::kTmemCols);
+  }
+}
+
+template <class P>
+static int launch_umma2(const char* label, const P& p, int M, int N, int Z, cudaStream_t st) {
+  using C = Cfg2<P>;
+  static bool configured = false;
+  if (!configured) {
+    B2_CHECK_CUDA(cudaFuncSetAttribute(k_umma2<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    configured = true;
+  }
+  dim3 grid((M + kBM - 1) / kBM, (N + C::BN - 1) / C::BN, Z);
+  k_umma2<P><<<grid, kThreads, C::kSmemBytes, st>>>(p);
+  B2_LAUNCH_CHECK();
+  B2_PROF(label, st);
+  return B200DQN_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Tile-image packer: one thread per 16-byte chunk of the image.
+// Source S: int tiles(), rows(), kblocks(); void src8(tile, row, k0, float v[8]) (zeros when out of range)
+// image layout: [tile][kb][hi rows*128 B | lo rows*128 B], chunk (r, c) at sw128_off(r, c).
+// ------------------------------------------------------------------------------------------
+template <class S>
+__global__ void __launch_bounds__(256) k_pack_image(const S src, uint8_t* __restrict__ image) {
+  const int rows = src.rows(), nkb = src.kblocks();
+  const int64_t chunks_per_tile_kb = int64_t(rows) * 8;
+  const int64_t total = int64_t(src.tiles()) * nkb * chunks_per_tile_kb;
+  const int64_t id = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (id >= total) return;
+  const int64_t tk = id / chunks_per_tile_kb;
+  const int within = int(id % chunks_per_tile_kb);
+  const int tile = int(tk / nkb), kb = int(tk % nkb);
+  const int r = S::kRowMajorThreads ? (within >> 3) : (within % rows);
+  const int c = S::kRowMajorThreads ? (within & 7) : (within / rows);
+  float v[8];
+  src.src8(tile, r, kb * kBK + c * 8, v);
+  uint4 hi, lo;
+  umma::split8(v, hi, lo);
+  uint8_t* base = image + tk * (int64_t(rows) * 256);
+  *reinterpret_cast<uint4*>(base + umma::sw128_off(r, c)) = hi;
+  *reinterpret_cast<uint4*>(base + int64_t(rows) * 128 + umma::sw128_off(r, c)) = lo;
+}
+
+template <class S>
+static int launch_pack(const char* label, const S& src, uint8_t* image, cudaStream_t st) {
+  const int64_t total = int64_t(src.tiles()) * src.kblocks() * src.rows() * 8;
+  k_pack_image<S><<<unsigned((total + 255) / 256), 256, 0, st>>>(src, image);
+  B2_LAUNCH_CHECK();
+  B2_PROF(label, st);
+  return B200DQN_OK;
+}
+
+}  // namespace umma2
+}  // namespace b200
