@@ -33,9 +33,10 @@ struct HeadTrainArgs {
   float* delta;       // [rows][A]
   float* cost_ring;
   uint32_t* step;
-  uint32_t* ticket;
+  uint32_t* ticket;   // [rows + 1]: per-row pair tickets, then the all-rows ticket
+  float* row_cost;    // [rows]
   float* dz4;         // [rows][512]
-  float* dw5;         // [512][A]
+  float* dw5_rows;    // [rows][512][A] per-row partials of dW5 (summed in row order by the optimizer)
   __half* dz4_hi;     // fp16 hi / scaled-lo planes of dZ4 for the tcgen05 dgrad (nullptr in fp32 mode)
   int64_t dz4_lo_off;
 };
@@ -67,60 +68,61 @@ k_head(const float* __restrict__ part, int splits, int rows, float* h4_online, f
   }
   if (!td.enable) return;
 
-  // ---- last CTA standing does the (tiny) TD + fc2 backward
+  // ---- the second CTA of the (online, target) pair of row b to get here owns that row's TD + fc2 backward
   __threadfence();
   __syncthreads();
-  if (t == 0) s_last = (atomicAdd(td.ticket, 1u) == gridDim.x * gridDim.y - 1) ? 1 : 0;
+  if (t == 0) s_last = (atomicAdd(td.ticket + b, 1u) == gridDim.y - 1) ? 1 : 0;
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  float c = 0.f;
-  for (int bb = t; bb < rows; bb += kHidden) {
-    const int64_t mi = td.midx[bb];
+  __shared__ float s_d;
+  __shared__ int s_a;
+  if (t == 0) {
+    const int64_t mi = td.midx[b];
     const int a = td.actions[mi];
     int64_t r = td.rewards[mi];
     r = r < td.min_reward ? td.min_reward : (r > td.max_reward ? td.max_reward : r);     // np.clip (:136)
-    float maxq = __ldcg(q_target + bb * A);
-    for (int j = 1; j < A; ++j) maxq = fmaxf(maxq, __ldcg(q_target + bb * A + j));       // be.max(postq) (:124)
+    float maxq = __ldcg(q_target + b * A);
+    for (int j = 1; j < A; ++j) maxq = fmaxf(maxq, __ldcg(q_target + b * A + j));        // be.max(postq) (:124)
     const double y = td.terminals[mi] ? double(r) : double(r) + td.discount * double(maxq);  // :140-143
     const float target = static_cast<float>(y);
-    float d = __ldcg(q_online + bb * A + a) - target;                                     // SumSquared grad (:149)
-    c += 0.5f * d * d;                                                                    // :154, before the clip
+    float d = __ldcg(q_online + b * A + a) - target;                                      // SumSquared grad (:149)
+    td.row_cost[b] = 0.5f * d * d;                                                        // :154, before the clip
     if (td.clip > 0.f) d = fminf(fmaxf(d, -td.clip), td.clip);                            // :158-159
-    for (int j = 0; j < A; ++j) td.delta[bb * A + j] = (j == a) ? d : 0.f;
+    for (int j = 0; j < A; ++j) td.delta[b * A + j] = (j == a) ? d : 0.f;
+    s_d = d;
+    s_a = a;
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-  if ((t & 31) == 0) red[t >> 5][0] = c;
-  __syncthreads();   // also orders the delta[] writes before the reads below (same CTA)
+  __syncthreads();
+  {
+    const float d = s_d;
+    const int a = s_a;
+    const float hv = __ldcg(h4_online + b * kHidden + t);
+    const float o = hv > 0.f ? d * w5_online[t * A + a] : 0.f;      // delta is non-zero only at the taken action
+    td.dz4[b * kHidden + t] = o;
+    if (td.dz4_hi) {
+      const __half hh = __float2half_rn(o);
+      td.dz4_hi[b * kHidden + t] = hh;
+      td.dz4_hi[td.dz4_lo_off + b * kHidden + t] = __float2half_rn((o - __half2float(hh)) * 2048.0f);
+    }
+    float* dw = td.dw5_rows + (int64_t(b) * kHidden + t) * A;        // per-row partial, summed by the optimizer
+    for (int j = 0; j < A; ++j) dw[j] = (j == a) ? hv * d : 0.f;
+  }
+  // ---- the last row to finish publishes the batch-mean cost and re-arms the tickets
+  __threadfence();
+  __syncthreads();
+  if (t == 0) s_last = (atomicAdd(td.ticket + rows, 1u) == uint32_t(rows) - 1) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
   if (t == 0) {
     float tot = 0.f;
-    for (int wI = 0; wI < kHidden / 32; ++wI) tot += red[wI][0];
+    for (int bb = 0; bb < rows; ++bb) tot += __ldcg(td.row_cost + bb);
     const uint32_t sidx = *td.step;
     td.cost_ring[sidx % kCostRing] = tot / float(rows);
     *td.step = sidx + 1;
-    *td.ticket = 0;   // re-arm for the next launch
   }
-  float dw[kMaxActions];
-#pragma unroll
-  for (int a = 0; a < kMaxActions; ++a) dw[a] = 0.f;
-  for (int bb = 0; bb < rows; ++bb) {
-    const float hv = __ldcg(h4_online + bb * kHidden + t);
-    float v = 0.f;
-    for (int a = 0; a < A; ++a) {
-      const float d = td.delta[bb * A + a];
-      v = fmaf(d, w5_online[t * A + a], v);
-      dw[a] = fmaf(hv, d, dw[a]);
-    }
-    const float o = hv > 0.f ? v : 0.f;
-    td.dz4[bb * kHidden + t] = o;
-    if (td.dz4_hi) {
-      const __half h = __float2half_rn(o);
-      td.dz4_hi[bb * kHidden + t] = h;
-      td.dz4_hi[td.dz4_lo_off + bb * kHidden + t] = __float2half_rn((o - __half2float(h)) * 2048.0f);
-    }
-  }
-  for (int a = 0; a < A; ++a) td.dw5[t * A + a] = dw[a];
+  for (int i = t; i <= rows; i += kHidden) td.ticket[i] = 0;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -390,7 +392,7 @@ static int train_step(b200dqn_net* n, const FrameSource& fs, const uint8_t* acti
                       const uint8_t* terminals, const int32_t* midx, cudaStream_t st) {
   const int rows = n->nb;
   HeadTrainArgs td{1, actions, rewards, terminals, midx, n->cfg.discount_rate, n->cfg.min_reward, n->cfg.max_reward,
-                   float(n->cfg.clip_error), n->d_delta, n->d_cost, n->d_step, n->d_ticket, n->d_dz4,
+                   float(n->cfg.clip_error), n->d_delta, n->d_cost, n->d_step, n->d_ticket, n->d_rowcost, n->d_dz4,
                    n->d_part + n->lt.part_off[4], nullptr, 0};
   umma_dz4_planes(n, &td.dz4_hi, &td.dz4_lo_off);
   B2_TRY(forward(n, fs, 2, rows, st, td));
@@ -481,7 +483,9 @@ extern "C" int b200dqn_net_create(int device, const b200dqn_net_config* cfg, b20
   const int base[3] = {512, 96, 112};
   int64_t po = 0;
   for (int l = 0; l < kLayers; ++l) {
-    if (cfg->math_mode == B200DQN_MATH_TCGEN05)
+    if (l == 4)
+      lt.splits[l] = nb;   // the head kernel leaves one dW5 partial per sample
+    else if (cfg->math_mode == B200DQN_MATH_TCGEN05)
       lt.splits[l] = l < 3 ? umma_wgrad_splits(l, nb) : 1;
     else
       lt.splits[l] = l < 3 ? int(cdiv(kred[l], wgrad_chunk(kred[l], base[l]))) : 1;
@@ -522,8 +526,9 @@ extern "C" int b200dqn_net_create(int device, const b200dqn_net_config* cfg, b20
   B2_CHECK_CUDA(fmalloc(&n->d_cost, kCostRing));
   B2_CHECK_CUDA(cudaMalloc(&n->d_step, sizeof(uint32_t)));
   B2_CHECK_CUDA(cudaMemset(n->d_step, 0, sizeof(uint32_t)));
-  B2_CHECK_CUDA(cudaMalloc(&n->d_ticket, sizeof(uint32_t)));
-  B2_CHECK_CUDA(cudaMemset(n->d_ticket, 0, sizeof(uint32_t)));
+  B2_CHECK_CUDA(cudaMalloc(&n->d_ticket, (nb + 1) * sizeof(uint32_t)));
+  B2_CHECK_CUDA(cudaMemset(n->d_ticket, 0, (nb + 1) * sizeof(uint32_t)));
+  B2_CHECK_CUDA(fmalloc(&n->d_rowcost, nb));
   const size_t state_bytes = size_t(nb) * kHist * kFrameBytes;
   B2_CHECK_CUDA(cudaMalloc(&n->d_pre, state_bytes + 256));
   B2_CHECK_CUDA(cudaMalloc(&n->d_post, state_bytes + 256));
@@ -562,7 +567,7 @@ extern "C" int b200dqn_net_destroy(b200dqn_net* n) {
     cudaFree(n->d_h1[z]); cudaFree(n->d_h2[z]); cudaFree(n->d_h3[z]); cudaFree(n->d_h4[z]); cudaFree(n->d_q[z]);
   }
   cudaFree(n->d_fc1part); cudaFree(n->d_delta); cudaFree(n->d_dz4); cudaFree(n->d_dz3); cudaFree(n->d_dz2);
-  cudaFree(n->d_dz1); cudaFree(n->d_cost); cudaFree(n->d_step); cudaFree(n->d_ticket); cudaFree(n->d_pre); cudaFree(n->d_post);
+  cudaFree(n->d_dz1); cudaFree(n->d_cost); cudaFree(n->d_step); cudaFree(n->d_ticket); cudaFree(n->d_rowcost); cudaFree(n->d_pre); cudaFree(n->d_post);
   cudaFree(n->d_act); cudaFree(n->d_term); cudaFree(n->d_rew); cudaFree(n->d_iota1); cudaFree(n->d_iota4);
   cudaFreeHost(n->h_pin);
   delete n;

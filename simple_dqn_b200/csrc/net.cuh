@@ -47,7 +47,8 @@ struct b200dqn_net {
   float* d_dz4 = nullptr, *d_dz3 = nullptr, *d_dz2 = nullptr, *d_dz1 = nullptr;
   float* d_cost = nullptr;     // cost ring [kCostRing]
   uint32_t* d_step = nullptr;  // device step counter (cost ring cursor)
-  uint32_t* d_ticket = nullptr;  // last-CTA-standing counter of the head kernel
+  uint32_t* d_ticket = nullptr;  // [nb + 1] tickets of the head kernel
+  float* d_rowcost = nullptr;    // [nb] per-sample cost
 
   // unfused-mode staging (host minibatch -> device)
   uint8_t* d_pre = nullptr, *d_post = nullptr, *d_act = nullptr, *d_term = nullptr;

@@ -386,14 +386,14 @@ struct V2ConvFwd {
   __device__ int M(int) const { return rows * P * P; }
   __device__ int N(int) const { return KO; }
   __device__ void krange(int, int& kb, int& ke) const { kb = 0; ke = K / 64; }
-  __device__ bool a_src(int z, int m, int k0, const __half*& hi, const __half*& lo) const {
-    const PlanePair& pl = z ? in16[1] : in16[0];
-    hi = pl.hi; lo = pl.hi + pl.lo_off;
-    if (m >= rows * P * P) return false;
+  __device__ umma2::Planes a_planes(int z) const { return {z ? in16[1].hi : in16[0].hi, in16[0].lo_off}; }
+  __device__ umma2::RowCtx a_row(int, int m) const {
     const int n = m / (P * P), pq = m % (P * P), p = pq / P, q = pq % P;
-    const int r = k0 / (R * C), sc = k0 % (R * C);
-    const int64_t off = (int64_t(n * H + p * ST + r) * H + q * ST) * C + sc;
-    hi += off; lo += off;
+    return {(int64_t(n * H + p * ST) * H + q * ST) * C, 0, 0, m < rows * P * P};
+  }
+  __device__ bool a_chunk(int, const umma2::RowCtx& rc, int kk, int64_t& off) const {
+    const int r = kk / (R * C), sc = kk % (R * C);
+    off = rc.base + r * (H * C) + sc;
     return true;
   }
   __device__ const uint8_t* b_tile(int z, int, int kb) const { return (z ? wimg[1] : wimg[0]) + kb * (KO * 256); }
@@ -423,11 +423,10 @@ struct V2Fc1Fwd {
   __device__ const uint8_t* a_tile(int z, int mtile, int kb) const {
     return ((z / splits) ? wimg[1] : wimg[0]) + (int64_t(mtile) * (kFlat / 64) + kb) * (128 * 256);
   }
-  __device__ bool b_src(int z, int n, int k0, const __half*& hi, const __half*& lo) const {
-    const PlanePair& pl = (z / splits) ? in16[1] : in16[0];
-    hi = pl.hi; lo = pl.hi + pl.lo_off;
-    if (n >= rows) return false;
-    hi += int64_t(n) * kFlat + k0; lo += int64_t(n) * kFlat + k0;
+  __device__ umma2::Planes b_planes(int z) const { return {(z / splits) ? in16[1].hi : in16[0].hi, in16[0].lo_off}; }
+  __device__ umma2::RowCtx b_row(int, int n) const { return {int64_t(n) * kFlat, 0, 0, n < rows}; }
+  __device__ bool b_chunk(int, const umma2::RowCtx& rc, int kk, int64_t& off) const {
+    off = rc.base + kk;
     return true;
   }
   __device__ void store8(int z, int m, int n0, const float v[8]) const {
@@ -454,10 +453,10 @@ struct V2Fc1Dgrad {
   __device__ const uint8_t* a_tile(int, int mtile, int kb) const {
     return wimg + (int64_t(mtile) * (kHidden / 64) + kb) * (128 * 256);
   }
-  __device__ bool b_src(int, int n, int k0, const __half*& hi, const __half*& lo) const {
-    hi = dz4.hi; lo = dz4.hi + dz4.lo_off;
-    if (n >= rows) return false;
-    hi += int64_t(n) * kHidden + k0; lo += int64_t(n) * kHidden + k0;
+  __device__ umma2::Planes b_planes(int) const { return {dz4.hi, dz4.lo_off}; }
+  __device__ umma2::RowCtx b_row(int, int n) const { return {int64_t(n) * kHidden, 0, 0, n < rows}; }
+  __device__ bool b_chunk(int, const umma2::RowCtx& rc, int kk, int64_t& off) const {
+    off = rc.base + kk;
     return true;
   }
   __device__ void store8(int, int m, int n0, const float v[8]) const {
@@ -491,17 +490,17 @@ struct V2ConvDgrad {
   __device__ int M(int) const { return rows * HC * HC; }
   __device__ int N(int) const { return C; }
   __device__ void krange(int, int& kb, int& ke) const { kb = 0; ke = K / 64; }
-  __device__ bool a_src(int z, int m, int k0, const __half*& hi, const __half*& lo) const {
-    hi = dz.hi; lo = dz.hi + dz.lo_off;
-    if (m >= rows * HC * HC) return false;
+  __device__ umma2::Planes a_planes(int) const { return {dz.hi, dz.lo_off}; }
+  __device__ umma2::RowCtx a_row(int z, int m) const {
     const int n = m / (HC * HC), yx = m % (HC * HC), yy = yx / HC, xx = yx % HC;
-    const int rp = k0 / (RT * KO), sp = (k0 / KO) % RT, ko = k0 % KO;
-    if (yy * ST + z / ST >= H || xx * ST + z % ST >= H) return false;
-    const int p = yy - rp, q = xx - sp;
-    if (p < 0 || p >= P || q < 0 || q >= P) return false;
-    const int64_t off = (int64_t(n * P + p) * P + q) * KO + ko;
-    hi += off; lo += off;
-    return true;
+    const bool ok = m < rows * HC * HC && yy * ST + z / ST < H && xx * ST + z % ST < H;
+    return {(int64_t(n * P + yy) * P + xx) * KO, yy, xx, ok};
+  }
+  __device__ bool a_chunk(int, const umma2::RowCtx& rc, int kk, int64_t& off) const {
+    const int rp = kk / (RT * KO), sp = (kk / KO) % RT, ko = kk % KO;
+    const int p = rc.y - rp, q = rc.x - sp;
+    off = rc.base - (rp * P + sp) * KO + ko;
+    return p >= 0 && p < P && q >= 0 && q < P;
   }
   __device__ const uint8_t* b_tile(int z, int, int kb) const { return wimg + (int64_t(z) * (K / 64) + kb) * (C * 256); }
   __device__ void store8(int z, int m, int c0, const float v[8]) const {

@@ -23,6 +23,16 @@ using umma::kThreads;
 
 enum OperandMode { kReg = 0, kAsync = 1, kBulk = 2 };
 
+struct RowCtx {      // per-row part of a gather address, computed once outside the k loop
+  int64_t base;      // element offset
+  int y, x;          // problem-specific (e.g. pixel coordinates for boundary tests)
+  bool ok;           // row inside the problem
+};
+struct Planes {
+  const __half* hi;
+  int64_t lo_off;    // lo plane = hi + lo_off
+};
+
 __device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gsrc, uint32_t src_bytes) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(src_bytes) : "memory");
 }
@@ -55,8 +65,10 @@ __device__ __forceinline__ void split8_planes(const float v[8], __half* hi_dst, 
 //   static constexpr bool kARowMajorThreads, kBRowMajorThreads;  (thread -> chunk mapping, as in umma.cuh)
 //   int M(z), N(z); void krange(z, kb0, kb1);
 //   kReg  : void a8(z, m, k0, float v[8])                                   (A only)
-//   kAsync: bool a_src(z, m, k0, const __half*& hi, const __half*& lo)      false -> zero fill
-//           bool b_src(z, n, k0, const __half*& hi, const __half*& lo)
+//   kAsync: RowCtx a_row(z, m)  — once per (thread, tile row): everything that depends on the row only
+//           bool   a_chunk(z, row, kk, int64_t& off) — per k-block: element offset of the 8-wide chunk
+//                  starting at k index kk; false -> zero fill.   PlanePair-like a_planes(z) -> (hi, lo_off)
+//           same with b_row / b_chunk / b_planes for B
 //   kBulk : const uint8_t* a_tile(z, mtile, kb) / b_tile(z, ntile, kb)      -> [hi image | lo image]
 //   void store8(z, m, n0, const float v[8])
 template <class P>
@@ -115,6 +127,29 @@ __global__ void __launch_bounds__(kThreads, 1) k_umma2(const P p) {
   constexpr bool kAnyBulk = (P::kAMode == kBulk) || (P::kBMode == kBulk);
   constexpr uint32_t kBulkBytes = (P::kAMode == kBulk ? 2 * C::kABytes : 0) + (P::kBMode == kBulk ? 2 * C::kBBytes : 0);
 
+  // ---- per-thread gather context: the tile rows this thread copies never change over the k loop
+  constexpr int kACh = kBM * 8 / kThreads;
+  constexpr int kBCh = (BN * 8 + kThreads - 1) / kThreads;
+  RowCtx arow[kACh];
+  RowCtx brow[kBCh];
+  Planes apl{nullptr, 0}, bpl{nullptr, 0};
+  if constexpr (P::kAMode == kAsync) {
+    apl = p.a_planes(z);
+#pragma unroll
+    for (int i = 0; i < kACh; ++i) {
+      const int id = tid + i * kThreads;
+      arow[i] = p.a_row(z, m0 + (P::kARowMajorThreads ? (id >> 3) : (id % kBM)));
+    }
+  }
+  if constexpr (P::kBMode == kAsync) {
+    bpl = p.b_planes(z);
+#pragma unroll
+    for (int i = 0; i < kBCh; ++i) {
+      const int id = tid + i * kThreads;
+      brow[i] = p.b_row(z, n0 + (P::kBRowMajorThreads ? (id >> 3) : (id % BN)));
+    }
+  }
+
   // ---- producer: everything needed for k-block (kb0 + j) goes into stage j % S
   auto issue_loads = [&](int j) {
     const int s = j % S, kb = kb0 + j, k0 = kb * kBK;
@@ -134,11 +169,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_umma2(const P p) {
         const int id = tid + i * kThreads;
         const int r = P::kARowMajorThreads ? (id >> 3) : (id % kBM);
         const int c = P::kARowMajorThreads ? (id & 7) : (id / kBM);
-        const __half *hi, *lo;
-        const uint32_t bytes = p.a_src(z, m0 + r, k0 + c * 8, hi, lo) ? 16u : 0u;
+        int64_t eoff = 0;
+        const bool ok = arow[i].ok && p.a_chunk(z, arow[i], k0 + c * 8, eoff);
+        const uint32_t bytes = ok ? 16u : 0u;
+        const __half* hi = apl.hi + (ok ? eoff : 0);
         const uint32_t off = umma::sw128_off(r, c);
         cp_async16(a_hi + off, hi, bytes);
-        if (!P::kAExact) cp_async16(a_lo + off, lo, bytes);
+        if (!P::kAExact) cp_async16(a_lo + off, hi + apl.lo_off, bytes);
       }
     } else if constexpr (P::kAMode == kReg) {
       constexpr int kCh = kBM * 8 / kThreads;
@@ -168,26 +205,30 @@ __global__ void __launch_bounds__(kThreads, 1) k_umma2(const P p) {
         if (id < BN * 8) {
           const int r = P::kBRowMajorThreads ? (id >> 3) : (id % BN);
           const int c = P::kBRowMajorThreads ? (id & 7) : (id / BN);
-          const __half *hi, *lo;
-          const uint32_t bytes = p.b_src(z, n0 + r, k0 + c * 8, hi, lo) ? 16u : 0u;
+          int64_t eoff = 0;
+          const bool ok = brow[i].ok && p.b_chunk(z, brow[i], k0 + c * 8, eoff);
+          const uint32_t bytes = ok ? 16u : 0u;
+          const __half* hi = bpl.hi + (ok ? eoff : 0);
           const uint32_t off = umma::sw128_off(r, c);
           cp_async16(b_hi + off, hi, bytes);
-          cp_async16(b_lo + off, lo, bytes);
+          cp_async16(b_lo + off, hi + bpl.lo_off, bytes);
         }
       }
     }
   };
 
-  // ---- prologue: fill S-1 stages
+  // ---- prologue: loads run PF k-blocks ahead of the tensor core; the stage being refilled was
+  // read by the MMAs issued S - PF iterations ago, so the wait on its "empty" barrier is normally free.
+  constexpr int PF = S - 2;
 #pragma unroll
-  for (int j = 0; j < S - 1; ++j) {
+  for (int j = 0; j < PF; ++j) {
     if (j < nkb) issue_loads(j);
     cp_async_commit();
   }
 
   for (int it = 0; it < nkb; ++it) {
     const int s = it % S;
-    cp_async_wait<S - 2>();          // this thread's copies for k-block `it` have landed
+    cp_async_wait<PF - 1>();         // this thread's copies for k-block `it` have landed
     fence_proxy_async_smem();        // generic/LDGSTS writes -> visible to the tensor core's async proxy
     __syncthreads();                 // ... for every thread's copies
     if (tid == 0) {
@@ -212,8 +253,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_umma2(const P p) {
       umma::mma_commit(&s_empty[s]);
       if (it == nkb - 1) umma::mma_commit(&s_done);
     }
-    // refill the stage that k-block it-1 used (its MMAs were issued one iteration ago)
-    const int nxt = it + S - 1;
+    // refill the stage that k-block it-2 used (its MMAs were issued two iterations ago)
+    const int nxt = it + PF;
     if (nxt < nkb) {
       if (nxt >= S) mbar_wait(&s_empty[nxt % S], ((nxt / S) - 1) & 1);
       issue_loads(nxt);
