@@ -233,6 +233,10 @@ int b200dqn_net_get_grads(b200dqn_net* n, int layer, float* host_dW, void* strea
 /* Number of kernels one fused train step launches (bench.py's gpu_launches). */
 int b200dqn_net_launches_per_step(const b200dqn_net* n, int* launches);
 
+/* Developer aid: clock64() stamps written by CTA (0,0,0) of the tcgen05 kernel whose label equals
+ * $B200DQN_TRACE_LABEL (slots documented in csrc/umma2.cuh).  Returns the number of slots or -1. */
+int b200dqn_debug_trace(unsigned long long* host_out, int n);
+
 /* ------------------------------------------------------------------ multi-GPU ----------- */
 
 /* Data-parallel learners with replicated replay (new capability, no reference

@@ -85,6 +85,7 @@ SIGNATURES = {
     "b200dqn_net_device_ptr": [_P, C.c_int, C.POINTER(_P), C.POINTER(C.c_size_t)],
     "b200dqn_net_get_grads": [_P, C.c_int, _P, _P],
     "b200dqn_net_launches_per_step": [_P, C.POINTER(C.c_int)],
+    "b200dqn_debug_trace": [_P, C.c_int],
     "b200dqn_comm_unique_id": [_P],
     "b200dqn_net_comm_init": [_P, _P, C.c_int, C.c_int],
     "b200dqn_net_comm_destroy": [_P],
@@ -114,6 +115,13 @@ def load():
         fn.restype = C.c_int
     _lib = lib
     return lib
+
+
+def debug_trace(n=96):
+    import numpy as np
+    out = np.zeros(n, dtype=np.uint64)
+    got = load().b200dqn_debug_trace(np_ptr(out), n)
+    return out[:max(got, 0)]
 
 
 def check(rc):

@@ -781,3 +781,8 @@ int umma_forward_launches() { return 4; }
 int umma_backward_launches() { return 7; }
 
 }  // namespace b200
+
+extern "C" int b200dqn_debug_trace(unsigned long long* host_out, int n) {
+  cudaDeviceSynchronize();
+  return b200::umma2::read_trace(host_out, n);
+}

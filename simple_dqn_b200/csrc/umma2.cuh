@@ -12,6 +12,8 @@
 // 4-stage ring: loads for k-block i+3 are in flight while the tensor core works on k-block i.
 // Accumulation scheme (3 MMAs / k-step, fp32 in TMEM) as in umma.cuh.
 #pragma once
+#include <stdlib.h>
+
 #include "umma.cuh"
 
 namespace b200 {
@@ -42,21 +44,17 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-// fp32 -> (hi, lo') with the "positive stays positive" rule: a strictly positive value whose fp16
-// rounding is 0 keeps the smallest subnormal in hi, so (hi > 0) is exactly the Rectlin mask.
+// fp32 -> fp16 hi + scaled fp16 lo (Rectlin masks are taken from the fp32 tensors, never from hi)
 __device__ __forceinline__ void split1(float x, __half& hi, __half& lo) {
-  __half h = __float2half_rn(x);
-  if (x > 0.f && __half_as_ushort(h) == 0) h = __ushort_as_half(1);
+  const __half h = __float2half_rn(x);
   hi = h;
   lo = __float2half_rn((x - __half2float(h)) * umma::kLoScale);
 }
 __device__ __forceinline__ void split8_planes(const float v[8], __half* hi_dst, __half* lo_dst) {
-  __align__(16) __half h[8];
-  __align__(16) __half l[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) split1(v[j], h[j], l[j]);
-  *reinterpret_cast<uint4*>(hi_dst) = *reinterpret_cast<const uint4*>(h);
-  *reinterpret_cast<uint4*>(lo_dst) = *reinterpret_cast<const uint4*>(l);
+  uint4 hi, lo;
+  umma::split8(v, hi, lo);
+  *reinterpret_cast<uint4*>(hi_dst) = hi;
+  *reinterpret_cast<uint4*>(lo_dst) = lo;
 }
 
 // Problem P (see net_umma.cu):
@@ -84,21 +82,48 @@ struct Cfg2 {
                                         : (2 * BN <= 256) ? 256 : 512;
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N for M=128 must be a multiple of 16 in [16,256]");
   static_assert(!(P::kAMode == kBulk && P::kAExact), "bulk A images always carry hi+lo");
+  static_assert(2 * BN <= 256, "[B_hi ; B_lo] is issued as one N = 2*BN MMA");
 };
 
+// Debug timeline (B200DQN_TRACE_LABEL=<kernel label>): the MMA thread and loader thread 0 of CTA
+// (0,0,0) of the selected kernel stamp clock64() at pipeline events; read with b200dqn_debug_trace().
+constexpr int kTraceSlots = 96;
+__device__ unsigned long long g_trace[kTraceSlots];
+#define B2_TRACE(cond, slot)                                                      \
+  do {                                                                            \
+    if (trace && (cond) && (slot) < kTraceSlots) g_trace[(slot)] = clock64();     \
+  } while (0)
+
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+constexpr int kLoadThreads = 256;            // warps 0..7: operand staging, then the epilogue
+constexpr int kThreads2 = kLoadThreads + 32; // warp 8: MMA issuer
+
+// Warp-specialised pipeline, no CTA-wide barrier inside the k loop:
+//   loaders : for each k-block j: wait empty[j % S] (the MMAs that read that stage S k-blocks ago are
+//             done), issue cp.async / TMA bulk / st.shared for stage j % S, and arrive on full[j % S]
+//             (cp.async.mbarrier.arrive.noinc: the arrive fires when this thread's copies have landed)
+//   MMA warp: wait full[s]; fence.proxy.async (generic-proxy smem writes -> async proxy); issue
+//             2 MMAs per k-step:  [acc0 | acc1] += A_hi x [B_hi ; B_lo]   (one N = 2*BN instruction:
+//             the hi and lo weight tiles are adjacent in shared memory)  and  acc1 += A_lo x B_hi;
+//             tcgen05.commit -> empty[s]
 template <class P>
-__global__ void __launch_bounds__(kThreads, 1) k_umma2(const P p) {
+__global__ void __launch_bounds__(kThreads2, 1) k_umma2(const P p, const int trace_in) {
   using C = Cfg2<P>;
   constexpr int BN = C::BN;
   constexpr int S = C::kStages;
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint32_t s_tmem;
-  __shared__ __align__(8) uint64_t s_full[S];    // TMA bulk tiles landed
+  __shared__ __align__(8) uint64_t s_full[S];    // operands of the stage have landed
   __shared__ __align__(8) uint64_t s_empty[S];   // MMAs reading the stage completed
   __shared__ __align__(8) uint64_t s_done;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int z = blockIdx.z;
+  const bool trace = trace_in && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+  B2_TRACE(tid == 0, 0);
   const int M = p.M(z), N = p.N(z);
   const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * BN;
   if (m0 >= M || n0 >= N) return;
@@ -108,12 +133,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_umma2(const P p) {
 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  constexpr bool kAnyBulk = (P::kAMode == kBulk) || (P::kBMode == kBulk);
+  constexpr uint32_t kBulkBytes = (P::kAMode == kBulk ? 2 * C::kABytes : 0) + (P::kBMode == kBulk ? 2 * C::kBBytes : 0);
 
-  if (warp == 0) umma::tmem_alloc(&s_tmem, C::kTmemCols);
+  if (warp == 8) umma::tmem_alloc(&s_tmem, C::kTmemCols);
   if (tid == 32) {
 #pragma unroll
     for (int s = 0; s < S; ++s) {
-      mbar_init(&s_full[s], 1);
+      mbar_init(&s_full[s], kLoadThreads + (kAnyBulk ? 1 : 0));
       mbar_init(&s_empty[s], 1);
     }
     mbar_init(&s_done, 1);
@@ -122,172 +149,171 @@ __global__ void __launch_bounds__(kThreads, 1) k_umma2(const P p) {
   umma::fence_before_sync();
   __syncthreads();
   umma::fence_after_sync();
+  B2_TRACE(tid == 0, 1);
   const uint32_t tmem = s_tmem;
-  constexpr uint32_t idesc = umma::make_idesc_f16(kBM, BN);
-  constexpr bool kAnyBulk = (P::kAMode == kBulk) || (P::kBMode == kBulk);
-  constexpr uint32_t kBulkBytes = (P::kAMode == kBulk ? 2 * C::kABytes : 0) + (P::kBMode == kBulk ? 2 * C::kBBytes : 0);
 
-  // ---- per-thread gather context: the tile rows this thread copies never change over the k loop
-  constexpr int kACh = kBM * 8 / kThreads;
-  constexpr int kBCh = (BN * 8 + kThreads - 1) / kThreads;
-  RowCtx arow[kACh];
-  RowCtx brow[kBCh];
-  Planes apl{nullptr, 0}, bpl{nullptr, 0};
-  if constexpr (P::kAMode == kAsync) {
-    apl = p.a_planes(z);
+  if (warp == 8) {
+    // ================================================================ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc1 = umma::make_idesc_f16(kBM, BN);
+      constexpr uint32_t idesc2 = umma::make_idesc_f16(kBM, 2 * BN);
+      for (int it = 0; it < nkb; ++it) {
+        const int s = it % S;
+        mbar_wait(&s_full[s], (it / S) & 1);
+        fence_proxy_async_smem();
+        umma::fence_after_sync();
+        B2_TRACE(true, 8 + it * 4 + 0);
+        const uint32_t sa = smem_base + s * C::kStageBytes;
+        const uint64_t da_hi = umma::make_desc_sw128(sa);
+        const uint64_t da_lo = umma::make_desc_sw128(sa + C::kABytes);
+        const uint64_t db = umma::make_desc_sw128(sa + C::kAStage);   // [B_hi ; B_lo], 2*BN rows
 #pragma unroll
-    for (int i = 0; i < kACh; ++i) {
-      const int id = tid + i * kThreads;
-      arow[i] = p.a_row(z, m0 + (P::kARowMajorThreads ? (id >> 3) : (id % kBM)));
+        for (int k = 0; k < kBK / 16; ++k) {
+          umma::mma_f16(tmem, da_hi + 2 * k, db + 2 * k, idesc2, (it > 0 || k > 0) ? 1u : 0u);
+          if (!P::kAExact) umma::mma_f16(tmem + BN, da_lo + 2 * k, db + 2 * k, idesc1, 1u);
+        }
+        umma::mma_commit(&s_empty[s]);
+        if (it == nkb - 1) umma::mma_commit(&s_done);
+        B2_TRACE(true, 8 + it * 4 + 1);
+      }
     }
-  }
-  if constexpr (P::kBMode == kAsync) {
-    bpl = p.b_planes(z);
-#pragma unroll
-    for (int i = 0; i < kBCh; ++i) {
-      const int id = tid + i * kThreads;
-      brow[i] = p.b_row(z, n0 + (P::kBRowMajorThreads ? (id >> 3) : (id % BN)));
-    }
-  }
-
-  // ---- producer: everything needed for k-block (kb0 + j) goes into stage j % S
-  auto issue_loads = [&](int j) {
-    const int s = j % S, kb = kb0 + j, k0 = kb * kBK;
-    const uint32_t st_addr = smem_base + s * C::kStageBytes;
-    uint8_t* st_gen = smem_gen + s * C::kStageBytes;
-    const uint32_t a_hi = st_addr, a_lo = st_addr + C::kABytes, b_hi = st_addr + C::kAStage, b_lo = b_hi + C::kBBytes;
-    if (kAnyBulk && tid == 0) {
-      mbar_arrive_expect_tx(&s_full[s], kBulkBytes);
-      if constexpr (P::kAMode == kBulk)
-        tma_bulk_g2s(st_gen, p.a_tile(z, blockIdx.x, kb), 2 * C::kABytes, &s_full[s]);
-      if constexpr (P::kBMode == kBulk)
-        tma_bulk_g2s(st_gen + C::kAStage, p.b_tile(z, blockIdx.y, kb), 2 * C::kBBytes, &s_full[s]);
-    }
+  } else {
+    // ================================================================ loaders
+    constexpr int kACh = kBM * 8 / kLoadThreads;
+    constexpr int kBCh = (BN * 8 + kLoadThreads - 1) / kLoadThreads;
+    RowCtx arow[kACh];
+    RowCtx brow[kBCh];
+    Planes apl{nullptr, 0}, bpl{nullptr, 0};
     if constexpr (P::kAMode == kAsync) {
+      apl = p.a_planes(z);
 #pragma unroll
-      for (int i = 0; i < kBM * 8 / kThreads; ++i) {
-        const int id = tid + i * kThreads;
-        const int r = P::kARowMajorThreads ? (id >> 3) : (id % kBM);
-        const int c = P::kARowMajorThreads ? (id & 7) : (id / kBM);
-        int64_t eoff = 0;
-        const bool ok = arow[i].ok && p.a_chunk(z, arow[i], k0 + c * 8, eoff);
-        const uint32_t bytes = ok ? 16u : 0u;
-        const __half* hi = apl.hi + (ok ? eoff : 0);
-        const uint32_t off = umma::sw128_off(r, c);
-        cp_async16(a_hi + off, hi, bytes);
-        if (!P::kAExact) cp_async16(a_lo + off, hi + apl.lo_off, bytes);
-      }
-    } else if constexpr (P::kAMode == kReg) {
-      constexpr int kCh = kBM * 8 / kThreads;
-      float av[kCh][8];
-#pragma unroll
-      for (int i = 0; i < kCh; ++i) {
-        const int id = tid + i * kThreads;
-        const int r = P::kARowMajorThreads ? (id >> 3) : (id % kBM);
-        const int c = P::kARowMajorThreads ? (id & 7) : (id / kBM);
-        p.a8(z, m0 + r, k0 + c * 8, av[i]);
-      }
-#pragma unroll
-      for (int i = 0; i < kCh; ++i) {
-        const int id = tid + i * kThreads;
-        const int r = P::kARowMajorThreads ? (id >> 3) : (id % kBM);
-        const int c = P::kARowMajorThreads ? (id & 7) : (id / kBM);
-        uint4 hi, lo;
-        umma::split8(av[i], hi, lo);
-        *reinterpret_cast<uint4*>(st_gen + umma::sw128_off(r, c)) = hi;
-        if (!P::kAExact) *reinterpret_cast<uint4*>(st_gen + C::kABytes + umma::sw128_off(r, c)) = lo;
+      for (int i = 0; i < kACh; ++i) {
+        const int id = tid + i * kLoadThreads;
+        arow[i] = p.a_row(z, m0 + (P::kARowMajorThreads ? (id >> 3) : (id % kBM)));
       }
     }
     if constexpr (P::kBMode == kAsync) {
+      bpl = p.b_planes(z);
 #pragma unroll
-      for (int i = 0; i < (BN * 8 + kThreads - 1) / kThreads; ++i) {
-        const int id = tid + i * kThreads;
-        if (id < BN * 8) {
-          const int r = P::kBRowMajorThreads ? (id >> 3) : (id % BN);
-          const int c = P::kBRowMajorThreads ? (id & 7) : (id / BN);
+      for (int i = 0; i < kBCh; ++i) {
+        const int id = tid + i * kLoadThreads;
+        brow[i] = p.b_row(z, n0 + (P::kBRowMajorThreads ? (id >> 3) : (id % BN)));
+      }
+    }
+    for (int j = 0; j < nkb; ++j) {
+      const int s = j % S, kb = kb0 + j, k0 = kb * kBK;
+      if (j >= S) mbar_wait(&s_empty[s], ((j / S) - 1) & 1);
+      B2_TRACE(tid == 0, 8 + j * 4 + 2);
+      const uint32_t st_addr = smem_base + s * C::kStageBytes;
+      uint8_t* st_gen = smem_gen + s * C::kStageBytes;
+      const uint32_t a_hi = st_addr, a_lo = st_addr + C::kABytes, b_hi = st_addr + C::kAStage, b_lo = b_hi + C::kBBytes;
+      if (kAnyBulk && tid == 0) {
+        mbar_arrive_expect_tx(&s_full[s], kBulkBytes);
+        if constexpr (P::kAMode == kBulk)
+          tma_bulk_g2s(st_gen, p.a_tile(z, blockIdx.x, kb), 2 * C::kABytes, &s_full[s]);
+        if constexpr (P::kBMode == kBulk)
+          tma_bulk_g2s(st_gen + C::kAStage, p.b_tile(z, blockIdx.y, kb), 2 * C::kBBytes, &s_full[s]);
+      }
+      if constexpr (P::kAMode == kAsync) {
+#pragma unroll
+        for (int i = 0; i < kACh; ++i) {
+          const int id = tid + i * kLoadThreads;
+          const int r = P::kARowMajorThreads ? (id >> 3) : (id % kBM);
+          const int c = P::kARowMajorThreads ? (id & 7) : (id / kBM);
           int64_t eoff = 0;
-          const bool ok = brow[i].ok && p.b_chunk(z, brow[i], k0 + c * 8, eoff);
+          const bool ok = arow[i].ok && p.a_chunk(z, arow[i], k0 + c * 8, eoff);
           const uint32_t bytes = ok ? 16u : 0u;
-          const __half* hi = bpl.hi + (ok ? eoff : 0);
+          const __half* hi = apl.hi + (ok ? eoff : 0);
           const uint32_t off = umma::sw128_off(r, c);
-          cp_async16(b_hi + off, hi, bytes);
-          cp_async16(b_lo + off, hi + bpl.lo_off, bytes);
+          cp_async16(a_hi + off, hi, bytes);
+          if (!P::kAExact) cp_async16(a_lo + off, hi + apl.lo_off, bytes);
+        }
+      } else if constexpr (P::kAMode == kReg) {
+        float av[kACh][8];
+#pragma unroll
+        for (int i = 0; i < kACh; ++i) {
+          const int id = tid + i * kLoadThreads;
+          const int r = P::kARowMajorThreads ? (id >> 3) : (id % kBM);
+          const int c = P::kARowMajorThreads ? (id & 7) : (id / kBM);
+          p.a8(z, m0 + r, k0 + c * 8, av[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < kACh; ++i) {
+          const int id = tid + i * kLoadThreads;
+          const int r = P::kARowMajorThreads ? (id >> 3) : (id % kBM);
+          const int c = P::kARowMajorThreads ? (id & 7) : (id / kBM);
+          uint4 hi, lo;
+          umma::split8(av[i], hi, lo);
+          *reinterpret_cast<uint4*>(st_gen + umma::sw128_off(r, c)) = hi;
+          if (!P::kAExact) *reinterpret_cast<uint4*>(st_gen + C::kABytes + umma::sw128_off(r, c)) = lo;
+        }
+        fence_proxy_async_smem();   // st.shared (generic proxy) -> async proxy, writer side
+      }
+      if constexpr (P::kBMode == kAsync) {
+#pragma unroll
+        for (int i = 0; i < kBCh; ++i) {
+          const int id = tid + i * kLoadThreads;
+          if (id < BN * 8) {
+            const int r = P::kBRowMajorThreads ? (id >> 3) : (id % BN);
+            const int c = P::kBRowMajorThreads ? (id & 7) : (id / BN);
+            int64_t eoff = 0;
+            const bool ok = brow[i].ok && p.b_chunk(z, brow[i], k0 + c * 8, eoff);
+            const uint32_t bytes = ok ? 16u : 0u;
+            const __half* hi = bpl.hi + (ok ? eoff : 0);
+            const uint32_t off = umma::sw128_off(r, c);
+            cp_async16(b_hi + off, hi, bytes);
+            cp_async16(b_lo + off, hi + bpl.lo_off, bytes);
+          }
         }
       }
+      if constexpr (P::kAMode == kAsync || P::kBMode == kAsync)
+        cp_async_arrive_noinc(&s_full[s]);   // fires when this thread's copies for the stage have landed
+      else
+        mbar_arrive(&s_full[s]);
+      B2_TRACE(tid == 0, 8 + j * 4 + 3);
     }
-  };
+    B2_TRACE(tid == 0, 3);
 
-  // ---- prologue: loads run PF k-blocks ahead of the tensor core; the stage being refilled was
-  // read by the MMAs issued S - PF iterations ago, so the wait on its "empty" barrier is normally free.
-  constexpr int PF = S - 2;
+    // ================================================================ epilogue (same 8 warps)
+    mbar_wait(&s_done, 0);
+    umma::fence_after_sync();
+    B2_TRACE(tid == 0, 4);
+    {
+      const int q = warp & 3, half = warp >> 2;
+      const int m = m0 + q * 32 + lane;
+      const uint32_t lane_addr = tmem + (uint32_t(q * 32) << 16);
+      constexpr int kColsPerHalf = BN / 2;
+      constexpr int kChunks = kColsPerHalf / 8;
+      float a0[kChunks][8], a1[kChunks][8];
 #pragma unroll
-  for (int j = 0; j < PF; ++j) {
-    if (j < nkb) issue_loads(j);
-    cp_async_commit();
-  }
-
-  for (int it = 0; it < nkb; ++it) {
-    const int s = it % S;
-    cp_async_wait<PF - 1>();         // this thread's copies for k-block `it` have landed
-    fence_proxy_async_smem();        // generic/LDGSTS writes -> visible to the tensor core's async proxy
-    __syncthreads();                 // ... for every thread's copies
-    if (tid == 0) {
-      if (kAnyBulk) mbar_wait(&s_full[s], (it / S) & 1);
-      umma::fence_after_sync();
-      const uint32_t sa = smem_base + s * C::kStageBytes;
-      const uint64_t da_hi = umma::make_desc_sw128(sa);
-      const uint64_t da_lo = umma::make_desc_sw128(sa + C::kABytes);
-      const uint64_t db_hi = umma::make_desc_sw128(sa + C::kAStage);
-      const uint64_t db_lo = umma::make_desc_sw128(sa + C::kAStage + C::kBBytes);
-#pragma unroll
-      for (int k = 0; k < kBK / 16; ++k) {
-        const uint32_t acc = (it > 0 || k > 0) ? 1u : 0u;
-        umma::mma_f16(tmem, da_hi + 2 * k, db_hi + 2 * k, idesc, acc);
-        if (!P::kAExact) {
-          umma::mma_f16(tmem + BN, da_lo + 2 * k, db_hi + 2 * k, idesc, acc);
-          umma::mma_f16(tmem + BN, da_hi + 2 * k, db_lo + 2 * k, idesc, 1u);
-        } else {
-          umma::mma_f16(tmem + BN, da_hi + 2 * k, db_lo + 2 * k, idesc, acc);
-        }
+      for (int c = 0; c < kChunks; ++c) {        // all TMEM loads in flight, one wait
+        const int col = half * kColsPerHalf + c * 8;
+        umma::tmem_ld8(lane_addr + col, a0[c]);
+        umma::tmem_ld8(lane_addr + BN + col, a1[c]);
       }
-      umma::mma_commit(&s_empty[s]);
-      if (it == nkb - 1) umma::mma_commit(&s_done);
-    }
-    // refill the stage that k-block it-2 used (its MMAs were issued two iterations ago)
-    const int nxt = it + PF;
-    if (nxt < nkb) {
-      if (nxt >= S) mbar_wait(&s_empty[nxt % S], ((nxt / S) - 1) & 1);
-      issue_loads(nxt);
-    }
-    cp_async_commit();
-  }
-
-  // ---- epilogue
-  mbar_wait(&s_done, 0);
-  umma::fence_after_sync();
-  {
-    const int q = warp & 3, half = warp >> 2;
-    const int m = m0 + q * 32 + lane;
-    const uint32_t lane_addr = tmem + (uint32_t(q * 32) << 16);
-    constexpr int kColsPerHalf = BN / 2;
-#pragma unroll
-    for (int c = 0; c < kColsPerHalf; c += 8) {
-      const int col = half * kColsPerHalf + c;
-      float a0[8], a1[8];
-      umma::tmem_ld8(lane_addr + col, a0);
-      umma::tmem_ld8(lane_addr + BN + col, a1);
       umma::tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 8; ++j) a0[j] = fmaf(a1[j], umma::kLoInv, a0[j]);
-      if (m < M && n0 + col < N) p.store8(z, m, n0 + col, a0);
+      for (int c = 0; c < kChunks; ++c) {
+        const int col = half * kColsPerHalf + c * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a0[c][j] = fmaf(a1[c][j], umma::kLoInv, a0[c][j]);
+        if (m < M && n0 + col < N) p.store8(z, m, n0 + col, a0[c]);
+      }
     }
+    B2_TRACE(tid == 0, 5);
   }
   umma::fence_before_sync();
   __syncthreads();
-  if (warp == 0) {
+  if (warp == 8) {
     umma::fence_after_sync();
     umma::tmem_dealloc(tmem, C::kTmemCols);
   }
+  B2_TRACE(tid == 0, 6);
+}
+
+static inline int read_trace(unsigned long long* out, int n) {
+  if (n > kTraceSlots) n = kTraceSlots;
+  return cudaMemcpyFromSymbol(out, g_trace, n * sizeof(unsigned long long)) == cudaSuccess ? n : -1;
 }
 
 template <class P>
@@ -299,7 +325,9 @@ static int launch_umma2(const char* label, const P& p, int M, int N, int Z, cuda
     configured = true;
   }
   dim3 grid((M + kBM - 1) / kBM, (N + C::BN - 1) / C::BN, Z);
-  k_umma2<P><<<grid, kThreads, C::kSmemBytes, st>>>(p);
+  static const char* trace_label = getenv("B200DQN_TRACE_LABEL");
+  const int trace = (trace_label && strcmp(trace_label, label) == 0) ? 1 : 0;
+  k_umma2<P><<<grid, kThreads2, C::kSmemBytes, st>>>(p, trace);
   B2_LAUNCH_CHECK();
   B2_PROF(label, st);
   return B200DQN_OK;
