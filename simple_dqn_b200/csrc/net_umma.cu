@@ -339,6 +339,7 @@ struct V2Conv1Fwd {
   static constexpr int kBN = 32;
   static constexpr bool kAExact = true, kARowMajorThreads = true, kBRowMajorThreads = false;
   static constexpr int kAMode = umma2::kReg, kBMode = umma2::kBulk;
+  static constexpr bool kStagedEpilogue = true;
   const uint8_t* src[2];
   const int32_t* idx[2];
   int shift[2];
@@ -378,6 +379,7 @@ struct V2ConvFwd {
   static constexpr int kBN = KO;
   static constexpr bool kAExact = false, kARowMajorThreads = true, kBRowMajorThreads = false;
   static constexpr int kAMode = umma2::kAsync, kBMode = umma2::kBulk;
+  static constexpr bool kStagedEpilogue = true;
   PlanePair in16[2];
   const uint8_t* wimg[2];   // [K/64][hi KOx128 | lo KOx128]
   float* out[2];
@@ -409,6 +411,7 @@ struct V2Fc1Fwd {
   static constexpr int kBN = 32;
   static constexpr bool kAExact = false, kARowMajorThreads = false, kBRowMajorThreads = true;
   static constexpr int kAMode = umma2::kBulk, kBMode = umma2::kAsync;
+  static constexpr bool kStagedEpilogue = false;   // outputs of a thread are strided; lanes are contiguous in m
   PlanePair in16[2];        // H3 planes [rows][3136]
   const uint8_t* wimg[2];   // [4 mtiles][49 kb][hi 128x128 | lo 128x128]
   float* part;              // [2*splits][rows][512]
@@ -441,6 +444,7 @@ struct V2Fc1Dgrad {
   static constexpr int kBN = 32;
   static constexpr bool kAExact = false, kARowMajorThreads = true, kBRowMajorThreads = true;
   static constexpr int kAMode = umma2::kBulk, kBMode = umma2::kAsync;
+  static constexpr bool kStagedEpilogue = false;
   const uint8_t* wimg;   // [25 mtiles][8 kb][hi | lo]   rows m = flat index (p,q,c), K = hidden unit
   PlanePair dz4;         // [rows][512]
   const float* h3;       // [rows][3136] (mask)
@@ -481,6 +485,7 @@ struct V2ConvDgrad {
   static constexpr int kBN = C;
   static constexpr bool kAExact = false, kARowMajorThreads = true, kBRowMajorThreads = true;
   static constexpr int kAMode = umma2::kAsync, kBMode = umma2::kBulk;
+  static constexpr bool kStagedEpilogue = true;
   PlanePair dz;          // [rows][P][P][KO]
   const uint8_t* wimg;   // [ST*ST classes][K/64][hi Cx128 | lo Cx128]
   const float* x;        // forward activation (mask)

@@ -69,6 +69,8 @@ __device__ __forceinline__ void split8_planes(const float v[8], __half* hi_dst, 
 //           same with b_row / b_chunk / b_planes for B
 //   kBulk : const uint8_t* a_tile(z, mtile, kb) / b_tile(z, ntile, kb)      -> [hi image | lo image]
 //   void store8(z, m, n0, const float v[8])
+//   static constexpr bool kStagedEpilogue: store8 writes 8 CONTIGUOUS outputs of row m (NHWC tensors) ->
+//        the tile is transposed through smem so that a warp's stores are whole cache lines
 template <class P>
 struct Cfg2 {
   static constexpr int BN = P::kBN;
@@ -96,6 +98,15 @@ __device__ unsigned long long g_trace[kTraceSlots];
 
 __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ bool elect_one() {   // one lane of a converged warp (CUTLASS elect_one_sync)
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 constexpr int kLoadThreads = 256;            // warps 0..7: operand staging, then the epilogue
@@ -154,19 +165,21 @@ __global__ void __launch_bounds__(kThreads2, 1) k_umma2(const P p, const int tra
 
   if (warp == 8) {
     // ================================================================ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc1 = umma::make_idesc_f16(kBM, BN);
-      constexpr uint32_t idesc2 = umma::make_idesc_f16(kBM, 2 * BN);
-      for (int it = 0; it < nkb; ++it) {
-        const int s = it % S;
-        mbar_wait(&s_full[s], (it / S) & 1);
-        fence_proxy_async_smem();
-        umma::fence_after_sync();
-        B2_TRACE(true, 8 + it * 4 + 0);
-        const uint32_t sa = smem_base + s * C::kStageBytes;
-        const uint64_t da_hi = umma::make_desc_sw128(sa);
-        const uint64_t da_lo = umma::make_desc_sw128(sa + C::kABytes);
-        const uint64_t db = umma::make_desc_sw128(sa + C::kAStage);   // [B_hi ; B_lo], 2*BN rows
+    // The whole warp runs the loop converged; one elected lane issues (keeps descriptors in uniform
+    // registers and avoids the per-instruction re-convergence loop ptxas emits inside divergent code).
+    constexpr uint32_t idesc1 = umma::make_idesc_f16(kBM, BN);
+    constexpr uint32_t idesc2 = umma::make_idesc_f16(kBM, 2 * BN);
+    for (int it = 0; it < nkb; ++it) {
+      const int s = it % S;
+      mbar_wait(&s_full[s], (it / S) & 1);
+      fence_proxy_async_smem();
+      umma::fence_after_sync();
+      B2_TRACE(lane == 0, 8 + it * 4 + 0);
+      const uint32_t sa = smem_base + s * C::kStageBytes;
+      const uint64_t da_hi = umma::make_desc_sw128(sa);
+      const uint64_t da_lo = umma::make_desc_sw128(sa + C::kABytes);
+      const uint64_t db = umma::make_desc_sw128(sa + C::kAStage);   // [B_hi ; B_lo], 2*BN rows
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < kBK / 16; ++k) {
           umma::mma_f16(tmem, da_hi + 2 * k, db + 2 * k, idesc2, (it > 0 || k > 0) ? 1u : 0u);
@@ -174,8 +187,9 @@ __global__ void __launch_bounds__(kThreads2, 1) k_umma2(const P p, const int tra
         }
         umma::mma_commit(&s_empty[s]);
         if (it == nkb - 1) umma::mma_commit(&s_done);
-        B2_TRACE(true, 8 + it * 4 + 1);
       }
+      __syncwarp();
+      B2_TRACE(lane == 0, 8 + it * 4 + 1);
     }
   } else {
     // ================================================================ loaders
@@ -280,7 +294,7 @@ __global__ void __launch_bounds__(kThreads2, 1) k_umma2(const P p, const int tra
     B2_TRACE(tid == 0, 4);
     {
       const int q = warp & 3, half = warp >> 2;
-      const int m = m0 + q * 32 + lane;
+      const int row = q * 32 + lane;
       const uint32_t lane_addr = tmem + (uint32_t(q * 32) << 16);
       constexpr int kColsPerHalf = BN / 2;
       constexpr int kChunks = kColsPerHalf / 8;
@@ -293,11 +307,38 @@ __global__ void __launch_bounds__(kThreads2, 1) k_umma2(const P p, const int tra
       }
       umma::tmem_ld_wait();
 #pragma unroll
-      for (int c = 0; c < kChunks; ++c) {
-        const int col = half * kColsPerHalf + c * 8;
+      for (int c = 0; c < kChunks; ++c)
 #pragma unroll
         for (int j = 0; j < 8; ++j) a0[c][j] = fmaf(a1[c][j], umma::kLoInv, a0[c][j]);
-        if (m < M && n0 + col < N) p.store8(z, m, n0 + col, a0[c]);
+      if constexpr (P::kStagedEpilogue) {
+        // A thread owns one accumulator ROW; written straight to HBM every store instruction would
+        // touch 32 different lines.  Transpose through (now idle) pipeline smem so each warp store
+        // covers whole lines: row pitch BN*4 + 16 B keeps both phases bank-conflict free.
+        constexpr int kPitch = BN * 4 + 16;
+        static_assert(kBM * kPitch <= C::kStages * C::kStageBytes, "staging tile must fit the stage ring");
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c) {
+          float* dst = reinterpret_cast<float*>(smem_gen + row * kPitch + (half * kColsPerHalf + c * 8) * 4);
+          *reinterpret_cast<float4*>(dst) = make_float4(a0[c][0], a0[c][1], a0[c][2], a0[c][3]);
+          *reinterpret_cast<float4*>(dst + 4) = make_float4(a0[c][4], a0[c][5], a0[c][6], a0[c][7]);
+        }
+        named_bar_sync(1, kLoadThreads);
+        constexpr int kChunksPerRow = BN / 8;
+#pragma unroll
+        for (int i = 0; i < kBM * kChunksPerRow / kLoadThreads; ++i) {
+          const int id = tid + i * kLoadThreads;
+          const int r = id / kChunksPerRow, cc = id % kChunksPerRow;
+          const float* src = reinterpret_cast<const float*>(smem_gen + r * kPitch + cc * 32);
+          const float4 v0 = *reinterpret_cast<const float4*>(src), v1 = *reinterpret_cast<const float4*>(src + 4);
+          const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+          if (m0 + r < M && n0 + cc * 8 < N) p.store8(z, m0 + r, n0 + cc * 8, v);
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c) {
+          const int col = half * kColsPerHalf + c * 8;
+          if (m0 + row < M && n0 + col < N) p.store8(z, m0 + row, n0 + col, a0[c]);
+        }
       }
     }
     B2_TRACE(tid == 0, 5);
