@@ -149,7 +149,16 @@ k_optimizer(const LayerTable lt, const float* __restrict__ part, float* __restri
     const int64_t lsize = lt.off[l + 1] - lt.off[l];
     const float* p = part + lt.part_off[l] + (i - lt.off[l]);
     g = *reinterpret_cast<const float4*>(p);
-    for (int sp = 1; sp < lt.splits[l]; ++sp) {
+    const int nsp = lt.splits[l];
+    int sp = 1;
+    for (; sp + 8 <= nsp; sp += 8) {   // 8 independent loads in flight, summed in fixed order
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = *reinterpret_cast<const float4*>(p + (sp + u) * lsize);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { g.x += v[u].x; g.y += v[u].y; g.z += v[u].z; g.w += v[u].w; }
+    }
+    for (; sp < nsp; ++sp) {
       const float4 v = *reinterpret_cast<const float4*>(p + sp * lsize);
       g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w;
     }

@@ -6,6 +6,7 @@
 #include "net_umma.cuh"
 #include "umma.cuh"
 #include "umma2.cuh"
+#include "umma_mn.cuh"
 
 namespace b200 {
 
@@ -315,8 +316,8 @@ struct UmmaState {
   // activation planes per net: [hi plane | lo plane], NHWC fp16
   __half* h16[3][2] = {};     // H1, H2, H3  x  (online, target)
   int64_t h_elems[3] = {};
-  __half* dz16[3] = {};       // dZ4, dZ3, dZ2 (online)
-  int64_t dz_elems[3] = {};
+  __half* dz16[4] = {};       // dZ4, dZ3, dZ2, dZ1 (online)
+  int64_t dz_elems[4] = {};
   // weight tile images ([hi | lo] per (tile, k-block))
   uint8_t* img_fwd[2][4] = {};  // conv1, conv2, conv3, fc1  x  (online, target)
   int64_t img_fwd_bytes[4] = {};
@@ -522,6 +523,107 @@ struct V2ConvDgrad {
   }
 };
 
+// ---- wgrad (MN-major operands, umma_mn.cuh) -----------------------------------------------------
+// conv2 / conv3: dW[(r,s,c)][ko] = sum_{n,p,q} X[n, p*ST+r, q*ST+s, c] * dZ[n,p,q,ko]
+// One 64-wide m chunk is a contiguous run of the NHWC input: (s, c) are adjacent dims and R*C % 64 == 0.
+template <int H, int C, int R, int ST, int KO>
+struct WConvWgrad {
+  static constexpr int P = (H - R) / ST + 1, KW = R * R * C;
+  static_assert((R * C) % 64 == 0 && KO == 64, "64-element runs must not straddle a filter row");
+  static constexpr int kBN = 64;
+  static constexpr bool kAExact = false, kARegs = false;
+  PlanePair x16;    // [rows][H][H][C]
+  PlanePair dz16;   // [rows][P][P][KO]
+  float* part;      // [splits][KW][KO]
+  int rows, kb_per_split;
+  __device__ int M(int) const { return KW; }
+  __device__ int N(int) const { return KO; }
+  __device__ void krange(int z, int& kb, int& ke) const {
+    const int total = (rows * P * P + 63) / 64;
+    kb = min(z * kb_per_split, total);
+    ke = min(kb + kb_per_split, total);
+  }
+  __device__ umma_mn::PixCtx pix(int, int kpix) const {
+    const int n = kpix / (P * P), pq = kpix % (P * P);
+    return {n, pq / P, pq % P, kpix < rows * P * P};
+  }
+  __device__ umma2::Planes a_planes(int) const { return {x16.hi, x16.lo_off}; }
+  __device__ bool a_run(int, const umma_mn::PixCtx& px, int mchunk, int64_t& off) const {
+    const int m = mchunk * 64, r = m / (R * C), sc = m % (R * C);
+    off = (int64_t(px.n * H + px.p * ST + r) * H + px.q * ST) * C + sc;
+    return m < KW;
+  }
+  __device__ umma2::Planes b_planes(int) const { return {dz16.hi, dz16.lo_off}; }
+  __device__ int64_t b_off(int, const umma_mn::PixCtx& px) const { return (int64_t(px.n * P + px.p) * P + px.q) * KO; }
+  __device__ void store8(int z, int m, int n0, const float v[8]) const { st8(part + (int64_t(z) * KW + m) * KO + n0, v); }
+};
+
+// conv1: A = the u8 frame window (exact in fp16); m chunk = frame c, piece j = filter row r (8 pixels).
+struct WConv1Wgrad {
+  static constexpr int kBN = 32;
+  static constexpr bool kAExact = true, kARegs = true;
+  const uint8_t* src;
+  const int32_t* idx;
+  int shift;
+  PlanePair dz16;   // dZ1 [rows][20][20][32]
+  float* part;      // [splits][256][32]
+  int rows, kb_per_split;
+  __device__ int M(int) const { return kK1; }
+  __device__ int N(int) const { return kC1; }
+  __device__ void krange(int z, int& kb, int& ke) const {
+    const int total = (rows * kP1 * kP1 + 63) / 64;
+    kb = min(z * kb_per_split, total);
+    ke = min(kb + kb_per_split, total);
+  }
+  __device__ umma_mn::PixCtx pix(int, int kpix) const {
+    const int n = kpix / (kP1 * kP1), pq = kpix % (kP1 * kP1);
+    return {n, pq / kP1, pq % kP1, kpix < rows * kP1 * kP1};
+  }
+  __device__ void a_piece(int, const umma_mn::PixCtx& px, int c, int r, float v[8]) const {
+    if (!px.ok) { zero8(v); return; }
+    const int64_t f = static_cast<int64_t>(idx[px.n]) + shift + c;
+    const uint8_t* ptr = src + f * kFrameBytes + (px.p * 4 + r) * kFrameW + px.q * 4;
+    const uint32_t lo = *reinterpret_cast<const uint32_t*>(ptr), hi = *reinterpret_cast<const uint32_t*>(ptr + 4);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v[j] = float((lo >> (8 * j)) & 0xffu);
+      v[4 + j] = float((hi >> (8 * j)) & 0xffu);
+    }
+  }
+  __device__ umma2::Planes b_planes(int) const { return {dz16.hi, dz16.lo_off}; }
+  __device__ int64_t b_off(int, const umma_mn::PixCtx& px) const {
+    return (int64_t(px.n * kP1 + px.p) * kP1 + px.q) * kC1;
+  }
+  __device__ void store8(int z, int m, int n0, const float v[8]) const {
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = v[j] * (1.0f / 255.0f);
+    st8(part + (int64_t(z) * kK1 + m) * kC1 + n0, o);
+  }
+};
+
+// fc1: dW4[m][n] = sum_b H3[b][m] * dZ4[b][n]; the reduction rows are the batch samples.
+struct WFc1Wgrad {
+  static constexpr int kBN = 64;
+  static constexpr bool kAExact = false, kARegs = false;
+  PlanePair h3_16;   // [rows][3136]
+  PlanePair dz4_16;  // [rows][512]
+  float* dw4;        // [3136][512]
+  int rows;
+  __device__ int M(int) const { return kFlat; }
+  __device__ int N(int) const { return kHidden; }
+  __device__ void krange(int, int& kb, int& ke) const { kb = 0; ke = (rows + 63) / 64; }
+  __device__ umma_mn::PixCtx pix(int, int b) const { return {b, 0, 0, b < rows}; }
+  __device__ umma2::Planes a_planes(int) const { return {h3_16.hi, h3_16.lo_off}; }
+  __device__ bool a_run(int, const umma_mn::PixCtx& px, int mchunk, int64_t& off) const {
+    off = int64_t(px.n) * kFlat + mchunk * 64;
+    return mchunk * 64 < kFlat;
+  }
+  __device__ umma2::Planes b_planes(int) const { return {dz4_16.hi, dz4_16.lo_off}; }
+  __device__ int64_t b_off(int, const umma_mn::PixCtx& px) const { return int64_t(px.n) * kHidden; }
+  __device__ void store8(int, int m, int n0, const float v[8]) const { st8(dw4 + int64_t(m) * kHidden + n0, v); }
+};
+
 // ---- weight tile-image sources (k_pack_image) --------------------------------------------------
 template <int K, int N>
 struct PackFwdConv {   // B operand of a forward conv: rows = output channel n, K = filter taps
@@ -632,11 +734,14 @@ int umma_net_init(b200dqn_net* n) {
   u->dz_elems[0] = int64_t(nb) * kHidden;
   u->dz_elems[1] = int64_t(nb) * kFlat;
   u->dz_elems[2] = int64_t(nb) * kP2 * kP2 * kC2;
+  u->dz_elems[3] = int64_t(nb) * kP1 * kP1 * kC1;
   for (int i = 0; i < 3; ++i) {
     for (int z = 0; z < 2; ++z) {
       B2_CHECK_CUDA(cudaMalloc(&u->h16[i][z], 2 * u->h_elems[i] * sizeof(__half)));
       B2_CHECK_CUDA(cudaMemset(u->h16[i][z], 0, 2 * u->h_elems[i] * sizeof(__half)));
     }
+  }
+  for (int i = 0; i < 4; ++i) {
     B2_CHECK_CUDA(cudaMalloc(&u->dz16[i], 2 * u->dz_elems[i] * sizeof(__half)));
     B2_CHECK_CUDA(cudaMemset(u->dz16[i], 0, 2 * u->dz_elems[i] * sizeof(__half)));
   }
@@ -662,9 +767,9 @@ void umma_net_destroy(b200dqn_net* n) {
   if (!u) return;
   for (int i = 0; i < 3; ++i) {
     for (int z = 0; z < 2; ++z) cudaFree(u->h16[i][z]);
-    cudaFree(u->dz16[i]);
     cudaFree(u->img_dgr[i]);
   }
+  for (int i = 0; i < 4; ++i) cudaFree(u->dz16[i]);
   for (int l = 0; l < 4; ++l) {
     if (u->img_fwd[1][l] != u->img_fwd[0][l]) cudaFree(u->img_fwd[1][l]);
     cudaFree(u->img_fwd[0][l]);
@@ -741,8 +846,10 @@ int umma_backward_op(b200dqn_net* n, int op, const uint8_t* src, const int32_t* 
   const float* w = n->d_w;
   switch (op) {
     case 0: {
-      UFc1Wgrad p{n->d_h3[0], n->d_dz4, n->d_part + lt.part_off[3], rows};
-      return umma::launch_umma("fc1_wgrad", p, kFlat, kHidden, 1, st);
+      UmmaState* u = ust(n);
+      WFc1Wgrad p{PlanePair{u->h16[2][0], u->h_elems[2]}, PlanePair{u->dz16[0], u->dz_elems[0]},
+                  n->d_part + lt.part_off[3], rows};
+      return umma_mn::launch_umma_mn("fc1_wgrad", p, kFlat, kHidden, 1, st);
     }
     case 1: {
       UmmaState* u = ust(n);
@@ -751,9 +858,11 @@ int umma_backward_op(b200dqn_net* n, int op, const uint8_t* src, const int32_t* 
       return umma2::launch_umma2("fc1_dgrad", p, kFlat, rows, 1, st);
     }
     case 2: {
-      using P = UConvWgrad<kP2, kC2, 3, 1, kC3>;
-      P p{n->d_h2[0], n->d_dz3, n->d_part + lt.part_off[2], rows, kUWgradKb};
-      return umma::launch_umma("conv3_wgrad", p, P::KW, kC3, lt.splits[2], st);
+      UmmaState* u = ust(n);
+      using P = WConvWgrad<kP2, kC2, 3, 1, kC3>;
+      P p{PlanePair{u->h16[1][0], u->h_elems[1]}, PlanePair{u->dz16[1], u->dz_elems[1]},
+          n->d_part + lt.part_off[2], rows, kUWgradKb};
+      return umma_mn::launch_umma_mn("conv3_wgrad", p, P::KW, kC3, lt.splits[2], st);
     }
     case 3: {
       UmmaState* u = ust(n);
@@ -763,19 +872,24 @@ int umma_backward_op(b200dqn_net* n, int op, const uint8_t* src, const int32_t* 
       return umma2::launch_umma2("conv3_dgrad", p, rows * P::HC * P::HC, kC2, 1, st);
     }
     case 4: {
-      using P = UConvWgrad<kP1, kC1, 4, 2, kC2>;
-      P p{n->d_h1[0], n->d_dz2, n->d_part + lt.part_off[1], rows, kUWgradKb};
-      return umma::launch_umma("conv2_wgrad", p, P::KW, kC2, lt.splits[1], st);
+      UmmaState* u = ust(n);
+      using P = WConvWgrad<kP1, kC1, 4, 2, kC2>;
+      P p{PlanePair{u->h16[0][0], u->h_elems[0]}, PlanePair{u->dz16[2], u->dz_elems[2]},
+          n->d_part + lt.part_off[1], rows, kUWgradKb};
+      return umma_mn::launch_umma_mn("conv2_wgrad", p, P::KW, kC2, lt.splits[1], st);
     }
     case 5: {
       UmmaState* u = ust(n);
       using P = V2ConvDgrad<kP1, kC1, 4, 2, kC2>;
-      P p{PlanePair{u->dz16[2], u->dz_elems[2]}, u->img_dgr[2], n->d_h1[0], n->d_dz1, PlanePair{nullptr, 0}, rows};
+      P p{PlanePair{u->dz16[2], u->dz_elems[2]}, u->img_dgr[2], n->d_h1[0], n->d_dz1,
+          PlanePair{u->dz16[3], u->dz_elems[3]}, rows};
       return umma2::launch_umma2("conv2_dgrad", p, rows * P::HC * P::HC, kC1, 4, st);
     }
     default: {
-      UConv1Wgrad p{src, idx, shift, n->d_dz1, n->d_part + lt.part_off[0], rows, kUWgradKb};
-      return umma::launch_umma("conv1_wgrad", p, kK1, kC1, lt.splits[0], st);
+      UmmaState* u = ust(n);
+      WConv1Wgrad p{src, idx, shift, PlanePair{u->dz16[3], u->dz_elems[3]}, n->d_part + lt.part_off[0], rows,
+                    kUWgradKb};
+      return umma_mn::launch_umma_mn("conv1_wgrad", p, kK1, kC1, lt.splits[0], st);
     }
   }
 }
