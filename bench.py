@@ -231,9 +231,8 @@ def run_b200(a, rank, world, local_rank):
     net = DeepQNetwork(NUM_ACTIONS, args, device=dev, math_mode=a.math, stream=stream)
     net.update_target_network()
     if world > 1:
-        uid = [DeepQNetwork.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        net.comm_init(uid[0], rank, world)
+        from simple_dqn_b200.parallel import broadcast_unique_id
+        net.comm_init(broadcast_unique_id(dist, DeepQNetwork.comm_unique_id, rank), rank, world)
     random.seed(1)
     mem.seed_device_rng(random)
 
@@ -361,7 +360,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3000)
     ap.add_argument("--warmup", type=int, default=100)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--math", default=os.environ.get("B200DQN_MATH", "fp32"), choices=["fp32", "tcgen05"])
+    ap.add_argument("--math", default=os.environ.get("B200DQN_MATH", "tcgen05"), choices=["fp32", "tcgen05"])
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--replay", type=int, default=1_000_000)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)

@@ -1,0 +1,89 @@
+"""world_size-2 `gloo` test (CPU) of the N>1 sharding rule of DESIGN.md §5: two ranks that each take their
+slice of ONE global minibatch, sum gradients with an all-reduce and apply RMSProp with g = sum / (world*B)
+must reproduce the single-process oracle trained with batch world*B (indexes bit-exact, weights to fp32
+reassociation), and must stay bit-identical to each other."""
+import os
+import random
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from helpers import rel_l2
+from oracle import dqn_oracle as O
+from oracle.mt19937 import MT19937
+from oracle.replay_oracle import ReplayOracle, synthetic_ring
+from simple_dqn_b200.parallel import broadcast_unique_id, global_batch, rank_slice
+
+B, WORLD, A = 4, 2, 4
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _ring():
+    ring = ReplayOracle(400, batch_size=global_batch(WORLD, B))
+    synthetic_ring(ring, seed=2, block=50, terminal_p=0.02)
+    return ring
+
+
+def _worker(rank, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=WORLD)
+    torch.set_num_threads(1)
+    uid = broadcast_unique_id(dist, lambda: bytes(range(128)), rank)
+    assert uid == bytes(range(128))
+    ring = _ring()                                   # replicated ring
+    rng = MT19937.from_python(random.Random(5))      # replicated stream
+    net = O.DQNOracle(A, batch_size=B, seed=9)
+    for _ in range(3):
+        pre, act, rew, post, term = ring.getMinibatch(rng)          # the GLOBAL minibatch, same on every rank
+        lo, hi = rank_slice(rank, WORLD, B)
+        mb = (pre[lo:hi], act[lo:hi], rew[lo:hi], post[lo:hi], term[lo:hi])
+        postq = O.forward(net.target_weights, mb[3])
+        preq, acts = O.forward(net.weights, mb[0], keep=True)
+        targets = O.td_targets(preq, postq.max(axis=1), mb[1], mb[2], mb[4])
+        deltas = np.clip(preq - targets, -1, 1).astype(np.float32)
+        grads = O.backward(net.weights, acts, deltas)
+        for g in grads:                                              # the one exchange step of the path
+            t = torch.from_numpy(g)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        O.rmsprop_update(net.weights, net.states, grads, global_batch(WORLD, B))
+    np.savez(os.path.join(out_dir, "rank%d.npz" % rank), *net.weights, pos=np.array(rng.state625()[-1]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharding_matches_single_process_oracle(tmp_path):
+    port = _free_port()
+    mp.spawn(_worker, args=(port, str(tmp_path)), nprocs=WORLD, join=True)
+    r0 = np.load(tmp_path / "rank0.npz")
+    r1 = np.load(tmp_path / "rank1.npz")
+    ring = _ring()
+    rng = MT19937.from_python(random.Random(5))
+    ref = O.DQNOracle(A, batch_size=WORLD * B, seed=9)
+    w0 = [w.copy() for w in ref.weights]
+    for _ in range(3):
+        ref.train(ring.getMinibatch(rng))
+    assert int(r0["pos"]) == int(r1["pos"]) == rng.state625()[-1]       # same draw count on every rank
+    for l in range(5):
+        a, b = r0["arr_%d" % l], r1["arr_%d" % l]
+        assert (a == b).all(), "ranks must stay bit-identical"
+        assert rel_l2(a - w0[l], ref.weights[l] - w0[l]) <= 1e-3, l
+
+
+def test_rank_slice_partition():
+    for world in (1, 2, 4, 8):
+        spans = [rank_slice(r, world, 32) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == global_batch(world, 32)
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+    with pytest.raises(AssertionError):
+        rank_slice(2, 2, 32)
