@@ -96,6 +96,14 @@ extern "C" int b200dqn_net_comm_init(b200dqn_net* n, const void* id128, int rank
   n->nccl_comm = comm;
   n->rank = rank;
   n->world = world_size;
+  // Warm-up collective outside any capture: NCCL sets up its channels/proxies lazily on the first call,
+  // which must not happen inside the CUDA-graph capture of the train step.
+  cudaStream_t ws;
+  B2_CHECK_CUDA(cudaStreamCreateWithFlags(&ws, cudaStreamNonBlocking));
+  B2_CHECK_CUDA(cudaMemsetAsync(n->d_g, 0, n->n_params * sizeof(float), ws));
+  B2_CHECK_NCCL(g_nccl.AllReduce(n->d_g, n->d_g, size_t(n->n_params), kNcclFloat32, kNcclSum, comm, ws));
+  B2_CHECK_CUDA(cudaStreamSynchronize(ws));
+  B2_CHECK_CUDA(cudaStreamDestroy(ws));
   return B200DQN_OK;
 }
 
