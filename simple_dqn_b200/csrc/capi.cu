@@ -1,5 +1,6 @@
 // capi.cu — library-wide entry points: error text, version, device probe.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -13,6 +14,7 @@ void set_error(const char* fmt, ...) {
 }
 
 bool g_prof_on = false;
+bool g_use_pdl = getenv("B200DQN_NO_PDL") == nullptr;
 namespace {
 constexpr int kProfCap = 8192;
 struct Prof {

@@ -56,6 +56,25 @@ extern bool g_prof_on;
 
 // ---------------------------------------------------------------- device-side PTX helpers
 #ifdef __CUDACC__
+extern bool g_use_pdl;   // B200DQN_NO_PDL unset
+
+// Launch `kernel` with the programmatic-dependent-launch attribute (every kernel launched this way
+// calls pdl_wait() before it touches data produced by earlier kernels).
+template <class... KArgs, class... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_use_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
@@ -108,6 +127,12 @@ __device__ __forceinline__ void tma_bulk_wait_all() { asm volatile("cp.async.bul
 __device__ __forceinline__ void tma_bulk_wait_read_all() {
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
+// Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization
+// attribute may begin while its predecessor is still running; pdl_wait() blocks until every
+// prerequisite grid has completed and flushed (no-op without the attribute), pdl_launch_dependents()
+// lets the successor start its own prologue (TMEM alloc, barrier init, index setup) early.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 // generic-proxy writes -> visible to the async proxy (TMA / tcgen05 operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

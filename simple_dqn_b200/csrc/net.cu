@@ -48,6 +48,8 @@ k_head(const float* __restrict__ part, int splits, int rows, float* h4_online, f
   __shared__ float red[kHidden / 32][kMaxActions];
   __shared__ int s_last;
   const int b = blockIdx.x, z = blockIdx.y, t = threadIdx.x;
+  pdl_launch_dependents();
+  pdl_wait();
   float h = 0.f;
   for (int s = 0; s < splits; ++s) h += part[((z * splits + s) * rows + b) * kHidden + t];
   h = fmaxf(h, 0.f);
@@ -139,6 +141,8 @@ k_optimizer(const LayerTable lt, const float* __restrict__ part, float* __restri
             float* __restrict__ s, int64_t b4, int64_t e4, int mode, float inv_bsz, float lr, float decay,
             float one_m_decay, float eps) {
   const int64_t i4 = b4 + blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  pdl_launch_dependents();
+  pdl_wait();
   if (i4 >= e4) return;
   const int64_t i = i4 * 4;
   float4 g;
@@ -258,9 +262,9 @@ static int forward(b200dqn_net* n, const FrameSource& fs, int nets, int rows, cu
     }
   }
   const int fc1_splits = n->cfg.math_mode == B200DQN_MATH_TCGEN05 ? umma_fc1_splits() : kFc1Splits;
-  k_head<<<dim3(rows, nets), kHidden, 0, st>>>(n->d_fc1part, fc1_splits, rows, n->d_h4[0], n->d_h4[1],
-                                               w[0] + lt.off[4], w[1] + lt.off[4], n->d_q[0], n->d_q[1], n->A, td);
-  B2_LAUNCH_CHECK();
+  B2_CHECK_CUDA(launch_pdl(k_head, dim3(rows, nets), dim3(kHidden), 0, st, (const float*)n->d_fc1part, fc1_splits, rows,
+                           n->d_h4[0], n->d_h4[1], w[0] + lt.off[4], w[1] + lt.off[4], n->d_q[0], n->d_q[1], n->A,
+                           td));
   B2_PROF(td.enable ? "head(fc2+td+fc2_bwd)" : "fc2_fwd", st);
   return B200DQN_OK;
 }
@@ -323,9 +327,8 @@ static int optimizer_range(b200dqn_net* n, int l0, int l1, int mode, int rows, c
   const float inv_bsz = 1.0f / float(rows * n->world);
   const float lr = float(n->cfg.learning_rate), decay = float(n->cfg.decay_rate);
   const float omd = float(1.0 - n->cfg.decay_rate), eps = 1e-6f;
-  k_optimizer<<<cdiv(e4 - b4, 256), 256, 0, st>>>(lt, n->d_part, n->d_g, n->d_w, n->d_s, b4, e4, mode, inv_bsz, lr,
-                                                  decay, omd, eps);
-  B2_LAUNCH_CHECK();
+  B2_CHECK_CUDA(launch_pdl(k_optimizer, dim3(cdiv(e4 - b4, 256)), dim3(256), 0, st, lt, (const float*)n->d_part, n->d_g,
+                           n->d_w, n->d_s, b4, e4, mode, inv_bsz, lr, decay, omd, eps));
   B2_PROF(label, st);
   if (mode & 4) return umma_pack_layers(n, 0, l0, l1, st);   // refresh the fp16 tile images of the updated layers
   return B200DQN_OK;

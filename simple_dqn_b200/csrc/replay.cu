@@ -67,6 +67,8 @@ k_sample(uint32_t* __restrict__ mt_state, const uint8_t* __restrict__ terminals,
   __shared__ int s_cut;
   const int tid = threadIdx.x;
   const int lane = tid & 31, wid = tid >> 5;
+  pdl_launch_dependents();
+  pdl_wait();
 
   for (int i = tid; i < kMtN + 1; i += kSampleThreads) mt[i] = mt_state[i];
   __syncthreads();
@@ -142,9 +144,8 @@ k_sample(uint32_t* __restrict__ mt_state, const uint8_t* __restrict__ terminals,
 }
 
 int launch_sample(b200dqn_replay* r, cudaStream_t st) {
-  k_sample<<<1, kSampleThreads, 0, st>>>(r->d_mt, r->d_terminals, r->d_cursor, r->hist, r->batch, r->d_idx,
-                                         r->d_words);
-  B2_LAUNCH_CHECK();
+  B2_CHECK_CUDA(launch_pdl(k_sample, dim3(1), dim3(kSampleThreads), 0, st, r->d_mt, (const uint8_t*)r->d_terminals,
+                           (const int64_t*)r->d_cursor, r->hist, r->batch, r->d_idx, r->d_words));
   B2_PROF("sample", st);
   return B200DQN_OK;
 }

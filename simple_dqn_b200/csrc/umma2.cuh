@@ -134,6 +134,7 @@ __global__ void __launch_bounds__(kThreads2, 1) k_umma2(const P p, const int tra
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int z = blockIdx.z;
   const bool trace = trace_in && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+  pdl_launch_dependents();
   B2_TRACE(tid == 0, 0);
   const int M = p.M(z), N = p.N(z);
   const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * BN;
@@ -160,6 +161,7 @@ __global__ void __launch_bounds__(kThreads2, 1) k_umma2(const P p, const int tra
   umma::fence_before_sync();
   __syncthreads();
   umma::fence_after_sync();
+  pdl_wait();   // everything above overlapped the previous kernel; from here on we read its outputs
   B2_TRACE(tid == 0, 1);
   const uint32_t tmem = s_tmem;
 
@@ -368,8 +370,7 @@ static int launch_umma2(const char* label, const P& p, int M, int N, int Z, cuda
   dim3 grid((M + kBM - 1) / kBM, (N + C::BN - 1) / C::BN, Z);
   static const char* trace_label = getenv("B200DQN_TRACE_LABEL");
   const int trace = (trace_label && strcmp(trace_label, label) == 0) ? 1 : 0;
-  k_umma2<P><<<grid, kThreads2, C::kSmemBytes, st>>>(p, trace);
-  B2_LAUNCH_CHECK();
+  B2_CHECK_CUDA(launch_pdl(k_umma2<P>, grid, dim3(kThreads2), C::kSmemBytes, st, p, trace));
   B2_PROF(label, st);
   return B200DQN_OK;
 }
@@ -385,6 +386,8 @@ __global__ void __launch_bounds__(256) k_pack_image(const S src, uint8_t* __rest
   const int64_t chunks_per_tile_kb = int64_t(rows) * 8;
   const int64_t total = int64_t(src.tiles()) * nkb * chunks_per_tile_kb;
   const int64_t id = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  pdl_launch_dependents();
+  pdl_wait();
   if (id >= total) return;
   const int64_t tk = id / chunks_per_tile_kb;
   const int within = int(id % chunks_per_tile_kb);
@@ -403,8 +406,7 @@ __global__ void __launch_bounds__(256) k_pack_image(const S src, uint8_t* __rest
 template <class S>
 static int launch_pack(const char* label, const S& src, uint8_t* image, cudaStream_t st) {
   const int64_t total = int64_t(src.tiles()) * src.kblocks() * src.rows() * 8;
-  k_pack_image<S><<<unsigned((total + 255) / 256), 256, 0, st>>>(src, image);
-  B2_LAUNCH_CHECK();
+  B2_CHECK_CUDA(launch_pdl(k_pack_image<S>, dim3(unsigned((total + 255) / 256)), dim3(256), 0, st, src, image));
   B2_PROF(label, st);
   return B200DQN_OK;
 }

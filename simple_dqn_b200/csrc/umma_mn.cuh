@@ -77,6 +77,7 @@ __global__ void __launch_bounds__(kThreads2, 1) k_umma_mn(const P p) {
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int z = blockIdx.z;
+  pdl_launch_dependents();
   const int M = p.M(z), N = p.N(z);
   const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * BN;
   if (m0 >= M || n0 >= N) return;
@@ -100,6 +101,7 @@ __global__ void __launch_bounds__(kThreads2, 1) k_umma_mn(const P p) {
   umma::fence_before_sync();
   __syncthreads();
   umma::fence_after_sync();
+  pdl_wait();
   const uint32_t tmem = s_tmem;
 
   if (nkb <= 0) {
@@ -249,8 +251,7 @@ static int launch_umma_mn(const char* label, const P& p, int M, int N, int Z, cu
     configured = true;
   }
   dim3 grid((M + kBM - 1) / kBM, (N + C::BN - 1) / C::BN, Z);
-  k_umma_mn<P><<<grid, kThreads2, C::kSmemBytes, st>>>(p);
-  B2_LAUNCH_CHECK();
+  B2_CHECK_CUDA(launch_pdl(k_umma_mn<P>, grid, dim3(kThreads2), C::kSmemBytes, st, p));
   B2_PROF(label, st);
   return B200DQN_OK;
 }
