@@ -72,6 +72,12 @@ int b200dqn_stream_synchronize(int device, void* stream);
 int b200dqn_profile_begin(int device, void* stream);
 int b200dqn_profile_end(int max_entries, char* names32, float* ms, int* count);
 
+/* In-graph kernel timeline: arm, run ONE fused step (train_fused re-captures its graph with timing
+ * slots), then read [label, first CTA start, last CTA end] (GPU %globaltimer, ns) per launch. */
+int b200dqn_ktrace_begin(int device);
+int b200dqn_ktrace_end(int max_entries, char* names32, unsigned long long* start_ns, unsigned long long* end_ns,
+                       int* count);
+
 /* ------------------------------------------------------------------ replay ring --------- */
 
 /* ReplayMemory.__init__(size, args)  — src/replay_memory.py:7-24.

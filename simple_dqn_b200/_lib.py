@@ -45,6 +45,8 @@ SIGNATURES = {
     "b200dqn_stream_create": [C.c_int, C.POINTER(_P)],
     "b200dqn_stream_destroy": [C.c_int, _P],
     "b200dqn_stream_synchronize": [C.c_int, _P],
+    "b200dqn_ktrace_begin": [C.c_int],
+    "b200dqn_ktrace_end": [C.c_int, _P, _P, _P, C.POINTER(C.c_int)],
     "b200dqn_profile_begin": [C.c_int, _P],
     "b200dqn_profile_end": [C.c_int, _P, _P, C.POINTER(C.c_int)],
     "b200dqn_replay_create": [C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_P)],
@@ -210,3 +212,19 @@ class Stream:
                 load().b200dqn_stream_destroy(self.device, C.c_void_p(h))
             except Exception:
                 pass
+
+
+def ktrace_begin(device=0):
+    call("b200dqn_ktrace_begin", device)
+
+
+def ktrace_end(max_entries=128):
+    """[(label, start_ns, end_ns)] of every instrumented launch since ktrace_begin (GPU globaltimer)."""
+    import numpy as np
+    names = C.create_string_buffer(max_entries * 32)
+    st = np.zeros(max_entries, dtype=np.uint64)
+    en = np.zeros(max_entries, dtype=np.uint64)
+    n = C.c_int()
+    call("b200dqn_ktrace_end", max_entries, names, np_ptr(st), np_ptr(en), C.byref(n))
+    raw = names.raw
+    return [(raw[i * 32:(i + 1) * 32].split(b"\0")[0].decode(), int(st[i]), int(en[i])) for i in range(n.value)]

@@ -26,6 +26,25 @@ struct Prof {
 } g_prof;
 }  // namespace
 
+int g_ktrace_gen = 0;
+namespace {
+constexpr int kKtCap = 128;
+struct KtState {
+  unsigned long long* d_buf = nullptr;
+  bool on = false;
+  int n = 0;
+  char names[kKtCap][32];
+} g_kt;
+}  // namespace
+
+KTrace ktrace_slot(const char* label) {
+  if (!g_kt.on || g_kt.n >= kKtCap) return KTrace{nullptr, 0};
+  const int slot = g_kt.n++;
+  strncpy(g_kt.names[slot], label, 31);
+  g_kt.names[slot][31] = 0;
+  return KTrace{g_kt.d_buf, slot};
+}
+
 void prof_mark(const char* label, cudaStream_t st) {
   if (g_prof.n >= kProfCap) return;
   const int i = ++g_prof.n;
@@ -126,5 +145,37 @@ extern "C" int b200dqn_stream_destroy(int device, void* stream) {
 extern "C" int b200dqn_stream_synchronize(int device, void* stream) {
   b200::DeviceGuard g(device);
   B2_CHECK_CUDA(cudaStreamSynchronize(b200::as_stream(stream)));
+  return B200DQN_OK;
+}
+
+extern "C" int b200dqn_ktrace_begin(int device) {
+  using namespace b200;
+  DeviceGuard g(device);
+  if (!g_kt.d_buf) B2_CHECK_CUDA(cudaMalloc(&g_kt.d_buf, kKtCap * 2 * sizeof(unsigned long long)));
+  unsigned long long init[kKtCap * 2];
+  for (int i = 0; i < kKtCap; ++i) { init[2 * i] = ~0ull; init[2 * i + 1] = 0ull; }
+  B2_CHECK_CUDA(cudaMemcpy(g_kt.d_buf, init, sizeof(init), cudaMemcpyHostToDevice));
+  g_kt.n = 0;
+  g_kt.on = true;
+  ++g_ktrace_gen;
+  return B200DQN_OK;
+}
+
+extern "C" int b200dqn_ktrace_end(int max_entries, char* names32, unsigned long long* start_ns,
+                                  unsigned long long* end_ns, int* count) {
+  using namespace b200;
+  B2_REQUIRE(names32 && start_ns && end_ns && count, B200DQN_EINVAL, "ktrace_end: null argument");
+  B2_CHECK_CUDA(cudaDeviceSynchronize());
+  g_kt.on = false;
+  ++g_ktrace_gen;
+  unsigned long long host[kKtCap * 2];
+  B2_CHECK_CUDA(cudaMemcpy(host, g_kt.d_buf, sizeof(host), cudaMemcpyDeviceToHost));
+  const int n = g_kt.n < max_entries ? g_kt.n : max_entries;
+  for (int i = 0; i < n; ++i) {
+    memcpy(names32 + i * 32, g_kt.names[i], 32);
+    start_ns[i] = host[2 * i];
+    end_ns[i] = host[2 * i + 1];
+  }
+  *count = n;
   return B200DQN_OK;
 }

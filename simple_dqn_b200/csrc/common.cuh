@@ -54,8 +54,29 @@ extern bool g_prof_on;
     if (::b200::g_prof_on) ::b200::prof_mark(label, st); \
   } while (0)
 
+// In-graph kernel timeline (b200dqn_ktrace_begin/_end): when armed, every instrumented launch gets a
+// slot; each CTA's thread 0 folds its %globaltimer into [min start, max end] of that slot.  Unlike the
+// event profiler this works inside the replayed CUDA graph with all branches and PDL overlap live.
+struct KTrace {
+  unsigned long long* buf;   // [slot][2] = {start_ns, end_ns}; nullptr = off
+  int slot;
+};
+KTrace ktrace_slot(const char* label);   // host: slot for this launch (registers the label), {nullptr,0} when off
+extern int g_ktrace_gen;                 // bumped whenever tracing is switched, invalidates captured graphs
+
 // ---------------------------------------------------------------- device-side PTX helpers
 #ifdef __CUDACC__
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void kt_begin(const KTrace& kt) {
+  if (kt.buf && threadIdx.x == 0) atomicMin(kt.buf + 2 * kt.slot, globaltimer_ns());
+}
+__device__ __forceinline__ void kt_end(const KTrace& kt) {
+  if (kt.buf && threadIdx.x == 0) atomicMax(kt.buf + 2 * kt.slot + 1, globaltimer_ns());
+}
 extern bool g_use_pdl;   // B200DQN_NO_PDL unset
 
 // Launch `kernel` with the programmatic-dependent-launch attribute (every kernel launched this way

@@ -44,11 +44,12 @@ struct HeadTrainArgs {
 __global__ void __launch_bounds__(kHidden)
 k_head(const float* __restrict__ part, int splits, int rows, float* h4_online, float* h4_target,
        const float* __restrict__ w5_online, const float* __restrict__ w5_target, float* q_online,
-       float* q_target, int A, const HeadTrainArgs td) {
+       float* q_target, int A, const HeadTrainArgs td, const KTrace kt) {
   __shared__ float red[kHidden / 32][kMaxActions];
   __shared__ int s_last;
   const int b = blockIdx.x, z = blockIdx.y, t = threadIdx.x;
   pdl_launch_dependents();
+  kt_begin(kt);
   pdl_wait();
   float h = 0.f;
   for (int s = 0; s < splits; ++s) h += part[((z * splits + s) * rows + b) * kHidden + t];
@@ -68,6 +69,7 @@ k_head(const float* __restrict__ part, int splits, int rows, float* h4_online, f
     for (int wI = 0; wI < kHidden / 32; ++wI) v += red[wI][t];
     (z ? q_target : q_online)[b * A + t] = v;
   }
+  kt_end(kt);
   if (!td.enable) return;
 
   // ---- the second CTA of the (online, target) pair of row b to get here owns that row's TD + fc2 backward
@@ -110,6 +112,7 @@ k_head(const float* __restrict__ part, int splits, int rows, float* h4_online, f
     float* dw = td.dw5_rows + (int64_t(b) * kHidden + t) * A;        // per-row partial, summed by the optimizer
     for (int j = 0; j < A; ++j) dw[j] = (j == a) ? hv * d : 0.f;
   }
+  kt_end(kt);
   // ---- the last row to finish publishes the batch-mean cost and re-arms the tickets
   __threadfence();
   __syncthreads();
@@ -125,6 +128,7 @@ k_head(const float* __restrict__ part, int splits, int rows, float* h4_online, f
     *td.step = sidx + 1;
   }
   for (int i = t; i <= rows; i += kHidden) td.ticket[i] = 0;
+  kt_end(kt);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -139,9 +143,10 @@ k_head(const float* __restrict__ part, int splits, int rows, float* h4_online, f
 __global__ void __launch_bounds__(256)
 k_optimizer(const LayerTable lt, const float* __restrict__ part, float* __restrict__ g_buf, float* __restrict__ w,
             float* __restrict__ s, int64_t b4, int64_t e4, int mode, float inv_bsz, float lr, float decay,
-            float one_m_decay, float eps) {
+            float one_m_decay, float eps, const KTrace kt) {
   const int64_t i4 = b4 + blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
   pdl_launch_dependents();
+  kt_begin(kt);
   pdl_wait();
   if (i4 >= e4) return;
   const int64_t i = i4 * 4;
@@ -187,6 +192,7 @@ k_optimizer(const LayerTable lt, const float* __restrict__ part, float* __restri
     *reinterpret_cast<float4*>(w + i) = wv;
     *reinterpret_cast<float4*>(s + i) = sv;
   }
+  kt_end(kt);
 }
 
 __global__ void k_iota(int32_t* a, int32_t* b, int n, int mult) {
@@ -264,7 +270,7 @@ static int forward(b200dqn_net* n, const FrameSource& fs, int nets, int rows, cu
   const int fc1_splits = n->cfg.math_mode == B200DQN_MATH_TCGEN05 ? umma_fc1_splits() : kFc1Splits;
   B2_CHECK_CUDA(launch_pdl(k_head, dim3(rows, nets), dim3(kHidden), 0, st, (const float*)n->d_fc1part, fc1_splits, rows,
                            n->d_h4[0], n->d_h4[1], w[0] + lt.off[4], w[1] + lt.off[4], n->d_q[0], n->d_q[1], n->A,
-                           td));
+                           td, ktrace_slot("head")));
   B2_PROF(td.enable ? "head(fc2+td+fc2_bwd)" : "fc2_fwd", st);
   return B200DQN_OK;
 }
@@ -328,7 +334,7 @@ static int optimizer_range(b200dqn_net* n, int l0, int l1, int mode, int rows, c
   const float lr = float(n->cfg.learning_rate), decay = float(n->cfg.decay_rate);
   const float omd = float(1.0 - n->cfg.decay_rate), eps = 1e-6f;
   B2_CHECK_CUDA(launch_pdl(k_optimizer, dim3(cdiv(e4 - b4, 256)), dim3(256), 0, st, lt, (const float*)n->d_part, n->d_g,
-                           n->d_w, n->d_s, b4, e4, mode, inv_bsz, lr, decay, omd, eps));
+                           n->d_w, n->d_s, b4, e4, mode, inv_bsz, lr, decay, omd, eps, ktrace_slot(label)));
   B2_PROF(label, st);
   if (mode & 4) return umma_pack_layers(n, 0, l0, l1, st);   // refresh the fp16 tile images of the updated layers
   return B200DQN_OK;
@@ -375,21 +381,21 @@ static int backward_and_update(b200dqn_net* n, const FrameSource& fs, int rows, 
   B2_TRY(bwd_op(n, fs, rows, kFc1Dgrad, st));
   B2_CHECK_CUDA(cudaEventRecord(ev[1], st));                 // dZ3 ready, W4 no longer needed
   B2_CHECK_CUDA(cudaStreamWaitEvent(sA, ev[1], 0));
-  B2_TRY(optimizer_range(n, 3, 4, 1 | 4, rows, sA, "optimizer"));
+  B2_TRY(optimizer_range(n, 3, 4, 1 | 4, rows, sA, "opt_fc"));
   B2_CHECK_CUDA(cudaStreamWaitEvent(sB, ev[1], 0));
   B2_TRY(bwd_op(n, fs, rows, kConv3Wgrad, sB));
   B2_TRY(bwd_op(n, fs, rows, kConv3Dgrad, st));
   B2_CHECK_CUDA(cudaEventRecord(ev[2], st));                 // dZ2 ready, W3 no longer needed
   B2_CHECK_CUDA(cudaStreamWaitEvent(sB, ev[2], 0));
-  B2_TRY(optimizer_range(n, 2, 2, 1 | 4, rows, sB, "optimizer"));
+  B2_TRY(optimizer_range(n, 2, 2, 1 | 4, rows, sB, "opt_conv3"));
   B2_CHECK_CUDA(cudaStreamWaitEvent(sC, ev[2], 0));
   B2_TRY(bwd_op(n, fs, rows, kConv2Wgrad, sC));
   B2_TRY(bwd_op(n, fs, rows, kConv2Dgrad, st));
   B2_CHECK_CUDA(cudaEventRecord(ev[3], st));                 // dZ1 ready, W2 no longer needed
   B2_CHECK_CUDA(cudaStreamWaitEvent(sC, ev[3], 0));
-  B2_TRY(optimizer_range(n, 1, 1, 1 | 4, rows, sC, "optimizer"));
+  B2_TRY(optimizer_range(n, 1, 1, 1 | 4, rows, sC, "opt_conv2"));
   B2_TRY(bwd_op(n, fs, rows, kConv1Wgrad, st));
-  B2_TRY(optimizer_range(n, 0, 0, 1 | 4, rows, st, "optimizer"));
+  B2_TRY(optimizer_range(n, 0, 0, 1 | 4, rows, st, "opt_conv1"));
   B2_CHECK_CUDA(cudaEventRecord(ev[4], sA));
   B2_CHECK_CUDA(cudaEventRecord(ev[5], sB));
   B2_CHECK_CUDA(cudaEventRecord(ev[6], sC));
@@ -760,7 +766,8 @@ extern "C" int b200dqn_net_train_fused(b200dqn_net* n, b200dqn_replay* r, int ns
   // and replayed: one graph launch per step instead of ~17 stream operations.
   const bool use_graph = n->use_graph && !g_prof_on && st != nullptr;
   if (use_graph) {
-    if (!n->graph_exec || n->graph_replay != r || n->graph_stream != st || n->graph_world != n->world) {
+    if (!n->graph_exec || n->graph_replay != r || n->graph_stream != st || n->graph_world != n->world ||
+        n->graph_trace_gen != g_ktrace_gen) {
       if (n->graph_exec) { cudaGraphExecDestroy(n->graph_exec); n->graph_exec = nullptr; }
       cudaGraph_t graph = nullptr;
       B2_CHECK_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
@@ -771,7 +778,7 @@ extern "C" int b200dqn_net_train_fused(b200dqn_net* n, b200dqn_replay* r, int ns
       B2_CHECK_CUDA(e);
       B2_CHECK_CUDA(cudaGraphInstantiate(&n->graph_exec, graph, 0));
       cudaGraphDestroy(graph);
-      n->graph_replay = r; n->graph_stream = st; n->graph_world = n->world;
+      n->graph_replay = r; n->graph_stream = st; n->graph_world = n->world; n->graph_trace_gen = g_ktrace_gen;
     }
     for (int i = 0; i < nsteps; ++i) B2_CHECK_CUDA(cudaGraphLaunch(n->graph_exec, st));
   } else {
@@ -835,7 +842,7 @@ extern "C" int b200dqn_net_get_grads(b200dqn_net* n, int layer, float* host_dW, 
   const int64_t n4 = n->n_params / 4;
   if (n->world == 1) {  // partials of the last step are still in scratch; sum them into d_g
     k_optimizer<<<cdiv(n4, 256), 256, 0, st>>>(n->lt, n->d_part, n->d_g, n->d_w, n->d_s, 0, n4, 1 | 2, 0.f, 0.f, 0.f,
-                                               0.f, 0.f);
+                                               0.f, 0.f, KTrace{nullptr, 0});
     B2_LAUNCH_CHECK();
   }
   return xfer_params(n, n->d_g, layer, host_dW, false, st);

@@ -69,6 +69,7 @@ struct b200dqn_net {
   b200dqn_replay* graph_replay = nullptr;
   cudaStream_t graph_stream = nullptr;
   int graph_world = 0;
+  int graph_trace_gen = 0;
 
   void* umma_state = nullptr;  // tcgen05 engine: fp16 operand planes + weight tile images (net_umma.cu)
 

@@ -693,20 +693,20 @@ int umma_pack_layers(b200dqn_net* n, int which, int l0, int l1, cudaStream_t st)
   int rc = 0;
   for (int l = l0; l <= l1 && !rc; ++l) {
     switch (l) {
-      case 0: rc = umma2::launch_pack("pack", PackFwdConv<kK1, kC1>{w + lt.off[0]}, u->img_fwd[which][0], st); break;
+      case 0: rc = umma2::launch_pack("pack_c1", PackFwdConv<kK1, kC1>{w + lt.off[0]}, u->img_fwd[which][0], st); break;
       case 1:
-        rc = umma2::launch_pack("pack", PackFwdConv<kK2, kC2>{w + lt.off[1]}, u->img_fwd[which][1], st);
+        rc = umma2::launch_pack("pack_c2f", PackFwdConv<kK2, kC2>{w + lt.off[1]}, u->img_fwd[which][1], st);
         if (!rc && !which)
-          rc = umma2::launch_pack("pack", PackConvDgrad<kP1, kC1, 4, 2, kC2>{w + lt.off[1]}, u->img_dgr[2], st);
+          rc = umma2::launch_pack("pack_c2d", PackConvDgrad<kP1, kC1, 4, 2, kC2>{w + lt.off[1]}, u->img_dgr[2], st);
         break;
       case 2:
-        rc = umma2::launch_pack("pack", PackFwdConv<kK3, kC3>{w + lt.off[2]}, u->img_fwd[which][2], st);
+        rc = umma2::launch_pack("pack_c3f", PackFwdConv<kK3, kC3>{w + lt.off[2]}, u->img_fwd[which][2], st);
         if (!rc && !which)
-          rc = umma2::launch_pack("pack", PackConvDgrad<kP2, kC2, 3, 1, kC3>{w + lt.off[2]}, u->img_dgr[1], st);
+          rc = umma2::launch_pack("pack_c3d", PackConvDgrad<kP2, kC2, 3, 1, kC3>{w + lt.off[2]}, u->img_dgr[1], st);
         break;
       case 3:
-        rc = umma2::launch_pack("pack", PackFc1Fwd{w + lt.off[3]}, u->img_fwd[which][3], st);
-        if (!rc && !which) rc = umma2::launch_pack("pack", PackFc1Dgrad{w + lt.off[3]}, u->img_dgr[0], st);
+        rc = umma2::launch_pack("pack_fc1f", PackFc1Fwd{w + lt.off[3]}, u->img_fwd[which][3], st);
+        if (!rc && !which) rc = umma2::launch_pack("pack_fc1d", PackFc1Dgrad{w + lt.off[3]}, u->img_dgr[0], st);
         break;
       default: break;  // fc2 runs on CUDA cores (N = A <= 18)
     }

@@ -61,13 +61,14 @@ constexpr int kSampleThreads = 256;
 __global__ void __launch_bounds__(kSampleThreads, 1)
 k_sample(uint32_t* __restrict__ mt_state, const uint8_t* __restrict__ terminals,
          const int64_t* __restrict__ cursor, int hist, int batch, int32_t* __restrict__ idx_out,
-         uint32_t* __restrict__ words_out) {
+         uint32_t* __restrict__ words_out, const KTrace kt) {
   __shared__ uint32_t mt[kMtN + 1];
   __shared__ int warp_cnt[kSampleThreads / 32];
   __shared__ int s_cut;
   const int tid = threadIdx.x;
   const int lane = tid & 31, wid = tid >> 5;
   pdl_launch_dependents();
+  kt_begin(kt);
   pdl_wait();
 
   for (int i = tid; i < kMtN + 1; i += kSampleThreads) mt[i] = mt_state[i];
@@ -141,11 +142,12 @@ k_sample(uint32_t* __restrict__ mt_state, const uint8_t* __restrict__ terminals,
     words_out[0] = words;
     words_out[1] += words;
   }
+  kt_end(kt);
 }
 
 int launch_sample(b200dqn_replay* r, cudaStream_t st) {
   B2_CHECK_CUDA(launch_pdl(k_sample, dim3(1), dim3(kSampleThreads), 0, st, r->d_mt, (const uint8_t*)r->d_terminals,
-                           (const int64_t*)r->d_cursor, r->hist, r->batch, r->d_idx, r->d_words));
+                           (const int64_t*)r->d_cursor, r->hist, r->batch, r->d_idx, r->d_words, ktrace_slot("sample")));
   B2_PROF("sample", st);
   return B200DQN_OK;
 }

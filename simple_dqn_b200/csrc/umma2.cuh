@@ -121,7 +121,7 @@ constexpr int kThreads2 = kLoadThreads + 32; // warp 8: MMA issuer
 //             the hi and lo weight tiles are adjacent in shared memory)  and  acc1 += A_lo x B_hi;
 //             tcgen05.commit -> empty[s]
 template <class P>
-__global__ void __launch_bounds__(kThreads2, 1) k_umma2(const P p, const int trace_in) {
+__global__ void __launch_bounds__(kThreads2, 1) k_umma2(const P p, const int trace_in, const KTrace kt) {
   using C = Cfg2<P>;
   constexpr int BN = C::BN;
   constexpr int S = C::kStages;
@@ -135,6 +135,7 @@ __global__ void __launch_bounds__(kThreads2, 1) k_umma2(const P p, const int tra
   const int z = blockIdx.z;
   const bool trace = trace_in && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
   pdl_launch_dependents();
+  kt_begin(kt);
   B2_TRACE(tid == 0, 0);
   const int M = p.M(z), N = p.N(z);
   const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * BN;
@@ -351,6 +352,7 @@ __global__ void __launch_bounds__(kThreads2, 1) k_umma2(const P p, const int tra
     umma::fence_after_sync();
     umma::tmem_dealloc(tmem, C::kTmemCols);
   }
+  kt_end(kt);
   B2_TRACE(tid == 0, 6);
 }
 
@@ -370,7 +372,7 @@ static int launch_umma2(const char* label, const P& p, int M, int N, int Z, cuda
   dim3 grid((M + kBM - 1) / kBM, (N + C::BN - 1) / C::BN, Z);
   static const char* trace_label = getenv("B200DQN_TRACE_LABEL");
   const int trace = (trace_label && strcmp(trace_label, label) == 0) ? 1 : 0;
-  B2_CHECK_CUDA(launch_pdl(k_umma2<P>, grid, dim3(kThreads2), C::kSmemBytes, st, p, trace));
+  B2_CHECK_CUDA(launch_pdl(k_umma2<P>, grid, dim3(kThreads2), C::kSmemBytes, st, p, trace, ktrace_slot(label)));
   B2_PROF(label, st);
   return B200DQN_OK;
 }
@@ -381,7 +383,8 @@ static int launch_umma2(const char* label, const P& p, int M, int N, int Z, cuda
 // image layout: [tile][kb][hi rows*128 B | lo rows*128 B], chunk (r, c) at sw128_off(r, c).
 // ------------------------------------------------------------------------------------------
 template <class S>
-__global__ void __launch_bounds__(256) k_pack_image(const S src, uint8_t* __restrict__ image) {
+__global__ void __launch_bounds__(256) k_pack_image(const S src, uint8_t* __restrict__ image, const KTrace kt) {
+  kt_begin(kt);
   const int rows = src.rows(), nkb = src.kblocks();
   const int64_t chunks_per_tile_kb = int64_t(rows) * 8;
   const int64_t total = int64_t(src.tiles()) * nkb * chunks_per_tile_kb;
@@ -401,12 +404,13 @@ __global__ void __launch_bounds__(256) k_pack_image(const S src, uint8_t* __rest
   uint8_t* base = image + tk * (int64_t(rows) * 256);
   *reinterpret_cast<uint4*>(base + umma::sw128_off(r, c)) = hi;
   *reinterpret_cast<uint4*>(base + int64_t(rows) * 128 + umma::sw128_off(r, c)) = lo;
+  kt_end(kt);
 }
 
 template <class S>
 static int launch_pack(const char* label, const S& src, uint8_t* image, cudaStream_t st) {
   const int64_t total = int64_t(src.tiles()) * src.kblocks() * src.rows() * 8;
-  B2_CHECK_CUDA(launch_pdl(k_pack_image<S>, dim3(unsigned((total + 255) / 256)), dim3(256), 0, st, src, image));
+  B2_CHECK_CUDA(launch_pdl(k_pack_image<S>, dim3(unsigned((total + 255) / 256)), dim3(256), 0, st, src, image, ktrace_slot(label)));
   B2_PROF(label, st);
   return B200DQN_OK;
 }

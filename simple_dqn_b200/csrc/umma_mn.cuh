@@ -65,7 +65,7 @@ struct CfgMN {
 };
 
 template <class P>
-__global__ void __launch_bounds__(kThreads2, 1) k_umma_mn(const P p) {
+__global__ void __launch_bounds__(kThreads2, 1) k_umma_mn(const P p, const KTrace kt) {
   using C = CfgMN<P>;
   constexpr int BN = C::BN;
   constexpr int S = C::kStages;
@@ -78,6 +78,7 @@ __global__ void __launch_bounds__(kThreads2, 1) k_umma_mn(const P p) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int z = blockIdx.z;
   pdl_launch_dependents();
+  kt_begin(kt);
   const int M = p.M(z), N = p.N(z);
   const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * BN;
   if (m0 >= M || n0 >= N) return;
@@ -240,6 +241,7 @@ __global__ void __launch_bounds__(kThreads2, 1) k_umma_mn(const P p) {
     umma::fence_after_sync();
     umma::tmem_dealloc(tmem, C::kTmemCols);
   }
+  kt_end(kt);
 }
 
 template <class P>
@@ -251,7 +253,7 @@ static int launch_umma_mn(const char* label, const P& p, int M, int N, int Z, cu
     configured = true;
   }
   dim3 grid((M + kBM - 1) / kBM, (N + C::BN - 1) / C::BN, Z);
-  B2_CHECK_CUDA(launch_pdl(k_umma_mn<P>, grid, dim3(kThreads2), C::kSmemBytes, st, p));
+  B2_CHECK_CUDA(launch_pdl(k_umma_mn<P>, grid, dim3(kThreads2), C::kSmemBytes, st, p, ktrace_slot(label)));
   B2_PROF(label, st);
   return B200DQN_OK;
 }
