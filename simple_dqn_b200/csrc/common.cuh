@@ -81,6 +81,16 @@ extern bool g_use_pdl;   // B200DQN_NO_PDL unset
 
 // Launch `kernel` with the programmatic-dependent-launch attribute (every kernel launched this way
 // calls pdl_wait() before it touches data produced by earlier kernels).
+// Side-branch launches (wgrad / optimizer / pack off the critical path) run inside this scope: they
+// must NOT start early — an early-launched 200-CTA wgrad parks on every SM at its pdl_wait() and
+// starves the critical-path kernels of shared memory — so they get ordinary full dependencies.
+extern thread_local bool g_pdl_suppressed;
+struct NoPdlScope {
+  bool prev;
+  NoPdlScope() : prev(g_pdl_suppressed) { g_pdl_suppressed = true; }
+  ~NoPdlScope() { g_pdl_suppressed = prev; }
+};
+
 template <class... KArgs, class... Args>
 static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
                                      Args&&... args) {
@@ -93,7 +103,7 @@ static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 b
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = g_use_pdl ? 1 : 0;
+  cfg.numAttrs = (g_use_pdl && !g_pdl_suppressed) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

@@ -377,23 +377,23 @@ static int backward_and_update(b200dqn_net* n, const FrameSource& fs, int rows, 
   cudaEvent_t* ev = n->ev;
   B2_CHECK_CUDA(cudaEventRecord(ev[0], st));                 // dZ4 ready
   B2_CHECK_CUDA(cudaStreamWaitEvent(sA, ev[0], 0));
-  B2_TRY(bwd_op(n, fs, rows, kFc1Wgrad, sA));
+  { NoPdlScope side; B2_TRY(bwd_op(n, fs, rows, kFc1Wgrad, sA)); }
   B2_TRY(bwd_op(n, fs, rows, kFc1Dgrad, st));
   B2_CHECK_CUDA(cudaEventRecord(ev[1], st));                 // dZ3 ready, W4 no longer needed
   B2_CHECK_CUDA(cudaStreamWaitEvent(sA, ev[1], 0));
-  B2_TRY(optimizer_range(n, 3, 4, 1 | 4, rows, sA, "opt_fc"));
+  { NoPdlScope side; B2_TRY(optimizer_range(n, 3, 4, 1 | 4, rows, sA, "opt_fc")); }
   B2_CHECK_CUDA(cudaStreamWaitEvent(sB, ev[1], 0));
-  B2_TRY(bwd_op(n, fs, rows, kConv3Wgrad, sB));
+  { NoPdlScope side; B2_TRY(bwd_op(n, fs, rows, kConv3Wgrad, sB)); }
   B2_TRY(bwd_op(n, fs, rows, kConv3Dgrad, st));
   B2_CHECK_CUDA(cudaEventRecord(ev[2], st));                 // dZ2 ready, W3 no longer needed
   B2_CHECK_CUDA(cudaStreamWaitEvent(sB, ev[2], 0));
-  B2_TRY(optimizer_range(n, 2, 2, 1 | 4, rows, sB, "opt_conv3"));
+  { NoPdlScope side; B2_TRY(optimizer_range(n, 2, 2, 1 | 4, rows, sB, "opt_conv3")); }
   B2_CHECK_CUDA(cudaStreamWaitEvent(sC, ev[2], 0));
-  B2_TRY(bwd_op(n, fs, rows, kConv2Wgrad, sC));
+  { NoPdlScope side; B2_TRY(bwd_op(n, fs, rows, kConv2Wgrad, sC)); }
   B2_TRY(bwd_op(n, fs, rows, kConv2Dgrad, st));
   B2_CHECK_CUDA(cudaEventRecord(ev[3], st));                 // dZ1 ready, W2 no longer needed
   B2_CHECK_CUDA(cudaStreamWaitEvent(sC, ev[3], 0));
-  B2_TRY(optimizer_range(n, 1, 1, 1 | 4, rows, sC, "opt_conv2"));
+  { NoPdlScope side; B2_TRY(optimizer_range(n, 1, 1, 1 | 4, rows, sC, "opt_conv2")); }
   B2_TRY(bwd_op(n, fs, rows, kConv1Wgrad, st));
   B2_TRY(optimizer_range(n, 0, 0, 1 | 4, rows, st, "opt_conv1"));
   B2_CHECK_CUDA(cudaEventRecord(ev[4], sA));
@@ -559,7 +559,11 @@ extern "C" int b200dqn_net_create(int device, const b200dqn_net_config* cfg, b20
   B2_LAUNCH_CHECK();
   n->pin_bytes = 2 * state_bytes + size_t(nb) * 16 + size_t(nb) * A * sizeof(float) + 256;
   B2_CHECK_CUDA(cudaMallocHost(&n->h_pin, n->pin_bytes));
-  for (auto& sd : n->side) B2_CHECK_CUDA(cudaStreamCreateWithFlags(&sd, cudaStreamNonBlocking));
+  {
+    int prio_lo = 0, prio_hi = 0;   // numerically larger = lower priority
+    B2_CHECK_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    for (auto& sd : n->side) B2_CHECK_CUDA(cudaStreamCreateWithPriority(&sd, cudaStreamNonBlocking, prio_lo));
+  }
   for (auto& e : n->ev) B2_CHECK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   n->use_graph = getenv("B200DQN_NO_GRAPH") == nullptr;
   n->use_branches = getenv("B200DQN_NO_BRANCHES") == nullptr;
