@@ -48,9 +48,9 @@ k_head(const float* __restrict__ part, int splits, int rows, float* h4_online, f
   __shared__ float red[kHidden / 32][kMaxActions];
   __shared__ int s_last;
   const int b = blockIdx.x, z = blockIdx.y, t = threadIdx.x;
-  pdl_launch_dependents();
   kt_begin(kt);
   pdl_wait();
+  pdl_launch_dependents();
   float h = 0.f;
   for (int s = 0; s < splits; ++s) h += part[((z * splits + s) * rows + b) * kHidden + t];
   h = fmaxf(h, 0.f);
@@ -145,9 +145,9 @@ k_optimizer(const LayerTable lt, const float* __restrict__ part, float* __restri
             float* __restrict__ s, int64_t b4, int64_t e4, int mode, float inv_bsz, float lr, float decay,
             float one_m_decay, float eps, const KTrace kt) {
   const int64_t i4 = b4 + blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
-  pdl_launch_dependents();
   kt_begin(kt);
   pdl_wait();
+  pdl_launch_dependents();
   if (i4 >= e4) return;
   const int64_t i = i4 * 4;
   float4 g;
@@ -157,20 +157,28 @@ k_optimizer(const LayerTable lt, const float* __restrict__ part, float* __restri
     for (int j = 1; j < kLayers; ++j) l += (i >= lt.off[j]) ? 1 : 0;
     const int64_t lsize = lt.off[l + 1] - lt.off[l];
     const float* p = part + lt.part_off[l] + (i - lt.off[l]);
-    g = *reinterpret_cast<const float4*>(p);
+    // Fixed summation tree shared with k_opt_conv (net_umma.cu): eight strided running sums
+    // a[l] = sum_{sp = l (mod 8)} part[sp], combined as ((a0+a1)+(a2+a3)) + ((a4+a5)+(a6+a7)).
     const int nsp = lt.splits[l];
-    int sp = 1;
-    for (; sp + 8 <= nsp; sp += 8) {   // 8 independent loads in flight, summed in fixed order
-      float4 v[8];
+    float4 a[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) v[u] = *reinterpret_cast<const float4*>(p + (sp + u) * lsize);
+    for (int u = 0; u < 8; ++u) a[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int sp0 = 0; sp0 < nsp; sp0 += 8) {
 #pragma unroll
-      for (int u = 0; u < 8; ++u) { g.x += v[u].x; g.y += v[u].y; g.z += v[u].z; g.w += v[u].w; }
+      for (int u = 0; u < 8; ++u) {
+        if (sp0 + u < nsp) {
+          const float4 v = *reinterpret_cast<const float4*>(p + (sp0 + u) * lsize);
+          a[u].x += v.x; a[u].y += v.y; a[u].z += v.z; a[u].w += v.w;
+        }
+      }
     }
-    for (; sp < nsp; ++sp) {
-      const float4 v = *reinterpret_cast<const float4*>(p + sp * lsize);
-      g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w;
-    }
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1)
+#pragma unroll
+      for (int u = 0; u < 8; u += 2 * o) {
+        a[u].x += a[u + o].x; a[u].y += a[u + o].y; a[u].z += a[u + o].z; a[u].w += a[u + o].w;
+      }
+    g = a[0];
   } else {
     g = *reinterpret_cast<const float4*>(g_buf + i);
   }
@@ -387,15 +395,24 @@ static int backward_and_update(b200dqn_net* n, const FrameSource& fs, int rows, 
   B2_TRY(bwd_op(n, fs, rows, kConv3Dgrad, st));
   B2_CHECK_CUDA(cudaEventRecord(ev[2], st));                 // dZ2 ready, W3 no longer needed
   B2_CHECK_CUDA(cudaStreamWaitEvent(sB, ev[2], 0));
-  { NoPdlScope side; B2_TRY(optimizer_range(n, 2, 2, 1 | 4, rows, sB, "opt_conv3")); }
+  {
+    NoPdlScope side;
+    if (n->cfg.math_mode == B200DQN_MATH_TCGEN05) B2_TRY(umma_opt_conv(n, 2, rows, sB, "opt_conv3"));
+    else B2_TRY(optimizer_range(n, 2, 2, 1 | 4, rows, sB, "opt_conv3"));
+  }
   B2_CHECK_CUDA(cudaStreamWaitEvent(sC, ev[2], 0));
   { NoPdlScope side; B2_TRY(bwd_op(n, fs, rows, kConv2Wgrad, sC)); }
   B2_TRY(bwd_op(n, fs, rows, kConv2Dgrad, st));
   B2_CHECK_CUDA(cudaEventRecord(ev[3], st));                 // dZ1 ready, W2 no longer needed
   B2_CHECK_CUDA(cudaStreamWaitEvent(sC, ev[3], 0));
-  { NoPdlScope side; B2_TRY(optimizer_range(n, 1, 1, 1 | 4, rows, sC, "opt_conv2")); }
+  {
+    NoPdlScope side;
+    if (n->cfg.math_mode == B200DQN_MATH_TCGEN05) B2_TRY(umma_opt_conv(n, 1, rows, sC, "opt_conv2"));
+    else B2_TRY(optimizer_range(n, 1, 1, 1 | 4, rows, sC, "opt_conv2"));
+  }
   B2_TRY(bwd_op(n, fs, rows, kConv1Wgrad, st));
-  B2_TRY(optimizer_range(n, 0, 0, 1 | 4, rows, st, "opt_conv1"));
+  if (n->cfg.math_mode == B200DQN_MATH_TCGEN05) B2_TRY(umma_opt_conv(n, 0, rows, st, "opt_conv1"));
+  else B2_TRY(optimizer_range(n, 0, 0, 1 | 4, rows, st, "opt_conv1"));
   B2_CHECK_CUDA(cudaEventRecord(ev[4], sA));
   B2_CHECK_CUDA(cudaEventRecord(ev[5], sB));
   B2_CHECK_CUDA(cudaEventRecord(ev[6], sC));

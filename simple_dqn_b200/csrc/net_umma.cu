@@ -321,6 +321,7 @@ struct UmmaState {
   // weight tile images ([hi | lo] per (tile, k-block))
   uint8_t* img_fwd[2][4] = {};  // conv1, conv2, conv3, fc1  x  (online, target)
   int64_t img_fwd_bytes[4] = {};
+  uint8_t* im2col1 = nullptr;   // conv1_fwd's A_hi tiles of the online net: [ceil(nb*400/128)][4][16 KB]
   uint8_t* img_dgr[3] = {};     // fc1_dgrad (A operand), conv3_dgrad (B), conv2_dgrad (B, 4 parity classes)
 };
 static inline UmmaState* ust(b200dqn_net* n) { return static_cast<UmmaState*>(n->umma_state); }
@@ -340,7 +341,8 @@ struct V2Conv1Fwd {
   static constexpr int kBN = 32;
   static constexpr bool kAExact = true, kARowMajorThreads = true, kBRowMajorThreads = false;
   static constexpr int kAMode = umma2::kReg, kBMode = umma2::kBulk;
-  static constexpr bool kStagedEpilogue = true;
+  static constexpr bool kStagedEpilogue = true, kDumpA = true;
+  uint8_t* im2col;          // online net only: [mtile][4 kb][128 x 128 B] A_hi tiles for conv1_wgrad (nullptr = off)
   const uint8_t* src[2];
   const int32_t* idx[2];
   int shift[2];
@@ -365,6 +367,9 @@ struct V2Conv1Fwd {
     }
   }
   __device__ const uint8_t* b_tile(int z, int, int kb) const { return (z ? wimg[1] : wimg[0]) + kb * (kC1 * 256); }
+  __device__ uint8_t* a_dump(int z, int mtile, int kb) const {
+    return (z == 0 && im2col) ? im2col + (int64_t(mtile) * (kK1 / 64) + kb) * (128 * 128) : nullptr;
+  }
   __device__ void store8(int z, int m, int n0, const float v[8]) const {
     float o[8];
 #pragma unroll
@@ -380,7 +385,7 @@ struct V2ConvFwd {
   static constexpr int kBN = KO;
   static constexpr bool kAExact = false, kARowMajorThreads = true, kBRowMajorThreads = false;
   static constexpr int kAMode = umma2::kAsync, kBMode = umma2::kBulk;
-  static constexpr bool kStagedEpilogue = true;
+  static constexpr bool kStagedEpilogue = true, kDumpA = false;
   PlanePair in16[2];
   const uint8_t* wimg[2];   // [K/64][hi KOx128 | lo KOx128]
   float* out[2];
@@ -412,7 +417,7 @@ struct V2Fc1Fwd {
   static constexpr int kBN = 32;
   static constexpr bool kAExact = false, kARowMajorThreads = false, kBRowMajorThreads = true;
   static constexpr int kAMode = umma2::kBulk, kBMode = umma2::kAsync;
-  static constexpr bool kStagedEpilogue = false;   // outputs of a thread are strided; lanes are contiguous in m
+  static constexpr bool kStagedEpilogue = false, kDumpA = false;   // a thread's outputs are strided; lanes run along m
   PlanePair in16[2];        // H3 planes [rows][3136]
   const uint8_t* wimg[2];   // [4 mtiles][49 kb][hi 128x128 | lo 128x128]
   float* part;              // [2*splits][rows][512]
@@ -445,7 +450,7 @@ struct V2Fc1Dgrad {
   static constexpr int kBN = 32;
   static constexpr bool kAExact = false, kARowMajorThreads = true, kBRowMajorThreads = true;
   static constexpr int kAMode = umma2::kBulk, kBMode = umma2::kAsync;
-  static constexpr bool kStagedEpilogue = false;
+  static constexpr bool kStagedEpilogue = false, kDumpA = false;
   const uint8_t* wimg;   // [25 mtiles][8 kb][hi | lo]   rows m = flat index (p,q,c), K = hidden unit
   PlanePair dz4;         // [rows][512]
   const float* h3;       // [rows][3136] (mask)
@@ -486,7 +491,7 @@ struct V2ConvDgrad {
   static constexpr int kBN = C;
   static constexpr bool kAExact = false, kARowMajorThreads = true, kBRowMajorThreads = true;
   static constexpr int kAMode = umma2::kAsync, kBMode = umma2::kBulk;
-  static constexpr bool kStagedEpilogue = true;
+  static constexpr bool kStagedEpilogue = true, kDumpA = false;
   PlanePair dz;          // [rows][P][P][KO]
   const uint8_t* wimg;   // [ST*ST classes][K/64][hi Cx128 | lo Cx128]
   const float* x;        // forward activation (mask)
@@ -530,8 +535,8 @@ template <int H, int C, int R, int ST, int KO>
 struct WConvWgrad {
   static constexpr int P = (H - R) / ST + 1, KW = R * R * C;
   static_assert((R * C) % 64 == 0 && KO == 64, "64-element runs must not straddle a filter row");
-  static constexpr int kBN = 64;
-  static constexpr bool kAExact = false, kARegs = false;
+  static constexpr int kBN = 64, kStages = 4;
+  static constexpr bool kAExact = false, kARegs = false, kABulk = false;
   PlanePair x16;    // [rows][H][H][C]
   PlanePair dz16;   // [rows][P][P][KO]
   float* part;      // [splits][KW][KO]
@@ -558,15 +563,15 @@ struct WConvWgrad {
   __device__ void store8(int z, int m, int n0, const float v[8]) const { st8(part + (int64_t(z) * KW + m) * KO + n0, v); }
 };
 
-// conv1: A = the u8 frame window (exact in fp16); m chunk = frame c, piece j = filter row r (8 pixels).
+// conv1: the A operand (row = output pixel, 64 contiguous taps (r,s) of frame c, exact u8 values) is
+// exactly the tile conv1_fwd staged for its own MMA, so conv1_fwd ships those tiles to an im2col image
+// (V2Conv1Fwd::kDumpA) and this kernel fetches each [64 pixels x 64 taps] sub-tile with ONE TMA bulk copy.
 struct WConv1Wgrad {
-  static constexpr int kBN = 32;
-  static constexpr bool kAExact = true, kARegs = true;
-  const uint8_t* src;
-  const int32_t* idx;
-  int shift;
-  PlanePair dz16;   // dZ1 [rows][20][20][32]
-  float* part;      // [splits][256][32]
+  static constexpr int kBN = 32, kStages = 4;
+  static constexpr bool kAExact = true, kARegs = false, kABulk = true;
+  const uint8_t* im2col;   // [pixel tile of 128][c = 4][128 x 128 B]
+  PlanePair dz16;          // dZ1 [rows][20][20][32]
+  float* part;             // [splits][256][32]
   int rows, kb_per_split;
   __device__ int M(int) const { return kK1; }
   __device__ int N(int) const { return kC1; }
@@ -575,25 +580,12 @@ struct WConv1Wgrad {
     kb = min(z * kb_per_split, total);
     ke = min(kb + kb_per_split, total);
   }
-  __device__ umma_mn::PixCtx pix(int, int kpix) const {
-    const int n = kpix / (kP1 * kP1), pq = kpix % (kP1 * kP1);
-    return {n, pq / kP1, pq % kP1, kpix < rows * kP1 * kP1};
-  }
-  __device__ void a_piece(int, const umma_mn::PixCtx& px, int c, int r, float v[8]) const {
-    if (!px.ok) { zero8(v); return; }
-    const int64_t f = static_cast<int64_t>(idx[px.n]) + shift + c;
-    const uint8_t* ptr = src + f * kFrameBytes + (px.p * 4 + r) * kFrameW + px.q * 4;
-    const uint32_t lo = *reinterpret_cast<const uint32_t*>(ptr), hi = *reinterpret_cast<const uint32_t*>(ptr + 4);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      v[j] = float((lo >> (8 * j)) & 0xffu);
-      v[4 + j] = float((hi >> (8 * j)) & 0xffu);
-    }
+  __device__ umma_mn::PixCtx pix(int, int kpix) const { return {kpix, 0, 0, kpix < rows * kP1 * kP1}; }
+  __device__ const uint8_t* a_sub(int, int c, int kb) const {   // kb = global 64-pixel block
+    return im2col + (int64_t(kb >> 1) * (kK1 / 64) + c) * (128 * 128) + (kb & 1) * (64 * 128);
   }
   __device__ umma2::Planes b_planes(int) const { return {dz16.hi, dz16.lo_off}; }
-  __device__ int64_t b_off(int, const umma_mn::PixCtx& px) const {
-    return (int64_t(px.n * kP1 + px.p) * kP1 + px.q) * kC1;
-  }
+  __device__ int64_t b_off(int, const umma_mn::PixCtx& px) const { return int64_t(px.n) * kC1; }
   __device__ void store8(int z, int m, int n0, const float v[8]) const {
     float o[8];
 #pragma unroll
@@ -604,8 +596,8 @@ struct WConv1Wgrad {
 
 // fc1: dW4[m][n] = sum_b H3[b][m] * dZ4[b][n]; the reduction rows are the batch samples.
 struct WFc1Wgrad {
-  static constexpr int kBN = 64;
-  static constexpr bool kAExact = false, kARegs = false;
+  static constexpr int kBN = 64, kStages = 2;
+  static constexpr bool kAExact = false, kARegs = false, kABulk = false;
   PlanePair h3_16;   // [rows][3136]
   PlanePair dz4_16;  // [rows][512]
   float* dw4;        // [3136][512]
@@ -675,6 +667,114 @@ struct PackConvDgrad { // B operand of a conv dgrad, one tile per output-parity 
   }
 };
 
+// ------------------------------------------------------------------------------------------
+// Conv-layer optimizer, fused: split-K partial reduction (8 lanes per element, fixed tree ->
+// deterministic) + Neon RMSProp (same operation order as k_optimizer, bit-exact given equal gradients)
+// + refresh of the layer's fp16 tile images (forward B operand; dgrad B operand for conv2/conv3).
+// Replaces three launches (optimizer, pack fwd, pack dgrad) on the tail of the step.
+// ------------------------------------------------------------------------------------------
+template <int KR, int N, bool DGRAD, int C, int R, int ST>
+__global__ void __launch_bounds__(256)
+k_opt_conv(const float* __restrict__ part, int splits, float* __restrict__ w, float* __restrict__ sst,
+           uint8_t* __restrict__ img_fwd, uint8_t* __restrict__ img_dgr, float inv_bsz, float lr, float decay,
+           float one_m_decay, float eps, const KTrace kt) {
+  constexpr int64_t kSize = int64_t(KR) * N;
+  kt_begin(kt);
+  pdl_wait();
+  pdl_launch_dependents();
+  const int tid = threadIdx.x, lane8 = tid & 7;
+  const int64_t e4 = blockIdx.x * 32 + (tid >> 3);
+  const int64_t i = e4 * 4;
+  const bool live = i < kSize;
+  float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (live) {
+    const float* p = part + i;
+    float4 v[8];
+    int cnt = 0;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {          // up to 64 splits: 8 independent loads per lane
+      const int sp = lane8 + 8 * u;
+      if (sp < splits) { v[u] = *reinterpret_cast<const float4*>(p + sp * kSize); cnt = u + 1; }
+    }
+    for (int u = 0; u < cnt; ++u) { g.x += v[u].x; g.y += v[u].y; g.z += v[u].z; g.w += v[u].w; }
+  }
+#pragma unroll
+  for (int o = 1; o < 8; o <<= 1) {
+    g.x += __shfl_xor_sync(0xffffffffu, g.x, o);
+    g.y += __shfl_xor_sync(0xffffffffu, g.y, o);
+    g.z += __shfl_xor_sync(0xffffffffu, g.z, o);
+    g.w += __shfl_xor_sync(0xffffffffu, g.w, o);
+  }
+  if (live && lane8 == 0) {
+    float4 wv = *reinterpret_cast<float4*>(w + i);
+    float4 sv = *reinterpret_cast<float4*>(sst + i);
+    float* gp = reinterpret_cast<float*>(&g);
+    float* wp = reinterpret_cast<float*>(&wv);
+    float* sp = reinterpret_cast<float*>(&sv);
+    __half hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float gg = __fmul_rn(gp[j], inv_bsz);
+      const float ns = __fadd_rn(__fmul_rn(decay, sp[j]), __fmul_rn(__fmul_rn(gg, gg), one_m_decay));
+      const float den = __fadd_rn(__fsqrt_rn(__fadd_rn(ns, eps)), eps);
+      wp[j] = __fsub_rn(wp[j], __fdiv_rn(__fmul_rn(gg, lr), den));
+      sp[j] = ns;
+      umma2::split1(wp[j], hi[j], lo[j]);
+    }
+    *reinterpret_cast<float4*>(w + i) = wv;
+    *reinterpret_cast<float4*>(sst + i) = sv;
+    const int k = int(i / N), n0 = int(i % N);
+    {  // forward image: rows = output channel n, 8-element chunks along k
+      uint8_t* base = img_fwd + int64_t(k / 64) * (N * 256) + (k % 8) * 2;
+      const int c8 = (k % 64) / 8;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t off = umma::sw128_off(n0 + j, c8);
+        *reinterpret_cast<__half*>(base + off) = hi[j];
+        *reinterpret_cast<__half*>(base + N * 128 + off) = lo[j];
+      }
+    }
+    if constexpr (DGRAD) {  // dgrad image: one tile per output-parity class, rows = input channel c, K = (r', s', ko)
+      constexpr int RT = R / ST, NKB = RT * RT * N / 64;
+      const int r = k / (R * C), s = (k / C) % R, c = k % C;
+      const int z = (r % ST) * ST + (s % ST);
+      const int kd = ((r / ST) * RT + (s / ST)) * N + n0;
+      uint8_t* base = img_dgr + (int64_t(z) * NKB + kd / 64) * (C * 256) + umma::sw128_off(c, (kd % 64) / 8) + (kd % 8) * 2;
+      *reinterpret_cast<uint2*>(base) = *reinterpret_cast<const uint2*>(hi);
+      *reinterpret_cast<uint2*>(base + C * 128) = *reinterpret_cast<const uint2*>(lo);
+    }
+  }
+  kt_end(kt);
+}
+
+// RMSProp + image refresh of conv layer l (0..2), fused (single-GPU path of the tcgen05 engine).
+int umma_opt_conv(b200dqn_net* n, int l, int rows, cudaStream_t st, const char* label) {
+  UmmaState* u = ust(n);
+  const LayerTable& lt = n->lt;
+  const float inv_bsz = 1.0f / float(rows * n->world);
+  const float lr = float(n->cfg.learning_rate), decay = float(n->cfg.decay_rate);
+  const float omd = float(1.0 - n->cfg.decay_rate), eps = 1e-6f;
+  const float* part = n->d_part + lt.part_off[l];
+  float* w = n->d_w + lt.off[l];
+  float* s = n->d_s + lt.off[l];
+  B2_REQUIRE(lt.splits[l] <= 64, B200DQN_EINVAL, "k_opt_conv handles at most 64 split-K partials");
+  const int64_t size = lt.off[l + 1] - lt.off[l];
+  const dim3 grid(unsigned((size / 4 + 31) / 32)), block(256);
+  cudaError_t e;
+  if (l == 0)
+    e = launch_pdl(k_opt_conv<kK1, kC1, false, 4, 8, 4>, grid, block, 0, st, part, lt.splits[l], w, s, u->img_fwd[0][0],
+                   (uint8_t*)nullptr, inv_bsz, lr, decay, omd, eps, ktrace_slot(label));
+  else if (l == 1)
+    e = launch_pdl(k_opt_conv<kK2, kC2, true, kC1, 4, 2>, grid, block, 0, st, part, lt.splits[l], w, s, u->img_fwd[0][1],
+                   u->img_dgr[2], inv_bsz, lr, decay, omd, eps, ktrace_slot(label));
+  else
+    e = launch_pdl(k_opt_conv<kK3, kC3, true, kC2, 3, 1>, grid, block, 0, st, part, lt.splits[l], w, s, u->img_fwd[0][2],
+                   u->img_dgr[1], inv_bsz, lr, decay, omd, eps, ktrace_slot(label));
+  B2_CHECK_CUDA(e);
+  B2_PROF(label, st);
+  return B200DQN_OK;
+}
+
 static int64_t fwd_image_bytes(int layer) {
   switch (layer) {
     case 0: return int64_t(kK1 / 64) * kC1 * 256;
@@ -717,10 +817,18 @@ int umma_pack_layers(b200dqn_net* n, int which, int l0, int l1, cudaStream_t st)
 constexpr int kUFc1Splits = 7;    // 49 k-blocks of 64 -> 7 per CTA; 4 M-tiles x 7 x 2 nets = 56 CTAs
 constexpr int kUWgradKb = 4;      // k-blocks (256 pixels) per wgrad split
 
-int umma_wgrad_splits(int layer, int rows) {
+// k-blocks (of 64 pixels) per wgrad split: at least kUWgradKb, and few enough splits (<= 48) for the
+// one-pass reduction of k_opt_conv
+int umma_wgrad_kb(int layer, int rows) {
   const int kred = layer == 0 ? rows * kP1 * kP1 : layer == 1 ? rows * kP2 * kP2 : rows * kP3 * kP3;
   const int kbs = (kred + 63) / 64;
-  return (kbs + kUWgradKb - 1) / kUWgradKb;
+  const int per = (kbs + 47) / 48;
+  return per > kUWgradKb ? per : kUWgradKb;
+}
+int umma_wgrad_splits(int layer, int rows) {
+  const int kred = layer == 0 ? rows * kP1 * kP1 : layer == 1 ? rows * kP2 * kP2 : rows * kP3 * kP3;
+  const int kbs = (kred + 63) / 64, per = umma_wgrad_kb(layer, rows);
+  return (kbs + per - 1) / per;
 }
 
 int umma_net_init(b200dqn_net* n) {
@@ -753,6 +861,7 @@ int umma_net_init(b200dqn_net* n) {
       B2_CHECK_CUDA(cudaMemset(u->img_fwd[z][l], 0, u->img_fwd_bytes[l]));
     }
   }
+  B2_CHECK_CUDA(cudaMalloc(&u->im2col1, int64_t((nb * kP1 * kP1 + 127) / 128) * (kK1 / 64) * 128 * 128));
   const int64_t dgr_bytes[3] = {int64_t((kFlat + 127) / 128) * (kHidden / 64) * 128 * 256,
                                 int64_t(kK3 / 64) * kC2 * 256, int64_t(4) * (256 / 64) * kC1 * 256};
   for (int i = 0; i < 3; ++i) {
@@ -770,6 +879,7 @@ void umma_net_destroy(b200dqn_net* n) {
     cudaFree(u->img_dgr[i]);
   }
   for (int i = 0; i < 4; ++i) cudaFree(u->dz16[i]);
+  cudaFree(u->im2col1);
   for (int l = 0; l < 4; ++l) {
     if (u->img_fwd[1][l] != u->img_fwd[0][l]) cudaFree(u->img_fwd[1][l]);
     cudaFree(u->img_fwd[0][l]);
@@ -811,6 +921,7 @@ int umma_forward(b200dqn_net* n, const uint8_t* const src[2], const int32_t* con
       p.wimg[z] = u->img_fwd[z][0]; p.out[z] = n->d_h1[z]; p.out16[z] = planes(0, z);
     }
     p.rows = rows;
+    p.im2col = (nets == 2 && rows == n->nb) ? u->im2col1 : nullptr;   // only a train step feeds conv1_wgrad
     if ((rc = umma2::launch_umma2("conv1_fwd", p, rows * kP1 * kP1, kC1, nets, st))) return rc;
   }
   {
@@ -861,7 +972,7 @@ int umma_backward_op(b200dqn_net* n, int op, const uint8_t* src, const int32_t* 
       UmmaState* u = ust(n);
       using P = WConvWgrad<kP2, kC2, 3, 1, kC3>;
       P p{PlanePair{u->h16[1][0], u->h_elems[1]}, PlanePair{u->dz16[1], u->dz_elems[1]},
-          n->d_part + lt.part_off[2], rows, kUWgradKb};
+          n->d_part + lt.part_off[2], rows, umma_wgrad_kb(2, rows)};
       return umma_mn::launch_umma_mn("conv3_wgrad", p, P::KW, kC3, lt.splits[2], st);
     }
     case 3: {
@@ -875,7 +986,7 @@ int umma_backward_op(b200dqn_net* n, int op, const uint8_t* src, const int32_t* 
       UmmaState* u = ust(n);
       using P = WConvWgrad<kP1, kC1, 4, 2, kC2>;
       P p{PlanePair{u->h16[0][0], u->h_elems[0]}, PlanePair{u->dz16[2], u->dz_elems[2]},
-          n->d_part + lt.part_off[1], rows, kUWgradKb};
+          n->d_part + lt.part_off[1], rows, umma_wgrad_kb(1, rows)};
       return umma_mn::launch_umma_mn("conv2_wgrad", p, P::KW, kC2, lt.splits[1], st);
     }
     case 5: {
@@ -887,8 +998,9 @@ int umma_backward_op(b200dqn_net* n, int op, const uint8_t* src, const int32_t* 
     }
     default: {
       UmmaState* u = ust(n);
-      WConv1Wgrad p{src, idx, shift, PlanePair{u->dz16[3], u->dz_elems[3]}, n->d_part + lt.part_off[0], rows,
-                    kUWgradKb};
+      (void)src; (void)idx; (void)shift;   // the frames were already gathered by conv1_fwd (im2col image)
+      WConv1Wgrad p{u->im2col1, PlanePair{u->dz16[3], u->dz_elems[3]}, n->d_part + lt.part_off[0], rows,
+                    umma_wgrad_kb(0, rows)};
       return umma_mn::launch_umma_mn("conv1_wgrad", p, kK1, kC1, lt.splits[0], st);
     }
   }

@@ -67,9 +67,9 @@ k_sample(uint32_t* __restrict__ mt_state, const uint8_t* __restrict__ terminals,
   __shared__ int s_cut;
   const int tid = threadIdx.x;
   const int lane = tid & 31, wid = tid >> 5;
-  pdl_launch_dependents();
   kt_begin(kt);
   pdl_wait();
+  pdl_launch_dependents();
 
   for (int i = tid; i < kMtN + 1; i += kSampleThreads) mt[i] = mt_state[i];
   __syncthreads();

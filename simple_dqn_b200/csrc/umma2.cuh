@@ -69,6 +69,8 @@ __device__ __forceinline__ void split8_planes(const float v[8], __half* hi_dst, 
 //           same with b_row / b_chunk / b_planes for B
 //   kBulk : const uint8_t* a_tile(z, mtile, kb) / b_tile(z, ntile, kb)      -> [hi image | lo image]
 //   void store8(z, m, n0, const float v[8])
+//   static constexpr bool kDumpA: after k-block kb is staged, bulk-store the A_hi tile to a_dump(z, mtile, kb)
+//        (needs every k-block in its own stage: nkb <= kStages)
 //   static constexpr bool kStagedEpilogue: store8 writes 8 CONTIGUOUS outputs of row m (NHWC tensors) ->
 //        the tile is transposed through smem so that a warp's stores are whole cache lines
 template <class P>
@@ -130,11 +132,11 @@ __global__ void __launch_bounds__(kThreads2, 1) k_umma2(const P p, const int tra
   __shared__ __align__(8) uint64_t s_full[S];    // operands of the stage have landed
   __shared__ __align__(8) uint64_t s_empty[S];   // MMAs reading the stage completed
   __shared__ __align__(8) uint64_t s_done;
+  __shared__ __align__(8) uint64_t s_dumped;     // kDumpA: the bulk stores have finished READING the A tiles
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int z = blockIdx.z;
   const bool trace = trace_in && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
-  pdl_launch_dependents();
   kt_begin(kt);
   B2_TRACE(tid == 0, 0);
   const int M = p.M(z), N = p.N(z);
@@ -157,12 +159,14 @@ __global__ void __launch_bounds__(kThreads2, 1) k_umma2(const P p, const int tra
       mbar_init(&s_empty[s], 1);
     }
     mbar_init(&s_done, 1);
+    mbar_init(&s_dumped, 1);
     mbar_fence_init();
   }
   umma::fence_before_sync();
   __syncthreads();
   umma::fence_after_sync();
   pdl_wait();   // everything above overlapped the previous kernel; from here on we read its outputs
+  pdl_launch_dependents();   // now let exactly ONE successor pre-launch (it parks at its own pdl_wait)
   B2_TRACE(tid == 0, 1);
   const uint32_t tmem = s_tmem;
 
@@ -183,13 +187,26 @@ __global__ void __launch_bounds__(kThreads2, 1) k_umma2(const P p, const int tra
       const uint64_t da_lo = umma::make_desc_sw128(sa + C::kABytes);
       const uint64_t db = umma::make_desc_sw128(sa + C::kAStage);   // [B_hi ; B_lo], 2*BN rows
       if (elect_one()) {
+        if constexpr (P::kDumpA) {
+          // The staged [128 x 64] A_hi tile IS the MN-major operand the wgrad of this layer needs
+          // (row = pixel, 64 contiguous taps): ship it out with one TMA bulk store per k-block.
+          uint8_t* dump = p.a_dump(z, blockIdx.x, kb0 + it);
+          if (dump) tma_bulk_s2g(dump, smem_gen + s * C::kStageBytes, C::kABytes);
+        }
 #pragma unroll
         for (int k = 0; k < kBK / 16; ++k) {
           umma::mma_f16(tmem, da_hi + 2 * k, db + 2 * k, idesc2, (it > 0 || k > 0) ? 1u : 0u);
           if (!P::kAExact) umma::mma_f16(tmem + BN, da_lo + 2 * k, db + 2 * k, idesc1, 1u);
         }
         umma::mma_commit(&s_empty[s]);
-        if (it == nkb - 1) umma::mma_commit(&s_done);
+        if (it == nkb - 1) {
+          umma::mma_commit(&s_done);
+          if constexpr (P::kDumpA) {
+            tma_bulk_commit();
+            tma_bulk_wait_read_all();   // smem may now be reused by the epilogue's staging tile
+            mbar_arrive(&s_dumped);
+          }
+        }
       }
       __syncwarp();
       B2_TRACE(lane == 0, 8 + it * 4 + 1);
@@ -293,6 +310,7 @@ __global__ void __launch_bounds__(kThreads2, 1) k_umma2(const P p, const int tra
 
     // ================================================================ epilogue (same 8 warps)
     mbar_wait(&s_done, 0);
+    if constexpr (P::kDumpA) mbar_wait(&s_dumped, 0);
     umma::fence_after_sync();
     B2_TRACE(tid == 0, 4);
     {
@@ -389,8 +407,8 @@ __global__ void __launch_bounds__(256) k_pack_image(const S src, uint8_t* __rest
   const int64_t chunks_per_tile_kb = int64_t(rows) * 8;
   const int64_t total = int64_t(src.tiles()) * nkb * chunks_per_tile_kb;
   const int64_t id = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
-  pdl_launch_dependents();
   pdl_wait();
+  pdl_launch_dependents();
   if (id >= total) return;
   const int64_t tk = id / chunks_per_tile_kb;
   const int within = int(id % chunks_per_tile_kb);

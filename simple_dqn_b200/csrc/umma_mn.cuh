@@ -48,6 +48,7 @@ struct PixCtx {   // decoded reduction index (one per thread per k-block)
 //   int M(z), N(z); void krange(z, kb0, kb1);  PixCtx pix(z, kpix);
 //   !kARegs: Planes a_planes(z); bool a_run(z, pix, mchunk, int64_t& off)     64 contiguous fp16 of A for this pixel
 //    kARegs: void a_piece(z, pix, mchunk, j, float v[8])                       (exact values, e.g. u8 pixels)
+//    kABulk: const uint8_t* a_sub(z, mchunk, kb)   ready-made [64 k-rows x 128 B] sub-tile image (exact A only)
 //   Planes b_planes(z); int64_t b_off(z, pix)                                  BN contiguous fp16 of B for this pixel
 //   void store8(z, m, n0, const float v[8])
 template <class P>
@@ -59,8 +60,9 @@ struct CfgMN {
   static constexpr uint32_t kAStage = (P::kAExact ? 1 : 2) * kAHalf;
   static constexpr uint32_t kBStage = (BN == 64 ? 2 : 1) * kSub;
   static constexpr uint32_t kStageBytes = kAStage + kBStage;
-  static constexpr int kStages = 4;
+  static constexpr int kStages = P::kStages;   // 4 for the split-K conv wgrads; 2 for the single-k-block fc1 wgrad
   static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024;
+  static_assert(kBM * (BN * 4 + 16) <= kStages * kStageBytes, "epilogue staging tile must fit the stage ring");
   static constexpr uint32_t kTmemCols = (2 * BN <= 64) ? 64 : 128;
 };
 
@@ -77,7 +79,6 @@ __global__ void __launch_bounds__(kThreads2, 1) k_umma_mn(const P p, const KTrac
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int z = blockIdx.z;
-  pdl_launch_dependents();
   kt_begin(kt);
   const int M = p.M(z), N = p.N(z);
   const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * BN;
@@ -93,7 +94,7 @@ __global__ void __launch_bounds__(kThreads2, 1) k_umma_mn(const P p, const KTrac
   if (tid == 32) {
 #pragma unroll
     for (int s = 0; s < S; ++s) {
-      mbar_init(&s_full[s], kLoadThreads);
+      mbar_init(&s_full[s], kLoadThreads + (P::kABulk ? 1 : 0));
       mbar_init(&s_empty[s], 1);
     }
     mbar_init(&s_done, 1);
@@ -103,6 +104,7 @@ __global__ void __launch_bounds__(kThreads2, 1) k_umma_mn(const P p, const KTrac
   __syncthreads();
   umma::fence_after_sync();
   pdl_wait();
+  pdl_launch_dependents();
   const uint32_t tmem = s_tmem;
 
   if (nkb <= 0) {
@@ -144,7 +146,7 @@ __global__ void __launch_bounds__(kThreads2, 1) k_umma_mn(const P p, const KTrac
     const int kr = tid >> 2, sub = tid & 3;
     const Planes bpl = p.b_planes(z);
     Planes apl{nullptr, 0};
-    if constexpr (!P::kARegs) apl = p.a_planes(z);
+    if constexpr (!P::kARegs && !P::kABulk) apl = p.a_planes(z);
     for (int j = 0; j < nkb; ++j) {
       const int s = j % S;
       if (j >= S) mbar_wait(&s_empty[s], ((j / S) - 1) & 1);
@@ -152,7 +154,14 @@ __global__ void __launch_bounds__(kThreads2, 1) k_umma_mn(const P p, const KTrac
       uint8_t* st_gen = smem_gen + s * C::kStageBytes;
       const PixCtx px = p.pix(z, (kb0 + j) * kKB + kr);
       // ---- A: 2 m-chunks x 8 pieces per row; this thread: chunk (sub >> 1), pieces (sub & 1) * 4 .. + 3
-      {
+      if constexpr (P::kABulk) {
+        static_assert(P::kAExact, "bulk A sub-tiles carry no lo part");
+        if (tid == 0) {
+          mbar_arrive_expect_tx(&s_full[s], 2 * C::kSub);
+          tma_bulk_g2s(st_gen, p.a_sub(z, blockIdx.x * 2, kb0 + j), C::kSub, &s_full[s]);
+          tma_bulk_g2s(st_gen + C::kSub, p.a_sub(z, blockIdx.x * 2 + 1, kb0 + j), C::kSub, &s_full[s]);
+        }
+      } else {
         const int mc = sub >> 1, j0 = (sub & 1) * 4;
         const int mchunk = blockIdx.x * 2 + mc;
         if constexpr (!P::kARegs) {
