@@ -85,6 +85,7 @@ SIGNATURES = {
     "b200dqn_net_read_costs": [_P, C.c_int, _P, _P],
     "b200dqn_net_train_iterations": [_P, _i64p],
     "b200dqn_net_device_ptr": [_P, C.c_int, C.POINTER(_P), C.POINTER(C.c_size_t)],
+    "b200dqn_net_set_keep_grads": [_P, C.c_int],
     "b200dqn_net_get_grads": [_P, C.c_int, _P, _P],
     "b200dqn_net_launches_per_step": [_P, C.POINTER(C.c_int)],
     "b200dqn_debug_trace": [_P, C.c_int],

@@ -65,6 +65,7 @@ struct b200dqn_net {
   cudaStream_t side[3] = {};
   cudaEvent_t ev[7] = {};
   bool use_graph = true, use_branches = true;
+  bool keep_grads = false;   // fused optimizers also write dW for b200dqn_net_get_grads (tests)
   cudaGraphExec_t graph_exec = nullptr;
   b200dqn_replay* graph_replay = nullptr;
   cudaStream_t graph_stream = nullptr;

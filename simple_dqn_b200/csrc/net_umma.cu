@@ -536,7 +536,7 @@ struct WConvWgrad {
   static constexpr int P = (H - R) / ST + 1, KW = R * R * C;
   static_assert((R * C) % 64 == 0 && KO == 64, "64-element runs must not straddle a filter row");
   static constexpr int kBN = 64, kStages = 4;
-  static constexpr bool kAExact = false, kARegs = false, kABulk = false;
+  static constexpr bool kAExact = false, kARegs = false, kABulk = false, kFusedUpdate = false;
   PlanePair x16;    // [rows][H][H][C]
   PlanePair dz16;   // [rows][P][P][KO]
   float* part;      // [splits][KW][KO]
@@ -568,7 +568,7 @@ struct WConvWgrad {
 // (V2Conv1Fwd::kDumpA) and this kernel fetches each [64 pixels x 64 taps] sub-tile with ONE TMA bulk copy.
 struct WConv1Wgrad {
   static constexpr int kBN = 32, kStages = 4;
-  static constexpr bool kAExact = true, kARegs = false, kABulk = true;
+  static constexpr bool kAExact = true, kARegs = false, kABulk = true, kFusedUpdate = false;
   const uint8_t* im2col;   // [pixel tile of 128][c = 4][128 x 128 B]
   PlanePair dz16;          // dZ1 [rows][20][20][32]
   float* part;             // [splits][256][32]
@@ -597,7 +597,7 @@ struct WConv1Wgrad {
 // fc1: dW4[m][n] = sum_b H3[b][m] * dZ4[b][n]; the reduction rows are the batch samples.
 struct WFc1Wgrad {
   static constexpr int kBN = 64, kStages = 2;
-  static constexpr bool kAExact = false, kARegs = false, kABulk = false;
+  static constexpr bool kAExact = false, kARegs = false, kABulk = false, kFusedUpdate = false;
   PlanePair h3_16;   // [rows][3136]
   PlanePair dz4_16;  // [rows][512]
   float* dw4;        // [3136][512]
@@ -614,6 +614,66 @@ struct WFc1Wgrad {
   __device__ umma2::Planes b_planes(int) const { return {dz4_16.hi, dz4_16.lo_off}; }
   __device__ int64_t b_off(int, const umma_mn::PixCtx& px) const { return int64_t(px.n) * kHidden; }
   __device__ void store8(int, int m, int n0, const float v[8]) const { st8(dw4 + int64_t(m) * kHidden + n0, v); }
+};
+
+// fc1 wgrad with the optimizer fused into its epilogue (single GPU): the tile of dW4 never leaves the
+// SM — RMSProp is applied in place and both fp16 tile images of W4 are refreshed.  Must run after
+// fc1_dgrad (which still reads the old dgrad image).
+struct WFc1WgradFused {
+  static constexpr int kBN = 64, kStages = 2;
+  static constexpr bool kAExact = false, kARegs = false, kABulk = false, kFusedUpdate = true;
+  PlanePair h3_16;
+  PlanePair dz4_16;
+  float* w;           // W4 [3136][512]
+  float* s;           // RMSProp state
+  float* dw_out;      // optional copy of dW4 (b200dqn_net_get_grads), nullptr in production
+  uint8_t* img_fwd;   // [4 n-tiles][49 kb][hi 128x128 | lo]
+  uint8_t* img_dgr;   // [25 m-tiles][8 kb][hi 128x128 | lo]
+  int rows;
+  float inv_bsz, lr, decay, one_m_decay, eps;
+  __device__ int M(int) const { return kFlat; }
+  __device__ int N(int) const { return kHidden; }
+  __device__ void krange(int, int& kb, int& ke) const { kb = 0; ke = (rows + 63) / 64; }
+  __device__ umma_mn::PixCtx pix(int, int b) const { return {b, 0, 0, b < rows}; }
+  __device__ umma2::Planes a_planes(int) const { return {h3_16.hi, h3_16.lo_off}; }
+  __device__ bool a_run(int, const umma_mn::PixCtx& px, int mchunk, int64_t& off) const {
+    off = int64_t(px.n) * kFlat + mchunk * 64;
+    return mchunk * 64 < kFlat;
+  }
+  __device__ umma2::Planes b_planes(int) const { return {dz4_16.hi, dz4_16.lo_off}; }
+  __device__ int64_t b_off(int, const umma_mn::PixCtx& px) const { return int64_t(px.n) * kHidden; }
+  __device__ void store8(int, int, int, const float*) const {}
+  __device__ void update8(int, int m, int n0, const float g[8], float nw[8]) const {
+    const int64_t i = int64_t(m) * kHidden + n0;
+    if (dw_out) st8(dw_out + i, g);
+    float wv[8], sv[8];
+    ld8(w + i, wv);
+    ld8(s + i, sv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {   // Neon RMSProp, same operation order as k_optimizer
+      const float gg = __fmul_rn(g[j], inv_bsz);
+      const float ns = __fadd_rn(__fmul_rn(decay, sv[j]), __fmul_rn(__fmul_rn(gg, gg), one_m_decay));
+      const float den = __fadd_rn(__fsqrt_rn(__fadd_rn(ns, eps)), eps);
+      nw[j] = __fsub_rn(wv[j], __fdiv_rn(__fmul_rn(gg, lr), den));
+      sv[j] = ns;
+    }
+    st8(w + i, nw);
+    st8(s + i, sv);
+    uint4 hi, lo;
+    umma::split8(nw, hi, lo);
+    uint8_t* base = img_dgr + (int64_t(m / 128) * (kHidden / 64) + n0 / 64) * (128 * 256) +
+                    umma::sw128_off(m % 128, (n0 % 64) / 8);
+    *reinterpret_cast<uint4*>(base) = hi;
+    *reinterpret_cast<uint4*>(base + 128 * 128) = lo;
+  }
+  __device__ void pack_col8(int, int m8, int n, const float wv[8]) const {
+    uint4 hi, lo;
+    umma::split8(wv, hi, lo);
+    uint8_t* base = img_fwd + (int64_t(n / 128) * (kFlat / 64) + m8 / 64) * (128 * 256) +
+                    umma::sw128_off(n % 128, (m8 % 64) / 8);
+    *reinterpret_cast<uint4*>(base) = hi;
+    *reinterpret_cast<uint4*>(base + 128 * 128) = lo;
+  }
 };
 
 // ---- weight tile-image sources (k_pack_image) --------------------------------------------------
@@ -1004,6 +1064,17 @@ int umma_backward_op(b200dqn_net* n, int op, const uint8_t* src, const int32_t* 
       return umma_mn::launch_umma_mn("conv1_wgrad", p, kK1, kC1, lt.splits[0], st);
     }
   }
+}
+
+// fc1 wgrad + RMSProp + image refresh in one kernel (single-GPU tcgen05 path); must follow fc1_dgrad.
+int umma_fc1_wgrad_fused(b200dqn_net* n, int rows, cudaStream_t st, bool keep_grads) {
+  UmmaState* u = ust(n);
+  const LayerTable& lt = n->lt;
+  WFc1WgradFused p{PlanePair{u->h16[2][0], u->h_elems[2]}, PlanePair{u->dz16[0], u->dz_elems[0]},
+                   n->d_w + lt.off[3], n->d_s + lt.off[3], keep_grads ? n->d_part + lt.part_off[3] : nullptr,
+                   u->img_fwd[0][3], u->img_dgr[0], rows, 1.0f / float(rows * n->world),
+                   float(n->cfg.learning_rate), float(n->cfg.decay_rate), float(1.0 - n->cfg.decay_rate), 1e-6f};
+  return umma_mn::launch_umma_mn("fc1_wgrad+opt", p, kFlat, kHidden, 1, st);
 }
 
 int umma_fc1_splits() { return kUFc1Splits; }

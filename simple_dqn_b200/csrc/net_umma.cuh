@@ -17,6 +17,7 @@ int umma_target_synced(b200dqn_net* n, cudaStream_t st);    // target <- online
 int umma_forward(b200dqn_net* n, const uint8_t* const src[2], const int32_t* const idx[2], const int shift[2],
                  int nets, int rows, cudaStream_t st);
 int umma_fc1_splits();
+int umma_fc1_wgrad_fused(b200dqn_net* n, int rows, cudaStream_t st, bool keep_grads);
 // fused split-K reduction + RMSProp + tile-image refresh of conv layer l (0..2), single-GPU tcgen05 path
 int umma_opt_conv(b200dqn_net* n, int l, int rows, cudaStream_t st, const char* label);
 // rebuild the fp16 hi/lo tile images of layers [l0, l1] of network `which` (0 online, 1 target)

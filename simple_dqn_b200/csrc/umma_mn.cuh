@@ -233,14 +233,48 @@ __global__ void __launch_bounds__(kThreads2, 1) k_umma_mn(const P p, const KTrac
       }
       umma2::named_bar_sync(1, kLoadThreads);
       constexpr int kChunksPerRow = BN / 8;
+      if constexpr (!P::kFusedUpdate) {
 #pragma unroll
-      for (int i = 0; i < kBM * kChunksPerRow / kLoadThreads; ++i) {
-        const int id = tid + i * kLoadThreads;
-        const int r = id / kChunksPerRow, cc = id % kChunksPerRow;
-        const float* src = reinterpret_cast<const float*>(smem_gen + r * kPitch + cc * 32);
-        const float4 v0 = *reinterpret_cast<const float4*>(src), v1 = *reinterpret_cast<const float4*>(src + 4);
-        const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-        if (m0 + r < M && n0 + cc * 8 < N) p.store8(z, m0 + r, n0 + cc * 8, v);
+        for (int i = 0; i < kBM * kChunksPerRow / kLoadThreads; ++i) {
+          const int id = tid + i * kLoadThreads;
+          const int r = id / kChunksPerRow, cc = id % kChunksPerRow;
+          const float* src = reinterpret_cast<const float*>(smem_gen + r * kPitch + cc * 32);
+          const float4 v0 = *reinterpret_cast<const float4*>(src), v1 = *reinterpret_cast<const float4*>(src + 4);
+          const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+          if (m0 + r < M && n0 + cc * 8 < N) p.store8(z, m0 + r, n0 + cc * 8, v);
+        }
+      } else {
+        // Fused optimizer (no split-K: this tile IS the whole gradient of its weights).
+        // pass 1, thread <-> (row m, 8 consecutive n): RMSProp on W/S in HBM, the updated weights go
+        //         back into the smem tile and into the row-oriented (dgrad) tile image;
+        // pass 2, thread <-> (column n, 8 consecutive m): the column-oriented (forward) tile image.
+#pragma unroll
+        for (int i = 0; i < kBM * kChunksPerRow / kLoadThreads; ++i) {
+          const int id = tid + i * kLoadThreads;
+          const int r = id / kChunksPerRow, cc = id % kChunksPerRow;
+          float* src = reinterpret_cast<float*>(smem_gen + r * kPitch + cc * 32);
+          const float4 v0 = *reinterpret_cast<const float4*>(src), v1 = *reinterpret_cast<const float4*>(src + 4);
+          const float g[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+          if (m0 + r < M && n0 + cc * 8 < N) {
+            float nw[8];
+            p.update8(z, m0 + r, n0 + cc * 8, g, nw);
+            *reinterpret_cast<float4*>(src) = make_float4(nw[0], nw[1], nw[2], nw[3]);
+            *reinterpret_cast<float4*>(src + 4) = make_float4(nw[4], nw[5], nw[6], nw[7]);
+          }
+        }
+        umma2::named_bar_sync(1, kLoadThreads);
+#pragma unroll
+        for (int i = 0; i < (kBM / 8) * BN / kLoadThreads; ++i) {
+          const int id = tid + i * kLoadThreads;
+          const int nn = id % BN, mg = id / BN;
+          if (m0 + mg * 8 < M && n0 + nn < N) {
+            float wv[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              wv[j] = *reinterpret_cast<const float*>(smem_gen + (mg * 8 + j) * kPitch + nn * 4);
+            p.pack_col8(z, m0 + mg * 8, n0 + nn, wv);
+          }
+        }
       }
     }
   }

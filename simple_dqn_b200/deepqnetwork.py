@@ -115,6 +115,10 @@ class DeepQNetwork:
             ss.append(s)
         return (ws, ss) if with_states else ws
 
+    def keep_grads(self, keep=True):
+        """Make the fused optimizers keep a copy of dW so :meth:`get_grads` works (tests / debugging)."""
+        L.call("b200dqn_net_set_keep_grads", self._h, int(bool(keep)))
+
     def get_grads(self):
         out = []
         for layer, shp in enumerate(self.layer_shapes()):

@@ -44,6 +44,7 @@ def _paired(num_actions, mode, seed=3, batch=32, stream=None):
     ss = [np.abs(rs.randn(*w.shape)).astype(np.float32) * np.float32(1e-4) for w in ws]
     net.set_weights(ws, ss)
     net.update_target_network()
+    net.keep_grads(True)            # the fused optimizers otherwise never materialise dW4
     orc = O.DQNOracle(num_actions, batch_size=batch, weights=ws, states=ss)
     return net, orc
 
