@@ -643,12 +643,14 @@ struct WFc1WgradFused {
   __device__ umma2::Planes b_planes(int) const { return {dz4_16.hi, dz4_16.lo_off}; }
   __device__ int64_t b_off(int, const umma_mn::PixCtx& px) const { return int64_t(px.n) * kHidden; }
   __device__ void store8(int, int, int, const float*) const {}
-  __device__ void update8(int, int m, int n0, const float g[8], float nw[8]) const {
+  __device__ void load_ws(int, int m, int n0, float wv[8], float sv[8]) const {
     const int64_t i = int64_t(m) * kHidden + n0;
-    if (dw_out) st8(dw_out + i, g);
-    float wv[8], sv[8];
     ld8(w + i, wv);
     ld8(s + i, sv);
+  }
+  __device__ void update8(int, int m, int n0, const float g[8], const float wv[8], float sv[8], float nw[8]) const {
+    const int64_t i = int64_t(m) * kHidden + n0;
+    if (dw_out) st8(dw_out + i, g);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {   // Neon RMSProp, same operation order as k_optimizer
       const float gg = __fmul_rn(g[j], inv_bsz);
@@ -875,14 +877,15 @@ int umma_pack_layers(b200dqn_net* n, int which, int l0, int l1, cudaStream_t st)
 }
 
 constexpr int kUFc1Splits = 7;    // 49 k-blocks of 64 -> 7 per CTA; 4 M-tiles x 7 x 2 nets = 56 CTAs
-constexpr int kUWgradKb = 4;      // k-blocks (256 pixels) per wgrad split
+constexpr int kUWgradKb = 4;      // minimum k-blocks (of 64 pixels) per wgrad split
 
 // k-blocks (of 64 pixels) per wgrad split: at least kUWgradKb, and few enough splits (<= 48) for the
 // one-pass reduction of k_opt_conv
 int umma_wgrad_kb(int layer, int rows) {
   const int kred = layer == 0 ? rows * kP1 * kP1 : layer == 1 ? rows * kP2 * kP2 : rows * kP3 * kP3;
   const int kbs = (kred + 63) / 64;
-  const int per = (kbs + 47) / 48;
+  int per = (kbs + 47) / 48;
+  if (layer == 0 && per < 8) per = 8;   // conv1: A tiles arrive by TMA, 8 k-blocks per CTA keep the grid at 50 CTAs
   return per > kUWgradKb ? per : kUWgradKb;
 }
 int umma_wgrad_splits(int layer, int rows) {

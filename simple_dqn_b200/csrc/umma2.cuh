@@ -166,7 +166,6 @@ __global__ void __launch_bounds__(kThreads2, 1) k_umma2(const P p, const int tra
   __syncthreads();
   umma::fence_after_sync();
   pdl_wait();   // everything above overlapped the previous kernel; from here on we read its outputs
-  pdl_launch_dependents();   // now let exactly ONE successor pre-launch (it parks at its own pdl_wait)
   B2_TRACE(tid == 0, 1);
   const uint32_t tmem = s_tmem;
 
@@ -307,6 +306,10 @@ __global__ void __launch_bounds__(kThreads2, 1) k_umma2(const P p, const int tra
       B2_TRACE(tid == 0, 8 + j * 4 + 3);
     }
     B2_TRACE(tid == 0, 3);
+    // All of this CTA's loads are issued: let the successor kernel pre-launch NOW (it sets up TMEM,
+    // barriers and index tables, then parks at its pdl_wait) — late enough that its parked CTAs
+    // do not hog shared memory for long, early enough to hide its prologue behind our epilogue.
+    pdl_launch_dependents();
 
     // ================================================================ epilogue (same 8 warps)
     mbar_wait(&s_done, 0);

@@ -104,7 +104,6 @@ __global__ void __launch_bounds__(kThreads2, 1) k_umma_mn(const P p, const KTrac
   __syncthreads();
   umma::fence_after_sync();
   pdl_wait();
-  pdl_launch_dependents();
   const uint32_t tmem = s_tmem;
 
   if (nkb <= 0) {
@@ -208,6 +207,8 @@ __global__ void __launch_bounds__(kThreads2, 1) k_umma_mn(const P p, const KTrac
       umma2::cp_async_arrive_noinc(&s_full[s]);
     }
 
+    pdl_launch_dependents();   // see umma2.cuh: successor pre-launch is deferred to the end of our mainloop
+
     // ================================================================ epilogue (smem-transposed, see umma2.cuh)
     mbar_wait(&s_done, 0);
     umma::fence_after_sync();
@@ -248,8 +249,16 @@ __global__ void __launch_bounds__(kThreads2, 1) k_umma_mn(const P p, const KTrac
         // pass 1, thread <-> (row m, 8 consecutive n): RMSProp on W/S in HBM, the updated weights go
         //         back into the smem tile and into the row-oriented (dgrad) tile image;
         // pass 2, thread <-> (column n, 8 consecutive m): the column-oriented (forward) tile image.
+        constexpr int kIt = kBM * kChunksPerRow / kLoadThreads;
+        float wv[kIt][8], sv[kIt][8];
 #pragma unroll
-        for (int i = 0; i < kBM * kChunksPerRow / kLoadThreads; ++i) {
+        for (int i = 0; i < kIt; ++i) {   // all parameter loads in flight before any arithmetic
+          const int id = tid + i * kLoadThreads;
+          const int r = id / kChunksPerRow, cc = id % kChunksPerRow;
+          if (m0 + r < M && n0 + cc * 8 < N) p.load_ws(z, m0 + r, n0 + cc * 8, wv[i], sv[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < kIt; ++i) {
           const int id = tid + i * kLoadThreads;
           const int r = id / kChunksPerRow, cc = id % kChunksPerRow;
           float* src = reinterpret_cast<float*>(smem_gen + r * kPitch + cc * 32);
@@ -257,7 +266,7 @@ __global__ void __launch_bounds__(kThreads2, 1) k_umma_mn(const P p, const KTrac
           const float g[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
           if (m0 + r < M && n0 + cc * 8 < N) {
             float nw[8];
-            p.update8(z, m0 + r, n0 + cc * 8, g, nw);
+            p.update8(z, m0 + r, n0 + cc * 8, g, wv[i], sv[i], nw);
             *reinterpret_cast<float4*>(src) = make_float4(nw[0], nw[1], nw[2], nw[3]);
             *reinterpret_cast<float4*>(src + 4) = make_float4(nw[4], nw[5], nw[6], nw[7]);
           }
