@@ -384,21 +384,21 @@ static int backward_and_update(b200dqn_net* n, const FrameSource& fs, int rows, 
   cudaStream_t sA = n->side[0], sB = n->side[1], sC = n->side[2];
   cudaEvent_t* ev = n->ev;
   const bool tc = n->cfg.math_mode == B200DQN_MATH_TCGEN05;
+  static const bool fc1_fused_epilogue = getenv("B200DQN_FC1_FUSED") != nullptr;   // experimental alternative
   B2_CHECK_CUDA(cudaEventRecord(ev[0], st));                 // dZ4 and the dW5 partials are ready
   B2_CHECK_CUDA(cudaStreamWaitEvent(sA, ev[0], 0));
-  if (tc) {
+  {
     NoPdlScope side;
-    B2_TRY(optimizer_range(n, 4, 4, 1 | 4, rows, sA, "opt_fc2"));
-  } else {
-    NoPdlScope side;
-    B2_TRY(bwd_op(n, fs, rows, kFc1Wgrad, sA));
+    if (tc) B2_TRY(optimizer_range(n, 4, 4, 1 | 4, rows, sA, "opt_fc2"));
+    if (!(tc && fc1_fused_epilogue)) B2_TRY(bwd_op(n, fs, rows, kFc1Wgrad, sA));   // overlaps fc1_dgrad (few CTAs)
   }
   B2_TRY(bwd_op(n, fs, rows, kFc1Dgrad, st));
   B2_CHECK_CUDA(cudaEventRecord(ev[1], st));                 // dZ3 ready, W4 no longer needed
   B2_CHECK_CUDA(cudaStreamWaitEvent(sA, ev[1], 0));
   {
     NoPdlScope side;
-    if (tc) B2_TRY(umma_fc1_wgrad_fused(n, rows, sA, n->keep_grads));   // wgrad + RMSProp + both image refreshes
+    if (tc && fc1_fused_epilogue) B2_TRY(umma_fc1_wgrad_fused(n, rows, sA, n->keep_grads));
+    else if (tc) B2_TRY(umma_opt_fc1(n, rows, sA));          // smem-free: co-resides with the dgrad chain
     else B2_TRY(optimizer_range(n, 3, 4, 1 | 4, rows, sA, "opt_fc"));
   }
   B2_CHECK_CUDA(cudaStreamWaitEvent(sB, ev[1], 0));
@@ -876,8 +876,9 @@ extern "C" int b200dqn_net_set_keep_grads(b200dqn_net* n, int keep) {
 
 extern "C" int b200dqn_net_get_grads(b200dqn_net* n, int layer, float* host_dW, void* stream) {
   B2_REQUIRE(n && host_dW && layer >= 0 && layer < kLayers, B200DQN_EINVAL, "net_get_grads: bad argument");
-  B2_REQUIRE(n->cfg.math_mode != B200DQN_MATH_TCGEN05 || n->world > 1 || n->keep_grads, B200DQN_ESTATE,
-             "net_get_grads: call b200dqn_net_set_keep_grads(net, 1) before the step (fused optimizer)");
+  B2_REQUIRE(n->cfg.math_mode != B200DQN_MATH_TCGEN05 || n->world > 1 || n->keep_grads ||
+                 getenv("B200DQN_FC1_FUSED") == nullptr,
+             B200DQN_ESTATE, "net_get_grads: call b200dqn_net_set_keep_grads(net, 1) before the step (fused optimizer)");
   DeviceGuard g(n->device);
   cudaStream_t st = as_stream(stream);
   const int64_t n4 = n->n_params / 4;

@@ -17,6 +17,8 @@ int umma_target_synced(b200dqn_net* n, cudaStream_t st);    // target <- online
 int umma_forward(b200dqn_net* n, const uint8_t* const src[2], const int32_t* const idx[2], const int shift[2],
                  int nets, int rows, cudaStream_t st);
 int umma_fc1_splits();
+// RMSProp of the fc1 layer + refresh of both of its tile images in one smem-free kernel
+int umma_opt_fc1(b200dqn_net* n, int rows, cudaStream_t st);
 int umma_fc1_wgrad_fused(b200dqn_net* n, int rows, cudaStream_t st, bool keep_grads);
 // fused split-K reduction + RMSProp + tile-image refresh of conv layer l (0..2), single-GPU tcgen05 path
 int umma_opt_conv(b200dqn_net* n, int l, int rows, cudaStream_t st, const char* label);
