@@ -61,6 +61,15 @@ int comm_allreduce_grads(b200dqn_net* n, cudaStream_t st) {
   return B200DQN_OK;
 }
 
+// all-reduce the summed gradients of layers [l0, l1] (contiguous in d_g) on stream st
+int comm_allreduce_range(b200dqn_net* n, int l0, int l1, cudaStream_t st) {
+  B2_REQUIRE(n->nccl_comm, B200DQN_ESTATE, "communicator not initialised");
+  float* p = n->d_g + n->lt.off[l0];
+  const size_t cnt = size_t(n->lt.off[l1 + 1] - n->lt.off[l0]);
+  B2_CHECK_NCCL(g_nccl.AllReduce(p, p, cnt, kNcclFloat32, kNcclSum, (ncclComm_t)n->nccl_comm, st));
+  return B200DQN_OK;
+}
+
 void comm_destroy(b200dqn_net* n) {
   if (n->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)n->nccl_comm);
   n->nccl_comm = nullptr;

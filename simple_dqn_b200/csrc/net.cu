@@ -366,7 +366,67 @@ static int optimizer_range(b200dqn_net* n, int l0, int l1, int mode, int rows, c
 //   sC   :                               conv2_wgrad .. [after conv2_dgrad] opt(conv2)
 // In a communicator the update follows one all-reduce of the whole gradient, so the simple
 // serial order is kept.
+// Data-parallel schedule (communicator, tcgen05 engine): the fc gradient (95 % of the bytes) is summed and
+// all-reduced as soon as fc1_wgrad is done, hidden behind the dgrad chain; the three small conv gradients
+// share one all-reduce at the tail.  Both collectives run in this order on one dedicated stream (a NCCL
+// communicator must not be used from two streams at once); updates read the reduced gradient from d_g.
+static int backward_and_update_multi(b200dqn_net* n, const FrameSource& fs, int rows, cudaStream_t st) {
+  cudaStream_t sA = n->side[0], sB = n->side[1], sC = n->side[2], sN = n->side[3];
+  cudaEvent_t* ev = n->ev;
+  B2_CHECK_CUDA(cudaEventRecord(ev[0], st));                 // head done: dZ4, dW5 partials
+  B2_CHECK_CUDA(cudaStreamWaitEvent(sA, ev[0], 0));
+  {
+    NoPdlScope side;
+    B2_TRY(bwd_op(n, fs, rows, kFc1Wgrad, sA));
+    B2_TRY(optimizer_range(n, 3, 4, 1 | 2, rows, sA, "reduce_fc"));        // partials -> d_g[fc1, fc2]
+    B2_CHECK_CUDA(cudaEventRecord(ev[7], sA));
+    B2_CHECK_CUDA(cudaStreamWaitEvent(sN, ev[7], 0));
+    B2_TRY(comm_allreduce_range(n, 3, 4, sN));
+    B2_CHECK_CUDA(cudaEventRecord(ev[8], sN));
+  }
+  B2_TRY(bwd_op(n, fs, rows, kFc1Dgrad, st));
+  B2_CHECK_CUDA(cudaEventRecord(ev[1], st));                 // W4 no longer needed
+  {
+    NoPdlScope side;
+    B2_CHECK_CUDA(cudaStreamWaitEvent(sA, ev[8], 0));
+    B2_CHECK_CUDA(cudaStreamWaitEvent(sA, ev[1], 0));
+    B2_TRY(umma_opt_fc1(n, rows, sA, true));
+    B2_TRY(optimizer_range(n, 4, 4, 4, rows, sA, "opt_fc2"));
+    B2_CHECK_CUDA(cudaStreamWaitEvent(sB, ev[1], 0));
+    B2_TRY(bwd_op(n, fs, rows, kConv3Wgrad, sB));
+  }
+  B2_TRY(bwd_op(n, fs, rows, kConv3Dgrad, st));
+  B2_CHECK_CUDA(cudaEventRecord(ev[2], st));
+  {
+    NoPdlScope side;
+    B2_CHECK_CUDA(cudaStreamWaitEvent(sC, ev[2], 0));
+    B2_TRY(bwd_op(n, fs, rows, kConv2Wgrad, sC));
+  }
+  B2_TRY(bwd_op(n, fs, rows, kConv2Dgrad, st));
+  B2_TRY(bwd_op(n, fs, rows, kConv1Wgrad, st));
+  B2_CHECK_CUDA(cudaEventRecord(ev[5], sB));
+  B2_CHECK_CUDA(cudaEventRecord(ev[6], sC));
+  B2_CHECK_CUDA(cudaStreamWaitEvent(st, ev[5], 0));
+  B2_CHECK_CUDA(cudaStreamWaitEvent(st, ev[6], 0));
+  {
+    NoPdlScope tail;   // kernels around the collective use ordinary dependencies
+    B2_TRY(optimizer_range(n, 0, 2, 1 | 2, rows, st, "reduce_conv"));      // partials -> d_g[conv1..3]
+    B2_CHECK_CUDA(cudaEventRecord(ev[9], st));
+    B2_CHECK_CUDA(cudaStreamWaitEvent(sN, ev[9], 0));
+    B2_TRY(comm_allreduce_range(n, 0, 2, sN));
+    B2_CHECK_CUDA(cudaEventRecord(ev[10], sN));
+    B2_CHECK_CUDA(cudaStreamWaitEvent(st, ev[10], 0));
+    for (int l = 0; l < 3; ++l) B2_TRY(umma_opt_conv(n, l, rows, st, "opt_conv", true));
+  }
+  B2_CHECK_CUDA(cudaEventRecord(ev[4], sA));
+  B2_CHECK_CUDA(cudaStreamWaitEvent(st, ev[4], 0));
+  return B200DQN_OK;
+}
+
 static int backward_and_update(b200dqn_net* n, const FrameSource& fs, int rows, cudaStream_t st, bool update) {
+  if (update && n->world > 1 && !g_prof_on && n->use_branches && st != nullptr &&
+      n->cfg.math_mode == B200DQN_MATH_TCGEN05)
+    return backward_and_update_multi(n, fs, rows, st);
   const bool branches = update && n->world == 1 && !g_prof_on && n->use_branches && st != nullptr;
   if (!branches) {
     for (int op = kFc1Wgrad; op <= kConv1Wgrad; ++op) B2_TRY(bwd_op(n, fs, rows, BwdOp(op), st));
@@ -590,7 +650,8 @@ extern "C" int b200dqn_net_create(int device, const b200dqn_net_config* cfg, b20
   {
     int prio_lo = 0, prio_hi = 0;   // numerically larger = lower priority
     B2_CHECK_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-    for (auto& sd : n->side) B2_CHECK_CUDA(cudaStreamCreateWithPriority(&sd, cudaStreamNonBlocking, prio_lo));
+    for (int i = 0; i < 4; ++i)   // the collective stream (3) keeps the default priority
+      B2_CHECK_CUDA(cudaStreamCreateWithPriority(&n->side[i], cudaStreamNonBlocking, i < 3 ? prio_lo : prio_hi));
   }
   for (auto& e : n->ev) B2_CHECK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   n->use_graph = getenv("B200DQN_NO_GRAPH") == nullptr;

@@ -821,9 +821,8 @@ k_opt_fc1(const float* __restrict__ dw, float* __restrict__ w, float* __restrict
   pdl_wait();
   pdl_launch_dependents();
   constexpr int kNB = kHidden / 8;                       // 64 n-blocks per row
-  const int id = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < (kFlat / 8) * kNB; id += gridDim.x * blockDim.x) {
   const int kblk = id / kNB, nblk = id % kNB;
-  if (kblk >= kFlat / 8) return;
   const int k0 = kblk * 8, n0 = nblk * 8;
   float g[8][8], wv[8][8], sv[8][8];
 #pragma unroll
@@ -867,15 +866,17 @@ k_opt_fc1(const float* __restrict__ dw, float* __restrict__ w, float* __restrict
     *reinterpret_cast<uint4*>(base) = hi;
     *reinterpret_cast<uint4*>(base + 128 * 128) = lo;
   }
+  }
   kt_end(kt);
 }
 
-int umma_opt_fc1(b200dqn_net* n, int rows, cudaStream_t st) {
+int umma_opt_fc1(b200dqn_net* n, int rows, cudaStream_t st, bool from_g) {
   UmmaState* u = ust(n);
   const LayerTable& lt = n->lt;
-  const int threads = (kFlat / 8) * (kHidden / 8);
-  B2_CHECK_CUDA(launch_pdl(k_opt_fc1, dim3((threads + 127) / 128), dim3(128), 0, st,
-                           (const float*)(n->d_part + lt.part_off[3]), n->d_w + lt.off[3], n->d_s + lt.off[3],
+  // 64 CTAs with a grid-stride loop: this kernel needs ~250 registers/thread, and an uncapped grid would
+  // fill the register files of most SMs and lock the critical chain's tcgen05 CTAs out.
+  const float* dw = from_g ? n->d_g + lt.off[3] : n->d_part + lt.part_off[3];
+  B2_CHECK_CUDA(launch_pdl(k_opt_fc1, dim3(64), dim3(128), 0, st, dw, n->d_w + lt.off[3], n->d_s + lt.off[3],
                            u->img_fwd[0][3], u->img_dgr[0], 1.0f / float(rows * n->world), float(n->cfg.learning_rate),
                            float(n->cfg.decay_rate), float(1.0 - n->cfg.decay_rate), 1e-6f, ktrace_slot("opt_fc1")));
   B2_PROF("opt_fc1", st);
@@ -883,27 +884,28 @@ int umma_opt_fc1(b200dqn_net* n, int rows, cudaStream_t st) {
 }
 
 // RMSProp + image refresh of conv layer l (0..2), fused (single-GPU path of the tcgen05 engine).
-int umma_opt_conv(b200dqn_net* n, int l, int rows, cudaStream_t st, const char* label) {
+int umma_opt_conv(b200dqn_net* n, int l, int rows, cudaStream_t st, const char* label, bool from_g) {
   UmmaState* u = ust(n);
   const LayerTable& lt = n->lt;
   const float inv_bsz = 1.0f / float(rows * n->world);
   const float lr = float(n->cfg.learning_rate), decay = float(n->cfg.decay_rate);
   const float omd = float(1.0 - n->cfg.decay_rate), eps = 1e-6f;
-  const float* part = n->d_part + lt.part_off[l];
+  const float* part = from_g ? n->d_g + lt.off[l] : n->d_part + lt.part_off[l];
+  const int nsplits = from_g ? 1 : lt.splits[l];
   float* w = n->d_w + lt.off[l];
   float* s = n->d_s + lt.off[l];
-  B2_REQUIRE(lt.splits[l] <= 64, B200DQN_EINVAL, "k_opt_conv handles at most 64 split-K partials");
+  B2_REQUIRE(nsplits <= 64, B200DQN_EINVAL, "k_opt_conv handles at most 64 split-K partials");
   const int64_t size = lt.off[l + 1] - lt.off[l];
   const dim3 grid(unsigned((size / 4 + 31) / 32)), block(256);
   cudaError_t e;
   if (l == 0)
-    e = launch_pdl(k_opt_conv<kK1, kC1, false, 4, 8, 4>, grid, block, 0, st, part, lt.splits[l], w, s, u->img_fwd[0][0],
+    e = launch_pdl(k_opt_conv<kK1, kC1, false, 4, 8, 4>, grid, block, 0, st, part, nsplits, w, s, u->img_fwd[0][0],
                    (uint8_t*)nullptr, inv_bsz, lr, decay, omd, eps, ktrace_slot(label));
   else if (l == 1)
-    e = launch_pdl(k_opt_conv<kK2, kC2, true, kC1, 4, 2>, grid, block, 0, st, part, lt.splits[l], w, s, u->img_fwd[0][1],
+    e = launch_pdl(k_opt_conv<kK2, kC2, true, kC1, 4, 2>, grid, block, 0, st, part, nsplits, w, s, u->img_fwd[0][1],
                    u->img_dgr[2], inv_bsz, lr, decay, omd, eps, ktrace_slot(label));
   else
-    e = launch_pdl(k_opt_conv<kK3, kC3, true, kC2, 3, 1>, grid, block, 0, st, part, lt.splits[l], w, s, u->img_fwd[0][2],
+    e = launch_pdl(k_opt_conv<kK3, kC3, true, kC2, 3, 1>, grid, block, 0, st, part, nsplits, w, s, u->img_fwd[0][2],
                    u->img_dgr[1], inv_bsz, lr, decay, omd, eps, ktrace_slot(label));
   B2_CHECK_CUDA(e);
   B2_PROF(label, st);

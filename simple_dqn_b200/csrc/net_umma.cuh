@@ -18,10 +18,11 @@ int umma_forward(b200dqn_net* n, const uint8_t* const src[2], const int32_t* con
                  int nets, int rows, cudaStream_t st);
 int umma_fc1_splits();
 // RMSProp of the fc1 layer + refresh of both of its tile images in one smem-free kernel
-int umma_opt_fc1(b200dqn_net* n, int rows, cudaStream_t st);
+int umma_opt_fc1(b200dqn_net* n, int rows, cudaStream_t st, bool from_g = false);
 int umma_fc1_wgrad_fused(b200dqn_net* n, int rows, cudaStream_t st, bool keep_grads);
 // fused split-K reduction + RMSProp + tile-image refresh of conv layer l (0..2), single-GPU tcgen05 path
-int umma_opt_conv(b200dqn_net* n, int l, int rows, cudaStream_t st, const char* label);
+// from_g: read the (all-reduced) gradient from d_g instead of the split-K partials
+int umma_opt_conv(b200dqn_net* n, int l, int rows, cudaStream_t st, const char* label, bool from_g = false);
 // rebuild the fp16 hi/lo tile images of layers [l0, l1] of network `which` (0 online, 1 target)
 int umma_pack_layers(b200dqn_net* n, int which, int l0, int l1, cudaStream_t st);
 // fp16 hi plane of dZ4 and the offset of its lo plane (nullptr when math_mode != TCGEN05)
@@ -36,6 +37,7 @@ int umma_backward_launches();
 
 // NCCL glue (comm.cu)
 int comm_allreduce_grads(b200dqn_net* n, cudaStream_t st);
+int comm_allreduce_range(b200dqn_net* n, int l0, int l1, cudaStream_t st);
 void comm_destroy(b200dqn_net* n);
 
 }  // namespace b200
