@@ -809,63 +809,41 @@ k_opt_conv(const float* __restrict__ part, int splits, float* __restrict__ w, fl
   kt_end(kt);
 }
 
-// fc1 optimizer, fused with both tile-image refreshes.  One thread owns an 8 (k) x 8 (n) block of W4,
-// so it can emit whole 16-byte chunks of BOTH images (dgrad: rows = k, chunks along n; forward: rows = n,
-// chunks along k).  No shared memory: these CTAs co-reside with the tcgen05 kernels of the critical
-// chain instead of competing with them for SMs.
-__global__ void __launch_bounds__(128)
-k_opt_fc1(const float* __restrict__ dw, float* __restrict__ w, float* __restrict__ sst, uint8_t* __restrict__ img_fwd,
-          uint8_t* __restrict__ img_dgr, float inv_bsz, float lr, float decay, float one_m_decay, float eps,
-          const KTrace kt) {
+// fc1 optimizer: RMSProp on 8 consecutive hidden units of one flat index per thread — which is exactly
+// one 16-byte chunk of the row-oriented (dgrad) tile image, refreshed in the same pass; the
+// column-oriented (forward) image is rebuilt by k_pack_image right after.  Both kernels are smem-free,
+// light on registers and launched on a CAPPED grid (2 CTAs per SM, grid-stride loop) so that they
+// co-reside with the tcgen05 kernels of the critical chain instead of locking them out of the SMs.
+__global__ void __launch_bounds__(256)
+k_opt_fc1(const float* __restrict__ dw, float* __restrict__ w, float* __restrict__ sst, uint8_t* __restrict__ img_dgr,
+          float inv_bsz, float lr, float decay, float one_m_decay, float eps, const KTrace kt) {
   kt_begin(kt);
   pdl_wait();
   pdl_launch_dependents();
-  constexpr int kNB = kHidden / 8;                       // 64 n-blocks per row
-  for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < (kFlat / 8) * kNB; id += gridDim.x * blockDim.x) {
-  const int kblk = id / kNB, nblk = id % kNB;
-  const int k0 = kblk * 8, n0 = nblk * 8;
-  float g[8][8], wv[8][8], sv[8][8];
-#pragma unroll
-  for (int r = 0; r < 8; ++r) {                          // 24 independent 32-byte loads in flight
-    const int64_t i = int64_t(k0 + r) * kHidden + n0;
-    ld8(dw + i, g[r]);
-    ld8(w + i, wv[r]);
-    ld8(sst + i, sv[r]);
-  }
-#pragma unroll
-  for (int r = 0; r < 8; ++r) {
+  constexpr int kNB = kHidden / 8;
+  for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < kFlat * kNB; id += gridDim.x * blockDim.x) {
+    const int m = id / kNB, n0 = (id % kNB) * 8;
+    const int64_t i = int64_t(m) * kHidden + n0;
+    float g[8], wv[8], sv[8];
+    ld8(dw + i, g);
+    ld8(w + i, wv);
+    ld8(sst + i, sv);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {                        // Neon RMSProp, operation order of k_optimizer
-      const float gg = __fmul_rn(g[r][j], inv_bsz);
-      const float ns = __fadd_rn(__fmul_rn(decay, sv[r][j]), __fmul_rn(__fmul_rn(gg, gg), one_m_decay));
+      const float gg = __fmul_rn(g[j], inv_bsz);
+      const float ns = __fadd_rn(__fmul_rn(decay, sv[j]), __fmul_rn(__fmul_rn(gg, gg), one_m_decay));
       const float den = __fadd_rn(__fsqrt_rn(__fadd_rn(ns, eps)), eps);
-      wv[r][j] = __fsub_rn(wv[r][j], __fdiv_rn(__fmul_rn(gg, lr), den));
-      sv[r][j] = ns;
+      wv[j] = __fsub_rn(wv[j], __fdiv_rn(__fmul_rn(gg, lr), den));
+      sv[j] = ns;
     }
-    const int64_t i = int64_t(k0 + r) * kHidden + n0;
-    st8(w + i, wv[r]);
-    st8(sst + i, sv[r]);
-    uint4 hi, lo;                                        // dgrad image: row = flat index k, chunk = 8 hidden units
-    umma::split8(wv[r], hi, lo);
-    const int m = k0 + r;
+    st8(w + i, wv);
+    st8(sst + i, sv);
+    uint4 hi, lo;
+    umma::split8(wv, hi, lo);
     uint8_t* base = img_dgr + (int64_t(m / 128) * (kHidden / 64) + n0 / 64) * (128 * 256) +
                     umma::sw128_off(m % 128, (n0 % 64) / 8);
     *reinterpret_cast<uint4*>(base) = hi;
     *reinterpret_cast<uint4*>(base + 128 * 128) = lo;
-  }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {                          // forward image: row = hidden unit n, chunk = 8 flat indexes
-    float col[8];
-#pragma unroll
-    for (int r = 0; r < 8; ++r) col[r] = wv[r][j];
-    uint4 hi, lo;
-    umma::split8(col, hi, lo);
-    const int nn = n0 + j;
-    uint8_t* base = img_fwd + (int64_t(nn / 128) * (kFlat / 64) + k0 / 64) * (128 * 256) +
-                    umma::sw128_off(nn % 128, (k0 % 64) / 8);
-    *reinterpret_cast<uint4*>(base) = hi;
-    *reinterpret_cast<uint4*>(base + 128 * 128) = lo;
-  }
   }
   kt_end(kt);
 }
@@ -873,14 +851,12 @@ k_opt_fc1(const float* __restrict__ dw, float* __restrict__ w, float* __restrict
 int umma_opt_fc1(b200dqn_net* n, int rows, cudaStream_t st, bool from_g) {
   UmmaState* u = ust(n);
   const LayerTable& lt = n->lt;
-  // 64 CTAs with a grid-stride loop: this kernel needs ~250 registers/thread, and an uncapped grid would
-  // fill the register files of most SMs and lock the critical chain's tcgen05 CTAs out.
   const float* dw = from_g ? n->d_g + lt.off[3] : n->d_part + lt.part_off[3];
-  B2_CHECK_CUDA(launch_pdl(k_opt_fc1, dim3(64), dim3(128), 0, st, dw, n->d_w + lt.off[3], n->d_s + lt.off[3],
-                           u->img_fwd[0][3], u->img_dgr[0], 1.0f / float(rows * n->world), float(n->cfg.learning_rate),
+  B2_CHECK_CUDA(launch_pdl(k_opt_fc1, dim3(2 * 148), dim3(256), 0, st, dw, n->d_w + lt.off[3], n->d_s + lt.off[3],
+                           u->img_dgr[0], 1.0f / float(rows * n->world), float(n->cfg.learning_rate),
                            float(n->cfg.decay_rate), float(1.0 - n->cfg.decay_rate), 1e-6f, ktrace_slot("opt_fc1")));
   B2_PROF("opt_fc1", st);
-  return B200DQN_OK;
+  return umma2::launch_pack("pack_fc1f", PackFc1Fwd{n->d_w + lt.off[3]}, u->img_fwd[0][3], st, 2 * 148);
 }
 
 // RMSProp + image refresh of conv layer l (0..2), fused (single-GPU path of the tcgen05 engine).

@@ -409,10 +409,9 @@ __global__ void __launch_bounds__(256) k_pack_image(const S src, uint8_t* __rest
   const int rows = src.rows(), nkb = src.kblocks();
   const int64_t chunks_per_tile_kb = int64_t(rows) * 8;
   const int64_t total = int64_t(src.tiles()) * nkb * chunks_per_tile_kb;
-  const int64_t id = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
   pdl_wait();
   pdl_launch_dependents();
-  if (id >= total) return;
+  for (int64_t id = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; id < total; id += int64_t(gridDim.x) * blockDim.x) {
   const int64_t tk = id / chunks_per_tile_kb;
   const int within = int(id % chunks_per_tile_kb);
   const int tile = int(tk / nkb), kb = int(tk % nkb);
@@ -425,13 +424,17 @@ __global__ void __launch_bounds__(256) k_pack_image(const S src, uint8_t* __rest
   uint8_t* base = image + tk * (int64_t(rows) * 256);
   *reinterpret_cast<uint4*>(base + umma::sw128_off(r, c)) = hi;
   *reinterpret_cast<uint4*>(base + int64_t(rows) * 128 + umma::sw128_off(r, c)) = lo;
+  }
   kt_end(kt);
 }
 
+// max_ctas > 0 caps the grid (grid-stride loop) for launches that must not crowd the SMs
 template <class S>
-static int launch_pack(const char* label, const S& src, uint8_t* image, cudaStream_t st) {
+static int launch_pack(const char* label, const S& src, uint8_t* image, cudaStream_t st, int max_ctas = 0) {
   const int64_t total = int64_t(src.tiles()) * src.kblocks() * src.rows() * 8;
-  B2_CHECK_CUDA(launch_pdl(k_pack_image<S>, dim3(unsigned((total + 255) / 256)), dim3(256), 0, st, src, image, ktrace_slot(label)));
+  unsigned grid = unsigned((total + 255) / 256);
+  if (max_ctas > 0 && grid > unsigned(max_ctas)) grid = unsigned(max_ctas);
+  B2_CHECK_CUDA(launch_pdl(k_pack_image<S>, dim3(grid), dim3(256), 0, st, src, image, ktrace_slot(label)));
   B2_PROF(label, st);
   return B200DQN_OK;
 }
