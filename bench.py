@@ -285,6 +285,9 @@ def run_b200(a, rank, world, local_rank):
         roof = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s"}
     roof["frac"] = roof["achieved"] / roof["peak"]
     roof["traffic"] = None
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")     # dram bytes per launch from the committed ncu capture
+    if os.path.exists(tp):
+        roof["traffic"] = json.load(open(tp)).get(a.math, {}).get(top)
     roof["peak_source"] = pk["source"] + (", sustained figure (kernel timed inside a long step)"
                                            if bound == "tensor" else "")
     roof["us_per_launch"] = per_kernel[top] * 1e3
@@ -329,10 +332,11 @@ def run_b200(a, rank, world, local_rank):
         dist.all_reduce(d, op=dist.ReduceOp.MAX)
         dts = d.cpu()
     e2e = {"value": world * e2e_steps / float(dts[0]), "unit": UNIT,
-           "h2d_bytes_per_step": 4 * 7056 + 625 * 4, "d2h_bytes_per_step": 625 * 4 + 4 * 1024 + 4,
+           "h2d_bytes_per_step": 4 * 7056, "d2h_bytes_per_step": 4 + 4,
            "steps": e2e_steps,
-           "what": "per step: 4x ReplayMemory.add(host frame) + getMinibatch() with the host `random` stream "
-                   "(MT19937 state up/down) + DeepQNetwork.train() + cost to the callback"}
+           "what": "per step: 4x ReplayMemory.add(host frame -> pinned -> HBM) + getMinibatch() in lock-step with the "
+                   "host `random` stream (words-consumed read back) + DeepQNetwork.train() + cost read back for "
+                   "the stats callback"}
     assert len(costs) == e2e_steps + 10 and np.isfinite(costs).all()
     net.callback = None
 

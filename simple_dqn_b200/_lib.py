@@ -59,6 +59,7 @@ SIGNATURES = {
     "b200dqn_replay_set_rng": [_P, _P, _P],
     "b200dqn_replay_get_rng": [_P, _P, _P],
     "b200dqn_replay_sample": [_P, _P],
+    "b200dqn_replay_sample_sync": [_P, _u32p, _P],
     "b200dqn_replay_set_indexes": [_P, _P, _P],
     "b200dqn_replay_gather": [_P, _P],
     "b200dqn_replay_read_minibatch": [_P, _P, _P, _P, _P, _P, _P, _P, _P],
@@ -81,6 +82,7 @@ SIGNATURES = {
     "b200dqn_net_train": [_P, _P, _P, _P, _P, _P, _f32p, _P],
     "b200dqn_net_train_device": [_P, _P, _P, _P, _P, _P, _P],
     "b200dqn_net_train_sampled": [_P, _P, _P],
+    "b200dqn_net_train_sampled_cost": [_P, _P, _f32p, _P],
     "b200dqn_net_train_fused": [_P, _P, C.c_int, _P],
     "b200dqn_net_read_costs": [_P, C.c_int, _P, _P],
     "b200dqn_net_train_iterations": [_P, _i64p],

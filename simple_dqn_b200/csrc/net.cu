@@ -125,6 +125,7 @@ k_head(const float* __restrict__ part, int splits, int rows, float* h4_online, f
     for (int bb = 0; bb < rows; ++bb) tot += __ldcg(td.row_cost + bb);
     const uint32_t sidx = *td.step;
     td.cost_ring[sidx % kCostRing] = tot / float(rows);
+    td.cost_ring[kCostRing] = tot / float(rows);   // "latest" slot: one 4-byte read for the stats callback
     *td.step = sidx + 1;
   }
   for (int i = t; i <= rows; i += kHidden) td.ticket[i] = 0;
@@ -629,7 +630,7 @@ extern "C" int b200dqn_net_create(int device, const b200dqn_net_config* cfg, b20
   B2_CHECK_CUDA(fmalloc(&n->d_dz3, size_t(nb) * kFlat));
   B2_CHECK_CUDA(fmalloc(&n->d_dz2, size_t(nb) * kP2 * kP2 * kC2));
   B2_CHECK_CUDA(fmalloc(&n->d_dz1, size_t(nb) * kP1 * kP1 * kC1));
-  B2_CHECK_CUDA(fmalloc(&n->d_cost, kCostRing));
+  B2_CHECK_CUDA(fmalloc(&n->d_cost, kCostRing + 1));
   B2_CHECK_CUDA(cudaMalloc(&n->d_step, sizeof(uint32_t)));
   B2_CHECK_CUDA(cudaMemset(n->d_step, 0, sizeof(uint32_t)));
   B2_CHECK_CUDA(cudaMalloc(&n->d_ticket, (nb + 1) * sizeof(uint32_t)));
@@ -670,6 +671,7 @@ extern "C" int b200dqn_net_destroy(b200dqn_net* n) {
   comm_destroy(n);
   umma_net_destroy(n);
   if (n->graph_exec) cudaGraphExecDestroy(n->graph_exec);
+  if (n->graph_train_exec) cudaGraphExecDestroy(n->graph_train_exec);
   for (auto& sd : n->side) if (sd) cudaStreamDestroy(sd);
   for (auto& e : n->ev) if (e) cudaEventDestroy(e);
   if (n->d_tw != n->d_w) { cudaFree(n->d_tw); cudaFree(n->d_ts); }
@@ -837,13 +839,48 @@ static int train_on_ring(b200dqn_net* n, b200dqn_replay* r, cudaStream_t st) {
   return train_step(n, fs, r->d_actions, r->d_rewards, r->d_terminals, my_idx, st);
 }
 
+// train_on_ring through a cached CUDA graph (the sampler is NOT part of it: the indexes are already in r)
+static int train_sampled_launch(b200dqn_net* n, b200dqn_replay* r, cudaStream_t st) {
+  const bool use_graph = n->use_graph && !g_prof_on && st != nullptr;
+  if (!use_graph) return train_on_ring(n, r, st);
+  if (!n->graph_train_exec || n->graph_train_replay != r || n->graph_train_stream != st ||
+      n->graph_train_world != n->world || n->graph_train_gen != g_ktrace_gen) {
+    if (n->graph_train_exec) { cudaGraphExecDestroy(n->graph_train_exec); n->graph_train_exec = nullptr; }
+    cudaGraph_t graph = nullptr;
+    B2_CHECK_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    int rc = train_on_ring(n, r, st);
+    cudaError_t e = cudaStreamEndCapture(st, &graph);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    B2_CHECK_CUDA(e);
+    B2_CHECK_CUDA(cudaGraphInstantiate(&n->graph_train_exec, graph, 0));
+    cudaGraphDestroy(graph);
+    n->graph_train_replay = r; n->graph_train_stream = st; n->graph_train_world = n->world;
+    n->graph_train_gen = g_ktrace_gen;
+  }
+  B2_CHECK_CUDA(cudaGraphLaunch(n->graph_train_exec, st));
+  return B200DQN_OK;
+}
+
 extern "C" int b200dqn_net_train_sampled(b200dqn_net* n, b200dqn_replay* r, void* stream) {
   B2_REQUIRE(n && r, B200DQN_EINVAL, "net_train_sampled: null argument");
   int rc = check_fusable(n, r);
   if (rc) return rc;
   DeviceGuard g(n->device);
-  B2_TRY(train_on_ring(n, r, as_stream(stream)));
+  B2_TRY(train_sampled_launch(n, r, as_stream(stream)));
   n->train_iterations += 1;
+  return B200DQN_OK;
+}
+
+extern "C" int b200dqn_net_train_sampled_cost(b200dqn_net* n, b200dqn_replay* r, float* host_cost, void* stream) {
+  B2_REQUIRE(host_cost, B200DQN_EINVAL, "net_train_sampled_cost: null argument");
+  int rc = b200dqn_net_train_sampled(n, r, stream);
+  if (rc) return rc;
+  DeviceGuard g(n->device);
+  cudaStream_t st = as_stream(stream);
+  float* pin = reinterpret_cast<float*>(n->h_pin);
+  B2_CHECK_CUDA(cudaMemcpyAsync(pin, n->d_cost + kCostRing, sizeof(float), cudaMemcpyDeviceToHost, st));
+  B2_CHECK_CUDA(cudaStreamSynchronize(st));
+  *host_cost = pin[0];
   return B200DQN_OK;
 }
 
@@ -932,6 +969,7 @@ extern "C" int b200dqn_net_set_keep_grads(b200dqn_net* n, int keep) {
   B2_REQUIRE(n, B200DQN_EINVAL, "null net");
   n->keep_grads = keep != 0;
   if (n->graph_exec) { cudaGraphExecDestroy(n->graph_exec); n->graph_exec = nullptr; }   // parameters are baked in
+  if (n->graph_train_exec) { cudaGraphExecDestroy(n->graph_train_exec); n->graph_train_exec = nullptr; }
   return B200DQN_OK;
 }
 

@@ -71,6 +71,10 @@ struct b200dqn_net {
   cudaStream_t graph_stream = nullptr;
   int graph_world = 0;
   int graph_trace_gen = 0;
+  cudaGraphExec_t graph_train_exec = nullptr;   // same step without the sampler (train on pre-sampled indexes)
+  b200dqn_replay* graph_train_replay = nullptr;
+  cudaStream_t graph_train_stream = nullptr;
+  int graph_train_world = 0, graph_train_gen = 0;
 
   void* umma_state = nullptr;  // tcgen05 engine: fp16 operand planes + weight tile images (net_umma.cu)
 

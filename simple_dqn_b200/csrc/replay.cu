@@ -394,6 +394,20 @@ extern "C" int b200dqn_replay_sample(b200dqn_replay* r, void* stream) {
   return launch_sample(r, as_stream(stream));
 }
 
+extern "C" int b200dqn_replay_sample_sync(b200dqn_replay* r, uint32_t* host_words_consumed, void* stream) {
+  B2_REQUIRE(host_words_consumed, B200DQN_EINVAL, "replay_sample_sync: null argument");
+  int rc = b200dqn_replay_sample(r, stream);
+  if (rc) return rc;
+  DeviceGuard g(r->device);
+  cudaStream_t st = as_stream(stream);
+  uint32_t* pin = reinterpret_cast<uint32_t*>(r->h_stage);   // slot 0 of the pinned block doubles as a 4-byte landing pad
+  B2_CHECK_CUDA(cudaEventSynchronize(r->slot_done[0]));
+  B2_CHECK_CUDA(cudaMemcpyAsync(pin, r->d_words, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  B2_CHECK_CUDA(cudaStreamSynchronize(st));
+  *host_words_consumed = pin[0];
+  return B200DQN_OK;
+}
+
 extern "C" int b200dqn_replay_set_indexes(b200dqn_replay* r, const int32_t* host_indexes, void* stream) {
   B2_REQUIRE(r && host_indexes, B200DQN_EINVAL, "replay_set_indexes: null argument");
   for (int i = 0; i < r->batch; ++i)

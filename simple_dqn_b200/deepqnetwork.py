@@ -159,10 +159,14 @@ class DeepQNetwork:
     def train(self, minibatch, epoch=0):
         """deepqnetwork.py:107-172.  A pristine DeviceMinibatch is trained in place from the ring."""
         if isinstance(minibatch, DeviceMinibatch) and not minibatch.materialised:
-            L.call("b200dqn_net_train_sampled", self._h, minibatch._mem._h, self._stream)
-            self.train_iterations += 1
             if self.callback:
-                self.callback.on_train(self.last_costs(1)[0])
+                cost = C.c_float()
+                L.call("b200dqn_net_train_sampled_cost", self._h, minibatch._mem._h, C.byref(cost), self._stream)
+                self.train_iterations += 1
+                self.callback.on_train(cost.value)                      # :171-172
+            else:
+                L.call("b200dqn_net_train_sampled", self._h, minibatch._mem._h, self._stream)
+                self.train_iterations += 1
             return
         prestates, actions, rewards, poststates, terminals = minibatch
         assert len(prestates.shape) == 4                                # :110-116

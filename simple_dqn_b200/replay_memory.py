@@ -77,6 +77,7 @@ class ReplayMemory:
         self.prestates = np.empty((self.batch_size, self.history_length) + self.dims, dtype=np.uint8)
         self.poststates = np.empty((self.batch_size, self.history_length) + self.dims, dtype=np.uint8)
         self._rng_on_device = False
+        self._host_state_in_sync = None       # host `random` state known to equal the device stream
         self._sample_ticket = 0
         self.last_indexes = None
         self.last_words_consumed = None
@@ -180,10 +181,17 @@ class ReplayMemory:
         """Enqueue the index draw of getMinibatch (:55-69); nothing comes back to the host."""
         assert self.count > self.history_length                        # :52
         if self.rng_mode == "python":
-            self.seed_device_rng(random)
-            L.call("b200dqn_replay_sample", self._h, self._stream)
-            key = self.read_device_rng()
-            random.setstate((3, tuple(int(x) for x in key), None))
+            # Lock-step with the process-global stream: upload the 625-word state only if somebody else
+            # drew from `random` since our last sample, and advance the host by exactly the number of
+            # 32-bit words the device consumed (every trial of replay_memory.py:59 costs one word).
+            if random.getstate()[1] != self._host_state_in_sync:
+                self.seed_device_rng(random)
+            words = C.c_uint32()
+            L.call("b200dqn_replay_sample_sync", self._h, C.byref(words), self._stream)
+            for _ in range(words.value):
+                random.getrandbits(32)
+            self._host_state_in_sync = random.getstate()[1]
+            self.last_words_consumed = words.value
         else:
             if not self._rng_on_device:
                 self.seed_device_rng(random)
