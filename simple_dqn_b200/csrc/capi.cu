@@ -16,6 +16,7 @@ void set_error(const char* fmt, ...) {
 bool g_prof_on = false;
 bool g_use_pdl = getenv("B200DQN_NO_PDL") == nullptr;
 thread_local bool g_pdl_suppressed = false;
+long long g_launch_count = 0;
 namespace {
 constexpr int kProfCap = 8192;
 struct Prof {

@@ -78,6 +78,7 @@ __device__ __forceinline__ void kt_end(const KTrace& kt) {
   if (kt.buf && threadIdx.x == 0) atomicMax(kt.buf + 2 * kt.slot + 1, globaltimer_ns());
 }
 extern bool g_use_pdl;   // B200DQN_NO_PDL unset
+extern long long g_launch_count;   // every kernel launch of the library (bench.py's gpu_launches)
 
 // Launch `kernel` with the programmatic-dependent-launch attribute (every kernel launched this way
 // calls pdl_wait() before it touches data produced by earlier kernels).
@@ -104,6 +105,7 @@ static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 b
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = (g_use_pdl && !g_pdl_suppressed) ? 1 : 0;
+  ++g_launch_count;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

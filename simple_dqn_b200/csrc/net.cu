@@ -223,6 +223,7 @@ static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 template <class P, int BM, int BN, int BK, int TM, int TN>
 static int launch_gemm(const char* label, const P& p, int M, int N, int Z, cudaStream_t st) {
   dim3 grid(cdiv(M, BM), cdiv(N, BN), Z);
+  ++g_launch_count;
   k_simt_gemm<P, BM, BN, BK, TM, TN><<<grid, (BM / TM) * (BN / TN), 0, st>>>(p);
   B2_LAUNCH_CHECK();
   B2_PROF(label, st);
@@ -428,7 +429,8 @@ static int backward_and_update(b200dqn_net* n, const FrameSource& fs, int rows, 
   if (update && n->world > 1 && !g_prof_on && n->use_branches && st != nullptr &&
       n->cfg.math_mode == B200DQN_MATH_TCGEN05)
     return backward_and_update_multi(n, fs, rows, st);
-  const bool branches = update && n->world == 1 && !g_prof_on && n->use_branches && st != nullptr;
+  // Under the event profiler the same kernels run, but every "branch" is the main stream (serialised).
+  const bool branches = update && n->world == 1 && n->use_branches && (st != nullptr || g_prof_on);
   if (!branches) {
     for (int op = kFc1Wgrad; op <= kConv1Wgrad; ++op) B2_TRY(bwd_op(n, fs, rows, BwdOp(op), st));
     if (!update) return B200DQN_OK;
@@ -442,7 +444,7 @@ static int backward_and_update(b200dqn_net* n, const FrameSource& fs, int rows, 
     }
     return B200DQN_OK;
   }
-  cudaStream_t sA = n->side[0], sB = n->side[1], sC = n->side[2];
+  cudaStream_t sA = g_prof_on ? st : n->side[0], sB = g_prof_on ? st : n->side[1], sC = g_prof_on ? st : n->side[2];
   cudaEvent_t* ev = n->ev;
   const bool tc = n->cfg.math_mode == B200DQN_MATH_TCGEN05;
   static const bool fc1_fused_epilogue = getenv("B200DQN_FC1_FUSED") != nullptr;   // experimental alternative
@@ -901,8 +903,10 @@ extern "C" int b200dqn_net_train_fused(b200dqn_net* n, b200dqn_replay* r, int ns
       if (n->graph_exec) { cudaGraphExecDestroy(n->graph_exec); n->graph_exec = nullptr; }
       cudaGraph_t graph = nullptr;
       B2_CHECK_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      const long long launches_before = g_launch_count;
       rc = launch_sample(r, st);
       if (!rc) rc = train_on_ring(n, r, st);
+      n->graph_launches = int(g_launch_count - launches_before);
       cudaError_t e = cudaStreamEndCapture(st, &graph);
       if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
       B2_CHECK_CUDA(e);
@@ -991,11 +995,13 @@ extern "C" int b200dqn_net_get_grads(b200dqn_net* n, int layer, float* host_dW, 
 
 extern "C" int b200dqn_net_launches_per_step(const b200dqn_net* n, int* launches) {
   B2_REQUIRE(n && launches, B200DQN_EINVAL, "null argument");
-  // sample + forward (4 GEMM-shaped) + head (fc2 + td + fc2_bwd) + 7 backward GEMMs + optimizer launches
-  // (5 per-layer-group launches on one GPU; reduce + update around the all-reduce in a communicator)
-  int fwd = (n->cfg.math_mode == B200DQN_MATH_TCGEN05) ? umma_forward_launches() : 4;
-  int bwd = (n->cfg.math_mode == B200DQN_MATH_TCGEN05 && umma_has_backward()) ? umma_backward_launches() : 7;
-  const bool branches = n->world == 1 && n->use_branches;
-  *launches = 1 + fwd + 1 + bwd + (n->world > 1 ? 2 : (branches ? 4 : 1));
+  // Counted at the launch sites while the step was captured into its CUDA graph; before the first
+  // fused step: the static schedule (sample, 4 forward, head, 7 backward GEMMs, per-layer optimizers).
+  if (n->graph_launches > 0) {
+    *launches = n->graph_launches;
+  } else {
+    const bool tc = n->cfg.math_mode == B200DQN_MATH_TCGEN05;
+    *launches = 1 + 4 + 1 + 7 + (n->world > 1 ? (tc ? 7 : 2) : (tc ? 6 : 4));
+  }
   return B200DQN_OK;
 }

@@ -71,6 +71,7 @@ struct b200dqn_net {
   cudaStream_t graph_stream = nullptr;
   int graph_world = 0;
   int graph_trace_gen = 0;
+  int graph_launches = 0;   // kernels launched by one captured step
   cudaGraphExec_t graph_train_exec = nullptr;   // same step without the sampler (train on pre-sampled indexes)
   b200dqn_replay* graph_train_replay = nullptr;
   cudaStream_t graph_train_stream = nullptr;
