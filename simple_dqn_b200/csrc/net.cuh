@@ -63,7 +63,7 @@ struct b200dqn_net {
   // step scheduling: side streams / events for the independent wgrad + optimizer branches, and the
   // captured CUDA graph of one fused step
   cudaStream_t side[4] = {};   // three wgrad/optimizer branches + the collective stream
-  cudaEvent_t ev[11] = {};
+  cudaEvent_t ev[15] = {};
   bool use_graph = true, use_branches = true;
   bool keep_grads = false;   // fused optimizers also write dW for b200dqn_net_get_grads (tests)
   cudaGraphExec_t graph_exec = nullptr;
