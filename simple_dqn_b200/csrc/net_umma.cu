@@ -341,7 +341,7 @@ struct V2Conv1Fwd {
   static constexpr int kBN = 32;
   static constexpr bool kAExact = true, kARowMajorThreads = true, kBRowMajorThreads = false;
   static constexpr int kAMode = umma2::kReg, kBMode = umma2::kBulk;
-  static constexpr bool kStagedEpilogue = true, kDumpA = true;
+  static constexpr bool kStagedEpilogue = true, kDumpA = true, kPrefetch = false;
   uint8_t* im2col;          // online net only: [mtile][4 kb][128 x 128 B] A_hi tiles for conv1_wgrad (nullptr = off)
   const uint8_t* src[2];
   const int32_t* idx[2];
@@ -385,7 +385,7 @@ struct V2ConvFwd {
   static constexpr int kBN = KO;
   static constexpr bool kAExact = false, kARowMajorThreads = true, kBRowMajorThreads = false;
   static constexpr int kAMode = umma2::kAsync, kBMode = umma2::kBulk;
-  static constexpr bool kStagedEpilogue = true, kDumpA = false;
+  static constexpr bool kStagedEpilogue = true, kDumpA = false, kPrefetch = false;
   PlanePair in16[2];
   const uint8_t* wimg[2];   // [K/64][hi KOx128 | lo KOx128]
   float* out[2];
@@ -417,7 +417,7 @@ struct V2Fc1Fwd {
   static constexpr int kBN = 32;
   static constexpr bool kAExact = false, kARowMajorThreads = false, kBRowMajorThreads = true;
   static constexpr int kAMode = umma2::kBulk, kBMode = umma2::kAsync;
-  static constexpr bool kStagedEpilogue = false, kDumpA = false;   // a thread's outputs are strided; lanes run along m
+  static constexpr bool kStagedEpilogue = false, kDumpA = false, kPrefetch = false;   // strided outputs; lanes run along m
   PlanePair in16[2];        // H3 planes [rows][3136]
   const uint8_t* wimg[2];   // [4 mtiles][49 kb][hi 128x128 | lo 128x128]
   float* part;              // [2*splits][rows][512]
@@ -450,7 +450,7 @@ struct V2Fc1Dgrad {
   static constexpr int kBN = 32;
   static constexpr bool kAExact = false, kARowMajorThreads = true, kBRowMajorThreads = true;
   static constexpr int kAMode = umma2::kBulk, kBMode = umma2::kAsync;
-  static constexpr bool kStagedEpilogue = false, kDumpA = false;
+  static constexpr bool kStagedEpilogue = false, kDumpA = false, kPrefetch = true;
   const uint8_t* wimg;   // [25 mtiles][8 kb][hi | lo]   rows m = flat index (p,q,c), K = hidden unit
   PlanePair dz4;         // [rows][512]
   const float* h3;       // [rows][3136] (mask)
@@ -469,12 +469,16 @@ struct V2Fc1Dgrad {
     off = rc.base + kk;
     return true;
   }
-  __device__ void store8(int, int m, int n0, const float v[8]) const {
+  __device__ void prefetch8(int, int m, int n0, float pf[8]) const {   // Rectlin mask of H3
+#pragma unroll
+    for (int j = 0; j < 8; ++j) pf[j] = (n0 + j < rows) ? h3[int64_t(n0 + j) * kFlat + m] : 0.f;
+  }
+  __device__ void store8p(int, int m, int n0, const float v[8], const float pf[8]) const {
 #pragma unroll
     for (int j = 0; j < 8; ++j)
       if (n0 + j < rows) {
         const int64_t i = int64_t(n0 + j) * kFlat + m;
-        const float o = h3[i] > 0.f ? v[j] : 0.f;
+        const float o = pf[j] > 0.f ? v[j] : 0.f;
         dz3[i] = o;
         __half h, l;
         umma2::split1(o, h, l);
@@ -491,7 +495,7 @@ struct V2ConvDgrad {
   static constexpr int kBN = C;
   static constexpr bool kAExact = false, kARowMajorThreads = true, kBRowMajorThreads = true;
   static constexpr int kAMode = umma2::kAsync, kBMode = umma2::kBulk;
-  static constexpr bool kStagedEpilogue = true, kDumpA = false;
+  static constexpr bool kStagedEpilogue = true, kDumpA = false, kPrefetch = true;
   PlanePair dz;          // [rows][P][P][KO]
   const uint8_t* wimg;   // [ST*ST classes][K/64][hi Cx128 | lo Cx128]
   const float* x;        // forward activation (mask)
@@ -514,13 +518,18 @@ struct V2ConvDgrad {
     return p >= 0 && p < P && q >= 0 && q < P;
   }
   __device__ const uint8_t* b_tile(int z, int, int kb) const { return wimg + (int64_t(z) * (K / 64) + kb) * (C * 256); }
-  __device__ void store8(int z, int m, int c0, const float v[8]) const {
+  __device__ void prefetch8(int z, int m, int c0, float pf[8]) const {   // Rectlin mask: the forward activation
+    const int n = m / (HC * HC), yx = m % (HC * HC), yy = yx / HC, xx = yx % HC;
+    const int y = yy * ST + z / ST, xq = xx * ST + z % ST;
+    if (y >= H || xq >= H) { zero8(pf); return; }
+    ld8(x + (int64_t(n * H + y) * H + xq) * C + c0, pf);
+  }
+  __device__ void store8p(int z, int m, int c0, const float v[8], const float xv[8]) const {
     const int n = m / (HC * HC), yx = m % (HC * HC), yy = yx / HC, xx = yx % HC;
     const int y = yy * ST + z / ST, xq = xx * ST + z % ST;
     if (y >= H || xq >= H) return;
     const int64_t i = (int64_t(n * H + y) * H + xq) * C + c0;
-    float xv[8], o[8];
-    ld8(x + i, xv);
+    float o[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) o[j] = xv[j] > 0.f ? v[j] : 0.f;
     st8(dx + i, o);

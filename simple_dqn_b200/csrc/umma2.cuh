@@ -165,7 +165,6 @@ __global__ void __launch_bounds__(kThreads2, 1) k_umma2(const P p, const int tra
   umma::fence_before_sync();
   __syncthreads();
   umma::fence_after_sync();
-  pdl_wait();   // everything above overlapped the previous kernel; from here on we read its outputs
   B2_TRACE(tid == 0, 1);
   const uint32_t tmem = s_tmem;
 
@@ -233,6 +232,9 @@ __global__ void __launch_bounds__(kThreads2, 1) k_umma2(const P p, const int tra
         brow[i] = p.b_row(z, n0 + (P::kBRowMajorThreads ? (id >> 3) : (id % BN)));
       }
     }
+    // Everything above (TMEM alloc, barrier init, the gather index tables) overlapped the previous kernel
+    // of the chain; only from here on do we touch its outputs.  (The MMA warp never reads global memory.)
+    pdl_wait();
     for (int j = 0; j < nkb; ++j) {
       const int s = j % S, kb = kb0 + j, k0 = kb * kBK;
       if (j >= S) mbar_wait(&s_empty[s], ((j / S) - 1) & 1);
@@ -312,6 +314,28 @@ __global__ void __launch_bounds__(kThreads2, 1) k_umma2(const P p, const int tra
     pdl_launch_dependents();
 
     // ================================================================ epilogue (same 8 warps)
+    // Operands of the epilogue that do not depend on the accumulators (Rectlin masks of the dgrads) are
+    // fetched now, while the tensor core is still draining the last k-blocks.
+    constexpr int kStIt = kBM * (BN / 8) / kLoadThreads;         // staged path: (row, chunk) items per thread
+    constexpr int kDirIt = BN / 16;                              // direct path: 8-column chunks per thread
+    float pf[P::kPrefetch ? (P::kStagedEpilogue ? kStIt : kDirIt) : 1][8];
+    if constexpr (P::kPrefetch) {
+      if constexpr (P::kStagedEpilogue) {
+#pragma unroll
+        for (int i = 0; i < kStIt; ++i) {
+          const int id = tid + i * kLoadThreads;
+          const int r = id / (BN / 8), cc = id % (BN / 8);
+          if (m0 + r < M && n0 + cc * 8 < N) p.prefetch8(z, m0 + r, n0 + cc * 8, pf[i]);
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < kDirIt; ++c) {
+          const int col = (warp >> 2) * (BN / 2) + c * 8;
+          const int m = m0 + (warp & 3) * 32 + lane;
+          if (m < M && n0 + col < N) p.prefetch8(z, m, n0 + col, pf[c]);
+        }
+      }
+    }
     mbar_wait(&s_done, 0);
     if constexpr (P::kDumpA) mbar_wait(&s_dumped, 0);
     umma::fence_after_sync();
@@ -355,13 +379,19 @@ __global__ void __launch_bounds__(kThreads2, 1) k_umma2(const P p, const int tra
           const float* src = reinterpret_cast<const float*>(smem_gen + r * kPitch + cc * 32);
           const float4 v0 = *reinterpret_cast<const float4*>(src), v1 = *reinterpret_cast<const float4*>(src + 4);
           const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-          if (m0 + r < M && n0 + cc * 8 < N) p.store8(z, m0 + r, n0 + cc * 8, v);
+          if (m0 + r < M && n0 + cc * 8 < N) {
+            if constexpr (P::kPrefetch) p.store8p(z, m0 + r, n0 + cc * 8, v, pf[i]);
+            else p.store8(z, m0 + r, n0 + cc * 8, v);
+          }
         }
       } else {
 #pragma unroll
         for (int c = 0; c < kChunks; ++c) {
           const int col = half * kColsPerHalf + c * 8;
-          if (m0 + row < M && n0 + col < N) p.store8(z, m0 + row, n0 + col, a0[c]);
+          if (m0 + row < M && n0 + col < N) {
+            if constexpr (P::kPrefetch) p.store8p(z, m0 + row, n0 + col, a0[c], pf[c]);
+            else p.store8(z, m0 + row, n0 + col, a0[c]);
+          }
         }
       }
     }

@@ -103,11 +103,11 @@ __global__ void __launch_bounds__(kThreads2, 1) k_umma_mn(const P p, const KTrac
   umma::fence_before_sync();
   __syncthreads();
   umma::fence_after_sync();
-  pdl_wait();
   const uint32_t tmem = s_tmem;
 
   if (nkb <= 0) {
     // nothing to reduce in this split: the partial is all zeros
+    pdl_wait();
     if (warp < 8) {
       const float zero[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       for (int id = tid; id < kBM * (BN / 8); id += kLoadThreads) {
@@ -146,6 +146,7 @@ __global__ void __launch_bounds__(kThreads2, 1) k_umma_mn(const P p, const KTrac
     const Planes bpl = p.b_planes(z);
     Planes apl{nullptr, 0};
     if constexpr (!P::kARegs && !P::kABulk) apl = p.a_planes(z);
+    pdl_wait();   // prologue above overlapped the predecessor; the MMA warp never reads global memory
     for (int j = 0; j < nkb; ++j) {
       const int s = j % S;
       if (j >= S) mbar_wait(&s_empty[s], ((j / S) - 1) & 1);
