@@ -454,8 +454,8 @@ static int backward_and_update(b200dqn_net* n, const FrameSource& fs, int rows, 
   B2_CHECK_CUDA(cudaStreamWaitEvent(sA, ev[0], 0));
   {
     NoPdlScope side;
-    if (tc) B2_TRY(optimizer_range(n, 4, 4, 1 | 4, rows, sA, "opt_fc2"));
     if (!(tc && fc1_fused_epilogue)) B2_TRY(bwd_op(n, fs, rows, kFc1Wgrad, sA));   // overlaps fc1_dgrad (few CTAs)
+    if (tc) B2_TRY(optimizer_range(n, 4, 4, 1 | 4, rows, sA, "opt_fc2"));          // tiny; must not delay the wgrad
   }
   B2_TRY(bwd_op(n, fs, rows, kFc1Dgrad, st));
   B2_CHECK_CUDA(cudaEventRecord(ev[1], st));                 // dZ3 ready, W4 no longer needed
