@@ -203,6 +203,12 @@ def run_b200(a, rank, world, local_rank):
 
     torch.cuda.set_device(local_rank)
     dev = local_rank
+    t_start = time.time()
+
+    def note(msg):      # progress on stderr (B200DQN_BENCH_VERBOSE=1): locating a stall on a multi-rank box
+        if os.environ.get("B200DQN_BENCH_VERBOSE"):
+            sys.stderr.write("[bench rank %d %.1fs] %s\n" % (rank, time.time() - t_start, msg))
+            sys.stderr.flush()
     if world > 1:
         dist.init_process_group("cpu:gloo,cuda:nccl", rank=rank, world_size=world)
     stream = torch.cuda.Stream()          # non-default: enables CUDA-graph replay + side-stream branches
@@ -235,10 +241,12 @@ def run_b200(a, rank, world, local_rank):
         net.comm_init(broadcast_unique_id(dist, DeepQNetwork.comm_unique_id, rank), rank, world)
     random.seed(1)
     mem.seed_device_rng(random)
+    note("objects + communicator up")
 
     # ---- value: fused device path, inputs resident in HBM
     net.train_fused(mem, a.warmup)
     barrier()
+    note("warm-up done")
     sampler = ClockSampler(dev)
     if rank == 0:
         sampler.start()
@@ -257,6 +265,7 @@ def run_b200(a, rank, world, local_rank):
         dist.all_reduce(msd, op=dist.ReduceOp.MAX)
         ms = msd.cpu()
     ms_total = float(ms[0])
+    note("timed region done: %.1f us/step" % (1e3 * ms_total / a.steps))
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
     cost_tail = net.last_costs(min(a.steps, 8))
     assert np.isfinite(cost_tail).all(), cost_tail
@@ -268,6 +277,7 @@ def run_b200(a, rank, world, local_rank):
     L.profile_begin(dev, L.stream_ptr(stream))
     net.train_fused(mem, prof_steps)
     prof = L.profile_end()
+    note("per-kernel profile done")
     per = {}
     for name, t in prof:
         per.setdefault(name, []).append(t)
@@ -321,11 +331,13 @@ def run_b200(a, rank, world, local_rank):
             net.train(mem2.getMinibatch(), 0)
 
     e2e_loop(10)
+    note("e2e warm-up done")
     barrier()
     t0 = time.perf_counter()
     e2e_loop(e2e_steps)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
+    note("e2e done")
     dts = torch.tensor([dt], dtype=torch.float64)
     if world > 1:
         d = dts.cuda()
