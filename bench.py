@@ -352,6 +352,11 @@ def run_b200(a, rank, world, local_rank):
     assert len(costs) == e2e_steps + 10 and np.isfinite(costs).all()
     net.callback = None
 
+    if world > 1:          # orderly teardown on EVERY rank before rank 0 goes on to print
+        torch.cuda.synchronize()
+        dist.barrier()
+        net.comm_destroy()
+        dist.destroy_process_group()
     if rank != 0:
         return
     line = {"metric": METRIC, "value": world * a.steps / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world,
@@ -366,8 +371,6 @@ def run_b200(a, rank, world, local_rank):
         cb, _, _ = cpu_arm(10 ** 9, 3, a.replay, a.batch, max_seconds=a.cpu_seconds)
         line["cpu_baseline"] = cb
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
 
 
 def main():

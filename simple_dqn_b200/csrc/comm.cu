@@ -120,6 +120,9 @@ extern "C" int b200dqn_net_comm_destroy(b200dqn_net* n) {
   B2_REQUIRE(n, B200DQN_EINVAL, "null net");
   DeviceGuard g(n->device);
   cudaDeviceSynchronize();
+  // captured steps hold nodes of this communicator
+  if (n->graph_exec) { cudaGraphExecDestroy(n->graph_exec); n->graph_exec = nullptr; }
+  if (n->graph_train_exec) { cudaGraphExecDestroy(n->graph_train_exec); n->graph_train_exec = nullptr; }
   comm_destroy(n);
   return B200DQN_OK;
 }

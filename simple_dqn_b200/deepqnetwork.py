@@ -243,6 +243,9 @@ class DeepQNetwork:
         buf = (C.c_char * 128).from_buffer_copy(bytes(unique_id))
         L.call("b200dqn_net_comm_init", self._h, buf, rank, world_size)
 
+    def comm_destroy(self):
+        L.call("b200dqn_net_comm_destroy", self._h)
+
     @staticmethod
     def comm_unique_id():
         buf = (C.c_char * 128)()
