@@ -403,24 +403,34 @@ static int backward_and_update_multi(b200dqn_net* n, const FrameSource& fs, int 
   B2_CHECK_CUDA(cudaEventRecord(ev[2], st));
   {
     NoPdlScope side;
+    B2_TRY(optimizer_range(n, 2, 2, 1 | 2, rows, sB, "reduce_conv3"));     // partials -> d_g, early, off the chain
     B2_CHECK_CUDA(cudaStreamWaitEvent(sC, ev[2], 0));
     B2_TRY(bwd_op(n, fs, rows, kConv2Wgrad, sC));
+    B2_TRY(optimizer_range(n, 1, 1, 1 | 2, rows, sC, "reduce_conv2"));
   }
   B2_TRY(bwd_op(n, fs, rows, kConv2Dgrad, st));
   B2_TRY(bwd_op(n, fs, rows, kConv1Wgrad, st));
-  B2_CHECK_CUDA(cudaEventRecord(ev[5], sB));
-  B2_CHECK_CUDA(cudaEventRecord(ev[6], sC));
-  B2_CHECK_CUDA(cudaStreamWaitEvent(st, ev[5], 0));
-  B2_CHECK_CUDA(cudaStreamWaitEvent(st, ev[6], 0));
   {
     NoPdlScope tail;   // kernels around the collective use ordinary dependencies
-    B2_TRY(optimizer_range(n, 0, 2, 1 | 2, rows, st, "reduce_conv"));      // partials -> d_g[conv1..3]
+    B2_TRY(optimizer_range(n, 0, 0, 1 | 2, rows, st, "reduce_conv1"));
+    B2_CHECK_CUDA(cudaEventRecord(ev[5], sB));
+    B2_CHECK_CUDA(cudaEventRecord(ev[6], sC));
     B2_CHECK_CUDA(cudaEventRecord(ev[9], st));
+    B2_CHECK_CUDA(cudaStreamWaitEvent(sN, ev[5], 0));
+    B2_CHECK_CUDA(cudaStreamWaitEvent(sN, ev[6], 0));
     B2_CHECK_CUDA(cudaStreamWaitEvent(sN, ev[9], 0));
-    B2_TRY(comm_allreduce_range(n, 0, 2, sN));
+    B2_TRY(comm_allreduce_range(n, 0, 2, sN));                              // one small collective for conv1..3
     B2_CHECK_CUDA(cudaEventRecord(ev[10], sN));
     B2_CHECK_CUDA(cudaStreamWaitEvent(st, ev[10], 0));
-    for (int l = 0; l < 3; ++l) B2_TRY(umma_opt_conv(n, l, rows, st, "opt_conv", true));
+    B2_CHECK_CUDA(cudaStreamWaitEvent(sB, ev[10], 0));
+    B2_CHECK_CUDA(cudaStreamWaitEvent(sC, ev[10], 0));
+    B2_TRY(umma_opt_conv(n, 2, rows, sB, "opt_conv3", true));               // the three tiny updates run side by side
+    B2_TRY(umma_opt_conv(n, 1, rows, sC, "opt_conv2", true));
+    B2_TRY(umma_opt_conv(n, 0, rows, st, "opt_conv1", true));
+    B2_CHECK_CUDA(cudaEventRecord(ev[11], sB));
+    B2_CHECK_CUDA(cudaEventRecord(ev[12], sC));
+    B2_CHECK_CUDA(cudaStreamWaitEvent(st, ev[11], 0));
+    B2_CHECK_CUDA(cudaStreamWaitEvent(st, ev[12], 0));
   }
   B2_CHECK_CUDA(cudaEventRecord(ev[4], sA));
   B2_CHECK_CUDA(cudaStreamWaitEvent(st, ev[4], 0));
