@@ -880,6 +880,7 @@ extern "C" int b200dqn_net_train_sampled(b200dqn_net* n, b200dqn_replay* r, void
   int rc = check_fusable(n, r);
   if (rc) return rc;
   DeviceGuard g(n->device);
+  B2_TRY(replay_flush(r, as_stream(stream)));   // pending add()s reach the ring first (not part of the graph)
   B2_TRY(train_sampled_launch(n, r, as_stream(stream)));
   n->train_iterations += 1;
   return B200DQN_OK;
@@ -906,6 +907,7 @@ extern "C" int b200dqn_net_train_fused(b200dqn_net* n, b200dqn_replay* r, int ns
   B2_REQUIRE(r->rng_set, B200DQN_ESTATE, "net_train_fused: call b200dqn_replay_set_rng first");
   DeviceGuard g(n->device);
   cudaStream_t st = as_stream(stream);
+  B2_TRY(replay_flush(r, st));
   // The whole step (sampler + 15 kernels, three side branches) is captured once into a CUDA graph
   // and replayed: one graph launch per step instead of ~17 stream operations.
   const bool use_graph = n->use_graph && !g_prof_on && st != nullptr;

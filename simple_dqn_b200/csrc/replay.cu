@@ -29,6 +29,24 @@ __global__ void k_set_cursor(int64_t* cursor, int64_t count, int64_t current) {
   cursor[1] = current;
 }
 
+// metadata of up to kPend deferred add()s; the scalar arrays are read straight from pinned host memory
+__global__ void k_add_meta_batch(uint8_t* actions, int64_t* rewards, uint8_t* terminals, int64_t* cursor,
+                                 int64_t pos0, int64_t size, int n, const uint8_t* __restrict__ h_actions,
+                                 const int64_t* __restrict__ h_rewards, const uint8_t* __restrict__ h_terminals,
+                                 int64_t new_count, int64_t new_current) {
+  const int i = threadIdx.x;
+  if (i < n) {
+    const int64_t pos = (pos0 + i) % size;
+    actions[pos] = h_actions[i];
+    rewards[pos] = h_rewards[i];
+    terminals[pos] = h_terminals[i] ? 1 : 0;
+  }
+  if (i == 0) {
+    cursor[0] = new_count;
+    cursor[1] = new_current;
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // K1a: the sampling loop of getMinibatch (src/replay_memory.py:55-69) on the device.
 //
@@ -145,7 +163,30 @@ k_sample(uint32_t* __restrict__ mt_state, const uint8_t* __restrict__ terminals,
   kt_end(kt);
 }
 
+int replay_flush(b200dqn_replay* r, cudaStream_t st) {
+  if (r->npend == 0) return B200DQN_OK;
+  const int b = r->bank, n = r->npend;
+  const int64_t pos0 = r->pend_pos0;
+  const int64_t first = (r->size - pos0) < n ? (r->size - pos0) : n;   // frames before the ring wraps
+  B2_CHECK_CUDA(cudaMemcpyAsync(r->d_screens + pos0 * r->frame_bytes, r->h_bank[b], first * r->frame_bytes,
+                                cudaMemcpyHostToDevice, st));
+  if (first < n)
+    B2_CHECK_CUDA(cudaMemcpyAsync(r->d_screens, r->h_bank[b] + first * r->frame_bytes, (n - first) * r->frame_bytes,
+                                  cudaMemcpyHostToDevice, st));
+  k_add_meta_batch<<<1, 32, 0, st>>>(r->d_actions, r->d_rewards, r->d_terminals, r->d_cursor, pos0, r->size, n,
+                                     r->bank_actions(b), r->bank_rewards(b), r->bank_terminals(b), r->count,
+                                     r->current);
+  B2_LAUNCH_CHECK();
+  B2_CHECK_CUDA(cudaEventRecord(r->bank_done[b], st));
+  r->bank ^= 1;
+  r->npend = 0;
+  B2_CHECK_CUDA(cudaEventSynchronize(r->bank_done[r->bank]));   // the other bank must have drained (it has, long ago)
+  return B200DQN_OK;
+}
+
 int launch_sample(b200dqn_replay* r, cudaStream_t st) {
+  int frc = replay_flush(r, st);
+  if (frc) return frc;
   B2_CHECK_CUDA(launch_pdl(k_sample, dim3(1), dim3(kSampleThreads), 0, st, r->d_mt, (const uint8_t*)r->d_terminals,
                            (const int64_t*)r->d_cursor, r->hist, r->batch, r->d_idx, r->d_words, ktrace_slot("sample")));
   B2_PROF("sample", st);
@@ -254,6 +295,10 @@ extern "C" int b200dqn_replay_create(int device, int64_t size, int screen_h, int
   B2_CHECK_CUDA(cudaMemset(r->d_idx, 0, batch_size * sizeof(int32_t)));
   B2_CHECK_CUDA(cudaMemset(r->d_words, 0, 2 * sizeof(uint32_t)));
   B2_CHECK_CUDA(cudaMallocHost(&r->h_stage, size_t(b200dqn_replay::kSlots) * r->frame_bytes));
+  for (int b = 0; b < 2; ++b) {
+    B2_CHECK_CUDA(cudaMallocHost(&r->h_bank[b], size_t(b200dqn_replay::kPend) * (r->frame_bytes + 16)));
+    B2_CHECK_CUDA(cudaEventCreateWithFlags(&r->bank_done[b], cudaEventDisableTiming));
+  }
   for (int i = 0; i < b200dqn_replay::kSlots; ++i)
     B2_CHECK_CUDA(cudaEventCreateWithFlags(&r->slot_done[i], cudaEventDisableTiming));
   B2_CHECK_CUDA(cudaFuncSetAttribute(k_gather, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -271,6 +316,7 @@ extern "C" int b200dqn_replay_destroy(b200dqn_replay* r) {
   cudaFree(r->d_pre); cudaFree(r->d_post); cudaFree(r->d_mb_actions); cudaFree(r->d_mb_rewards);
   cudaFree(r->d_mb_terminals);
   cudaFreeHost(r->h_stage);
+  for (int b = 0; b < 2; ++b) { cudaFreeHost(r->h_bank[b]); if (r->bank_done[b]) cudaEventDestroy(r->bank_done[b]); }
   for (auto& e : r->slot_done) if (e) cudaEventDestroy(e);
   delete r;
   return B200DQN_OK;
@@ -280,21 +326,17 @@ extern "C" int b200dqn_replay_add(b200dqn_replay* r, int action, int64_t reward,
                                   int terminal, void* stream) {
   B2_REQUIRE(r && host_screen, B200DQN_EINVAL, "replay_add: null argument");
   DeviceGuard g(r->device);
-  cudaStream_t st = as_stream(stream);
-  const int slot = r->next_slot;
-  r->next_slot = (slot + 1) % b200dqn_replay::kSlots;
-  B2_CHECK_CUDA(cudaEventSynchronize(r->slot_done[slot]));  // slot free again?
-  uint8_t* stage = r->h_stage + size_t(slot) * r->frame_bytes;
-  memcpy(stage, host_screen, r->frame_bytes);
+  const int b = r->bank, i = r->npend;
   const int64_t pos = r->current;
-  B2_CHECK_CUDA(cudaMemcpyAsync(r->d_screens + pos * r->frame_bytes, stage, r->frame_bytes,
-                                cudaMemcpyHostToDevice, st));
-  B2_CHECK_CUDA(cudaEventRecord(r->slot_done[slot], st));
+  if (i == 0) r->pend_pos0 = pos;
+  memcpy(r->h_bank[b] + size_t(i) * r->frame_bytes, host_screen, r->frame_bytes);
+  r->bank_actions(b)[i] = static_cast<uint8_t>(action);
+  r->bank_rewards(b)[i] = reward;
+  r->bank_terminals(b)[i] = terminal ? 1 : 0;
+  r->npend = i + 1;
   r->count = r->count > pos + 1 ? r->count : pos + 1;   // :33
   r->current = (pos + 1) % r->size;                      // :34
-  k_add_meta<<<1, 32, 0, st>>>(r->d_actions, r->d_rewards, r->d_terminals, r->d_cursor, pos, action, reward,
-                               terminal, r->count, r->current);
-  B2_LAUNCH_CHECK();
+  if (r->npend == b200dqn_replay::kPend) return replay_flush(r, as_stream(stream));
   return B200DQN_OK;
 }
 
@@ -305,6 +347,7 @@ extern "C" int b200dqn_replay_add_batch(b200dqn_replay* r, int64_t n, const uint
              "replay_add_batch: bad argument");
   DeviceGuard g(r->device);
   cudaStream_t st = as_stream(stream);
+  { int frc = replay_flush(r, st); if (frc) return frc; }
   int64_t done = 0;
   while (done < n) {
     const int64_t pos = r->current;
@@ -336,6 +379,7 @@ extern "C" int b200dqn_replay_set_cursor(b200dqn_replay* r, int64_t count, int64
   B2_REQUIRE(r && count >= 0 && count <= r->size && current >= 0 && current < r->size, B200DQN_EINVAL,
              "replay_set_cursor: out of range");
   DeviceGuard g(r->device);
+  { int frc = replay_flush(r, nullptr); if (frc) return frc; }
   r->count = count;
   r->current = current;
   k_set_cursor<<<1, 1>>>(r->d_cursor, count, current);
@@ -349,6 +393,7 @@ extern "C" int b200dqn_replay_get_state(b200dqn_replay* r, int64_t index, uint8_
   B2_REQUIRE(r->count > 0, B200DQN_ESTATE, "replay memory is empy, use at least --random_steps 1");  // :38
   DeviceGuard g(r->device);
   cudaStream_t st = as_stream(stream);
+  { int frc = replay_flush(r, st); if (frc) return frc; }
   index = ((index % r->count) + r->count) % r->count;  // python modulo (:40)
   if (index >= r->hist - 1) {
     B2_CHECK_CUDA(cudaMemcpyAsync(host_out, r->d_screens + (index - (r->hist - 1)) * r->frame_bytes,
@@ -423,6 +468,7 @@ extern "C" int b200dqn_replay_set_indexes(b200dqn_replay* r, const int32_t* host
 extern "C" int b200dqn_replay_gather(b200dqn_replay* r, void* stream) {
   B2_REQUIRE(r, B200DQN_EINVAL, "null replay");
   DeviceGuard g(r->device);
+  { int frc = replay_flush(r, as_stream(stream)); if (frc) return frc; }
   const int use_tma = (r->frame_bytes % 16 == 0) ? 1 : 0;
   dim3 grid(r->batch, r->hist + 1);
   k_gather<<<grid, 128, use_tma ? r->frame_bytes : 0, as_stream(stream)>>>(
@@ -457,6 +503,7 @@ extern "C" int b200dqn_replay_read_minibatch(b200dqn_replay* r, uint8_t* host_pr
 
 extern "C" int b200dqn_replay_device_ptr(b200dqn_replay* r, int which, void** dev_ptr, size_t* bytes) {
   B2_REQUIRE(r && dev_ptr, B200DQN_EINVAL, "replay_device_ptr: null argument");
+  { DeviceGuard g(r->device); int frc = replay_flush(r, nullptr); if (frc) return frc; cudaStreamSynchronize(nullptr); }
   const size_t state_bytes = size_t(r->batch) * r->hist * r->frame_bytes;
   void* p = nullptr;
   size_t b = 0;

@@ -25,12 +25,24 @@ struct b200dqn_replay {
   int64_t* d_mb_rewards = nullptr;
   uint8_t* d_mb_terminals = nullptr;
 
-  // pinned staging slots for add()
+  // pinned staging slots (small host<->device landing pads)
   static constexpr int kSlots = 16;
   uint8_t* h_stage = nullptr;
   cudaEvent_t slot_done[kSlots] = {};
   int next_slot = 0;
   bool rng_set = false;
+
+  // add() is deferred: frames + scalars collect in one of two pinned banks and reach HBM in ONE
+  // transfer + one tiny kernel when somebody needs the ring (sample / gather / getState / train) or
+  // the bank is full.  The host cursor mirror is always current.
+  static constexpr int kPend = 8;
+  uint8_t* h_bank[2] = {};            // [kPend][frame_bytes] frames, then the scalar arrays
+  cudaEvent_t bank_done[2] = {};
+  int bank = 0, npend = 0;
+  int64_t pend_pos0 = 0;              // ring slot of the first pending frame
+  int64_t* bank_rewards(int b) const { return reinterpret_cast<int64_t*>(h_bank[b] + size_t(kPend) * frame_bytes); }
+  uint8_t* bank_actions(int b) const { return reinterpret_cast<uint8_t*>(bank_rewards(b) + kPend); }
+  uint8_t* bank_terminals(int b) const { return bank_actions(b) + kPend; }
 };
 
 struct b200dqn_statebuf {
@@ -47,4 +59,6 @@ struct b200dqn_statebuf {
 namespace b200 {
 // Launches used by the fused train step (net.cu).
 int launch_sample(b200dqn_replay* r, cudaStream_t st);
+// push the pending add()s to HBM (no-op when there are none); call before anything reads the ring
+int replay_flush(b200dqn_replay* r, cudaStream_t st);
 }  // namespace b200
