@@ -51,6 +51,16 @@ k_head(const float* __restrict__ part, int splits, int rows, float* h4_online, f
   kt_begin(kt);
   pdl_wait();
   pdl_launch_dependents();
+  // the TD scalars of this sample do not depend on the forward pass: fetch them now (thread 0), so the
+  // dependent index -> action/reward/terminal loads are off the tail of the kernel
+  int td_a = 0, td_term = 0;
+  int64_t td_r = 0;
+  if (td.enable && t == 0) {
+    const int64_t mi = td.midx[b];
+    td_a = td.actions[mi];
+    td_r = td.rewards[mi];
+    td_term = td.terminals[mi];
+  }
   float h = 0.f;
   for (int s = 0; s < splits; ++s) h += part[((z * splits + s) * rows + b) * kHidden + t];
   h = fmaxf(h, 0.f);
@@ -82,13 +92,12 @@ k_head(const float* __restrict__ part, int splits, int rows, float* h4_online, f
   __shared__ float s_d;
   __shared__ int s_a;
   if (t == 0) {
-    const int64_t mi = td.midx[b];
-    const int a = td.actions[mi];
-    int64_t r = td.rewards[mi];
+    const int a = td_a;
+    int64_t r = td_r;
     r = r < td.min_reward ? td.min_reward : (r > td.max_reward ? td.max_reward : r);     // np.clip (:136)
     float maxq = __ldcg(q_target + b * A);
     for (int j = 1; j < A; ++j) maxq = fmaxf(maxq, __ldcg(q_target + b * A + j));        // be.max(postq) (:124)
-    const double y = td.terminals[mi] ? double(r) : double(r) + td.discount * double(maxq);  // :140-143
+    const double y = td_term ? double(r) : double(r) + td.discount * double(maxq);          // :140-143
     const float target = static_cast<float>(y);
     float d = __ldcg(q_online + b * A + a) - target;                                      // SumSquared grad (:149)
     td.row_cost[b] = 0.5f * d * d;                                                        // :154, before the clip
@@ -120,9 +129,13 @@ k_head(const float* __restrict__ part, int splits, int rows, float* h4_online, f
   __syncthreads();
   if (!s_last) return;
   __threadfence();
+  // batch cost: all loads in flight at once, then summed in row order by one thread (deterministic)
+  const bool staged = rows <= kHidden;
+  if (staged && t < rows) red[t >> 5][t & 31] = __ldcg(td.row_cost + t);
+  __syncthreads();
   if (t == 0) {
     float tot = 0.f;
-    for (int bb = 0; bb < rows; ++bb) tot += __ldcg(td.row_cost + bb);
+    for (int bb = 0; bb < rows; ++bb) tot += staged ? red[bb >> 5][bb & 31] : __ldcg(td.row_cost + bb);
     const uint32_t sidx = *td.step;
     td.cost_ring[sidx % kCostRing] = tot / float(rows);
     td.cost_ring[kCostRing] = tot / float(rows);   // "latest" slot: one 4-byte read for the stats callback

@@ -42,12 +42,17 @@ struct UConv1Fwd {
   __device__ int M(int) const { return rows * kP1 * kP1; }
   __device__ int N(int) const { return kC1; }
   __device__ void krange(int, int& kb, int& ke) const { kb = 0; ke = kK1 / 64; }
-  __device__ void a8(int z, int m, int k0, float v[8]) const {
-    if (m >= rows * kP1 * kP1) { zero8(v); return; }
+  // first byte of output pixel m's receptive field in frame 0 of its sample (nullptr = padding row)
+  __device__ const uint8_t* a_row_ptr(int z, int m) const {
+    if (m >= rows * kP1 * kP1) return nullptr;
     const int n = m / (kP1 * kP1), pq = m % (kP1 * kP1), p = pq / kP1, q = pq % kP1;
+    const int64_t f = static_cast<int64_t>((z ? idx[1] : idx[0])[n]) + (z ? shift[1] : shift[0]);
+    return (z ? src[1] : src[0]) + f * kFrameBytes + (p * 4) * kFrameW + q * 4;
+  }
+  __device__ void a8(const uint8_t* row, int k0, float v[8]) const {   // k0 = (c, r, 0): 8 pixels of filter row r, frame c
+    if (!row) { zero8(v); return; }
     const int c = k0 >> 6, r = (k0 >> 3) & 7;
-    const int64_t f = static_cast<int64_t>((z ? idx[1] : idx[0])[n]) + (z ? shift[1] : shift[0]) + c;
-    const uint8_t* ptr = (z ? src[1] : src[0]) + f * kFrameBytes + (p * 4 + r) * kFrameW + q * 4;
+    const uint8_t* ptr = row + c * kFrameBytes + r * kFrameW;
     const uint32_t lo = *reinterpret_cast<const uint32_t*>(ptr), hi = *reinterpret_cast<const uint32_t*>(ptr + 4);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -353,12 +358,17 @@ struct V2Conv1Fwd {
   __device__ int M(int) const { return rows * kP1 * kP1; }
   __device__ int N(int) const { return kC1; }
   __device__ void krange(int, int& kb, int& ke) const { kb = 0; ke = kK1 / 64; }
-  __device__ void a8(int z, int m, int k0, float v[8]) const {
-    if (m >= rows * kP1 * kP1) { zero8(v); return; }
+  // first byte of output pixel m's receptive field in frame 0 of its sample (nullptr = padding row)
+  __device__ const uint8_t* a_row_ptr(int z, int m) const {
+    if (m >= rows * kP1 * kP1) return nullptr;
     const int n = m / (kP1 * kP1), pq = m % (kP1 * kP1), p = pq / kP1, q = pq % kP1;
+    const int64_t f = static_cast<int64_t>((z ? idx[1] : idx[0])[n]) + (z ? shift[1] : shift[0]);
+    return (z ? src[1] : src[0]) + f * kFrameBytes + (p * 4) * kFrameW + q * 4;
+  }
+  __device__ void a8(const uint8_t* row, int k0, float v[8]) const {   // k0 = (c, r, 0): 8 pixels of filter row r, frame c
+    if (!row) { zero8(v); return; }
     const int c = k0 >> 6, r = (k0 >> 3) & 7;
-    const int64_t f = static_cast<int64_t>((z ? idx[1] : idx[0])[n]) + (z ? shift[1] : shift[0]) + c;
-    const uint8_t* ptr = (z ? src[1] : src[0]) + f * kFrameBytes + (p * 4 + r) * kFrameW + q * 4;
+    const uint8_t* ptr = row + c * kFrameBytes + r * kFrameW;
     const uint32_t lo = *reinterpret_cast<const uint32_t*>(ptr), hi = *reinterpret_cast<const uint32_t*>(ptr + 4);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {

@@ -62,7 +62,8 @@ __device__ __forceinline__ void split8_planes(const float v[8], __half* hi_dst, 
 //   static constexpr int kAMode, kBMode;                         (OperandMode)
 //   static constexpr bool kARowMajorThreads, kBRowMajorThreads;  (thread -> chunk mapping, as in umma.cuh)
 //   int M(z), N(z); void krange(z, kb0, kb1);
-//   kReg  : void a8(z, m, k0, float v[8])                                   (A only)
+//   kReg  : const uint8_t* a_row_ptr(z, m)  (once per row; nullptr = row outside the problem)
+//           void a8(row_ptr, k0, float v[8])                                 (A only)
 //   kAsync: RowCtx a_row(z, m)  — once per (thread, tile row): everything that depends on the row only
 //           bool   a_chunk(z, row, kk, int64_t& off) — per k-block: element offset of the 8-wide chunk
 //                  starting at k index kk; false -> zero fill.   PlanePair-like a_planes(z) -> (hi, lo_off)
@@ -235,6 +236,16 @@ __global__ void __launch_bounds__(kThreads2, 1) k_umma2(const P p, const int tra
     // Everything above (TMEM alloc, barrier init, the gather index tables) overlapped the previous kernel
     // of the chain; only from here on do we touch its outputs.  (The MMA warp never reads global memory.)
     pdl_wait();
+    // kReg operands: per-row source pointers, once per kernel (they may depend on upstream data — the
+    // sampled indexes — so they are built after the wait, but not again for every k-block)
+    const uint8_t* areg[kACh];
+    if constexpr (P::kAMode == kReg) {
+#pragma unroll
+      for (int i = 0; i < kACh; ++i) {
+        const int id = tid + i * kLoadThreads;
+        areg[i] = p.a_row_ptr(z, m0 + (P::kARowMajorThreads ? (id >> 3) : (id % kBM)));
+      }
+    }
     for (int j = 0; j < nkb; ++j) {
       const int s = j % S, kb = kb0 + j, k0 = kb * kBK;
       if (j >= S) mbar_wait(&s_empty[s], ((j / S) - 1) & 1);
@@ -270,7 +281,8 @@ __global__ void __launch_bounds__(kThreads2, 1) k_umma2(const P p, const int tra
           const int id = tid + i * kLoadThreads;
           const int r = P::kARowMajorThreads ? (id >> 3) : (id % kBM);
           const int c = P::kARowMajorThreads ? (id & 7) : (id / kBM);
-          p.a8(z, m0 + r, k0 + c * 8, av[i]);
+          (void)r;
+          p.a8(areg[i], k0 + c * 8, av[i]);
         }
 #pragma unroll
         for (int i = 0; i < kACh; ++i) {
