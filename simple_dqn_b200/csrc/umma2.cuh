@@ -63,7 +63,7 @@ __device__ __forceinline__ void split8_planes(const float v[8], __half* hi_dst, 
 //   static constexpr bool kARowMajorThreads, kBRowMajorThreads;  (thread -> chunk mapping, as in umma.cuh)
 //   int M(z), N(z); void krange(z, kb0, kb1);
 //   kReg  : const uint8_t* a_row_ptr(z, m)  (once per row; nullptr = row outside the problem)
-//           void a8(row_ptr, k0, float v[8])                                 (A only)
+//           uint2 a_raw8(row_ptr, k0)  8 raw bytes;  static void cvt8(uint2, float v[8])      (A only)
 //   kAsync: RowCtx a_row(z, m)  — once per (thread, tile row): everything that depends on the row only
 //           bool   a_chunk(z, row, kk, int64_t& off) — per k-block: element offset of the 8-wide chunk
 //                  starting at k index kk; false -> zero fill.   PlanePair-like a_planes(z) -> (hi, lo_off)
@@ -246,6 +246,19 @@ __global__ void __launch_bounds__(kThreads2, 1) k_umma2(const P p, const int tra
         areg[i] = p.a_row_ptr(z, m0 + (P::kARowMajorThreads ? (id >> 3) : (id % kBM)));
       }
     }
+    // ... and the raw bytes of the first S k-blocks are requested up front: one exposed global-memory
+    // latency for the whole tile instead of one per k-block (the conversion path is synchronous).
+    uint2 araw[S][kACh];
+    if constexpr (P::kAMode == kReg) {
+#pragma unroll
+      for (int j = 0; j < S; ++j)
+#pragma unroll
+        for (int i = 0; i < kACh; ++i) {
+          const int id = tid + i * kLoadThreads;
+          const int c = P::kARowMajorThreads ? (id & 7) : (id / kBM);
+          araw[j][i] = (j < nkb) ? p.a_raw8(areg[i], (kb0 + j) * kBK + c * 8) : make_uint2(0u, 0u);
+        }
+    }
     for (int j = 0; j < nkb; ++j) {
       const int s = j % S, kb = kb0 + j, k0 = kb * kBK;
       if (j >= S) mbar_wait(&s_empty[s], ((j / S) - 1) & 1);
@@ -282,7 +295,14 @@ __global__ void __launch_bounds__(kThreads2, 1) k_umma2(const P p, const int tra
           const int r = P::kARowMajorThreads ? (id >> 3) : (id % kBM);
           const int c = P::kARowMajorThreads ? (id & 7) : (id / kBM);
           (void)r;
-          p.a8(areg[i], k0 + c * 8, av[i]);
+          uint2 raw = make_uint2(0u, 0u);
+          if (j < S) {
+#pragma unroll
+            for (int jj = 0; jj < S; ++jj) if (jj == j) raw = araw[jj][i];   // static indexing keeps araw in registers
+          } else {
+            raw = p.a_raw8(areg[i], k0 + c * 8);
+          }
+          P::cvt8(raw, av[i]);
         }
 #pragma unroll
         for (int i = 0; i < kACh; ++i) {
