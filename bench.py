@@ -170,11 +170,11 @@ def run_reference(a, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(a, world):
+def workload_config(a, world, comm="NCCL grad all-reduce"):
     return {"workload": "configs[1]: synthetic 84x84 uint8 frames, replay %d, batch %d per GPU, history 4, A=%d "
                         "(fused getMinibatch+train, no env)" % (a.replay, a.batch, NUM_ACTIONS),
             "replay": a.replay, "batch_per_gpu": a.batch, "global_batch": a.batch * world, "num_actions": NUM_ACTIONS,
-            "math_mode": a.math, "parallelism": "dp%d replicated-replay learners, NCCL grad all-reduce" % world
+            "math_mode": a.math, "parallelism": "dp%d replicated-replay learners, %s" % (world, comm)
             if world > 1 else "single GPU",
             "l2_policy": "inputs larger than L2: random 35 KB windows of a 7.06 GB ring; weights/activations are the "
                          "step's own working set"}
@@ -360,6 +360,7 @@ def run_b200(a, rank, world, local_rank):
     assert len(costs) == e2e_steps + 10 and np.isfinite(costs).all()
     net.callback = None
 
+    comm_mode, comm_ok = net.comm_status()
     if world > 1:          # orderly teardown on EVERY rank before rank 0 goes on to print
         torch.cuda.synchronize()
         dist.barrier()
@@ -371,7 +372,10 @@ def run_b200(a, rank, world, local_rank):
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_total / a.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if a.math == "fp32" else "f16x3-split (fp32 accumulate)", "data": "synthetic",
-            "config": workload_config(a, world), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+            "config": workload_config(a, world, {"p2p": "gradients all-reduced in place by one peer-memory kernel per "
+                                                        "layer (NVLink P2P loads/stores, comm_p2p.cuh)",
+                                                 "nccl": "NCCL grad all-reduce"}.get(comm_mode, comm_mode)),
+            "comm_healthy": bool(comm_ok), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
             "roofline": roof, "last_costs": [float(c) for c in cost_tail]}
     if world > 1:
         line["config"]["global_updates_per_s"] = a.steps / (ms_total * 1e-3)

@@ -75,6 +75,9 @@ int b200dqn_profile_end(int max_entries, char* names32, float* ms, int* count);
 /* In-graph kernel timeline: arm, run ONE fused step (train_fused re-captures its graph with timing
  * slots), then read [label, first CTA start, last CTA end] (GPU %globaltimer, ns) per launch. */
 int b200dqn_ktrace_begin(int device);
+/* Same, but record only the step-th fused step after arming (step >= 1; run at least that many): a
+ * steady-state step out of a batch, which is what a multi-rank trace needs. */
+int b200dqn_ktrace_begin_at(int device, int step);
 int b200dqn_ktrace_end(int max_entries, char* names32, unsigned long long* start_ns, unsigned long long* end_ns,
                        int* count);
 
@@ -258,10 +261,24 @@ int b200dqn_debug_trace(unsigned long long* host_out, int n);
  * counterpart).  One process per GPU; the 128-byte NCCL unique id is produced on rank 0 and
  * distributed by the host (torch.distributed / a file).  After comm_init every train step
  * all-reduces the summed dW (fp32, 1.69 M elements) over NVLink before the RMSProp update, so
- * weights stay bit-identical on all ranks.  libnccl.so.2 is dlopen()ed at first use. */
+ * weights stay bit-identical on all ranks.  libnccl.so.2 is dlopen()ed at first use (bootstrap,
+ * handle exchange, and the fallback data path). */
 int b200dqn_comm_unique_id(void* out_id128);
 int b200dqn_net_comm_init(b200dqn_net* n, const void* id128, int rank, int world_size);
 int b200dqn_net_comm_destroy(b200dqn_net* n);
+/* How the gradients travel and whether the exchange is healthy (synchronises the device).
+ * *mode: 0 = single learner, 1 = NCCL all-reduce, 2 = peer-memory exchange — every rank maps every
+ * other rank's exchange buffers (cudaIpc); fc1's operand rows are gathered with P2P stores so its
+ * gradient is never reduced, the small layers use a one-shot LL all-reduce (csrc/comm_p2p.cuh;
+ * B200DQN_P2P_SCHED=layer|tail selects the two-shot in-place exchange instead).  Chosen at comm_init
+ * when all ranks can map each other, forced off with B200DQN_COMM=nccl.  *error != 0: a peer wait timed out (20 s) since comm_init — the learners
+ * are out of step and the results since then are invalid. */
+int b200dqn_net_comm_status(b200dqn_net* n, int* mode, int* error);
+/* Developer aid (mode 2 only, collective: every rank makes the same call): mean microseconds of `iters`
+ * back-to-back in-place exchanges of layers [l0, l1] with the k_xchg switches `flags` and a CTA cap
+ * `blocks` (0 = default), and whether one exchange reproduced its known answer.  flags & 16: time the
+ * one-shot LL all-reduce of the default schedule instead (l0 == l1, one of layers 0, 1, 2, 4). */
+int b200dqn_debug_xchg(b200dqn_net* n, int l0, int l1, int flags, int blocks, int iters, float* us_out, int* ok_out);
 
 #ifdef __cplusplus
 }

@@ -46,6 +46,7 @@ SIGNATURES = {
     "b200dqn_stream_destroy": [C.c_int, _P],
     "b200dqn_stream_synchronize": [C.c_int, _P],
     "b200dqn_ktrace_begin": [C.c_int],
+    "b200dqn_ktrace_begin_at": [C.c_int, C.c_int],
     "b200dqn_ktrace_end": [C.c_int, _P, _P, _P, C.POINTER(C.c_int)],
     "b200dqn_profile_begin": [C.c_int, _P],
     "b200dqn_profile_end": [C.c_int, _P, _P, C.POINTER(C.c_int)],
@@ -94,6 +95,8 @@ SIGNATURES = {
     "b200dqn_comm_unique_id": [_P],
     "b200dqn_net_comm_init": [_P, _P, C.c_int, C.c_int],
     "b200dqn_net_comm_destroy": [_P],
+    "b200dqn_net_comm_status": [_P, _P, _P],
+    "b200dqn_debug_xchg": [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P],
 }
 EXPORTS = sorted(list(SIGNATURES) + ["b200dqn_last_error", "b200dqn_version"])
 
@@ -217,8 +220,9 @@ class Stream:
                 pass
 
 
-def ktrace_begin(device=0):
-    call("b200dqn_ktrace_begin", device)
+def ktrace_begin(device=0, step=0):
+    """Arm the in-graph timeline; step >= 1 records only that fused step after arming (steady state)."""
+    call("b200dqn_ktrace_begin_at", device, step)
 
 
 def ktrace_end(max_entries=128):

@@ -30,10 +30,9 @@ struct Prof {
 
 int g_ktrace_gen = 0;
 namespace {
-constexpr int kKtCap = 128;
 struct KtState {
   unsigned long long* d_buf = nullptr;
-  bool on = false;
+  bool on = false, gated = false;
   int n = 0;
   char names[kKtCap][32];
 } g_kt;
@@ -45,6 +44,13 @@ KTrace ktrace_slot(const char* label) {
   strncpy(g_kt.names[slot], label, 31);
   g_kt.names[slot][31] = 0;
   return KTrace{g_kt.d_buf, slot};
+}
+
+__global__ void k_kt_tick(unsigned long long* buf) { buf[kKtGate] += 1; }
+bool ktrace_tick(cudaStream_t st) {
+  if (!g_kt.on || !g_kt.gated) return false;
+  k_kt_tick<<<1, 1, 0, st>>>(g_kt.d_buf);
+  return true;
 }
 
 void prof_mark(const char* label, cudaStream_t st) {
@@ -150,18 +156,23 @@ extern "C" int b200dqn_stream_synchronize(int device, void* stream) {
   return B200DQN_OK;
 }
 
-extern "C" int b200dqn_ktrace_begin(int device) {
+extern "C" int b200dqn_ktrace_begin_at(int device, int step) {
   using namespace b200;
+  B2_REQUIRE(step >= 0, B200DQN_EINVAL, "ktrace_begin_at: step must be >= 0");
   DeviceGuard g(device);
-  if (!g_kt.d_buf) B2_CHECK_CUDA(cudaMalloc(&g_kt.d_buf, kKtCap * 2 * sizeof(unsigned long long)));
-  unsigned long long init[kKtCap * 2];
+  if (!g_kt.d_buf) B2_CHECK_CUDA(cudaMalloc(&g_kt.d_buf, (kKtCap * 2 + 2) * sizeof(unsigned long long)));
+  unsigned long long init[kKtCap * 2 + 2];
   for (int i = 0; i < kKtCap; ++i) { init[2 * i] = ~0ull; init[2 * i + 1] = 0ull; }
+  init[kKtGate] = 0;
+  init[kKtGate + 1] = (unsigned long long)step;
   B2_CHECK_CUDA(cudaMemcpy(g_kt.d_buf, init, sizeof(init), cudaMemcpyHostToDevice));
   g_kt.n = 0;
   g_kt.on = true;
+  g_kt.gated = step > 0;
   ++g_ktrace_gen;
   return B200DQN_OK;
 }
+extern "C" int b200dqn_ktrace_begin(int device) { return b200dqn_ktrace_begin_at(device, 0); }
 
 extern "C" int b200dqn_ktrace_end(int max_entries, char* names32, unsigned long long* start_ns,
                                   unsigned long long* end_ns, int* count) {

@@ -63,6 +63,7 @@ struct KTrace {
 };
 KTrace ktrace_slot(const char* label);   // host: slot for this launch (registers the label), {nullptr,0} when off
 extern int g_ktrace_gen;                 // bumped whenever tracing is switched, invalidates captured graphs
+bool ktrace_tick(cudaStream_t st);       // host: count one fused step (first node of the step); true when gated
 
 // ---------------------------------------------------------------- device-side PTX helpers
 #ifdef __CUDACC__
@@ -71,11 +72,19 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+// Gate words behind the slots: [kKtGate] counts fused steps since arming (k_kt_tick), [kKtGate + 1] is the
+// one step to record (0 = record everything) — lets a trace pick a steady-state step out of a batch.
+constexpr int kKtCap = 128, kKtGate = 2 * kKtCap;
+__device__ __forceinline__ bool kt_armed(const KTrace& kt) {
+  if (!kt.buf || threadIdx.x != 0) return false;
+  const unsigned long long want = kt.buf[kKtGate + 1];
+  return want == 0 || *reinterpret_cast<volatile unsigned long long*>(kt.buf + kKtGate) == want;
+}
 __device__ __forceinline__ void kt_begin(const KTrace& kt) {
-  if (kt.buf && threadIdx.x == 0) atomicMin(kt.buf + 2 * kt.slot, globaltimer_ns());
+  if (kt_armed(kt)) atomicMin(kt.buf + 2 * kt.slot, globaltimer_ns());
 }
 __device__ __forceinline__ void kt_end(const KTrace& kt) {
-  if (kt.buf && threadIdx.x == 0) atomicMax(kt.buf + 2 * kt.slot + 1, globaltimer_ns());
+  if (kt_armed(kt)) atomicMax(kt.buf + 2 * kt.slot + 1, globaltimer_ns());
 }
 extern bool g_use_pdl;   // B200DQN_NO_PDL unset
 extern long long g_launch_count;   // every kernel launch of the library (bench.py's gpu_launches)

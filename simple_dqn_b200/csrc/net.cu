@@ -387,7 +387,137 @@ static int optimizer_range(b200dqn_net* n, int l0, int l1, int mode, int rows, c
 // two-collective schedule 144 us/step, one collective per layer 166 us/step — small NCCL all-reduces
 // cost ~15-20 us each inside the graph, so fewer is better once the big one is hidden.)  Both collectives run in this order on one dedicated stream (a NCCL
 // communicator must not be used from two streams at once); updates read the reduced gradient from d_g.
+// Peer-memory exchange (comm_p2p.cuh): no shared communicator, so every layer's gradient is reduced
+// the moment its wgrad has finished, on that layer's own branch, and only conv1's 32 KB exchange is left
+// on the critical chain:  wgrad -> partial sums -> exchange (in place, all ranks) -> RMSProp from d_g.
+static int backward_and_update_xchg(b200dqn_net* n, const FrameSource& fs, int rows, cudaStream_t st) {
+  cudaStream_t sA = n->side[0], sB = n->side[1], sC = n->side[2];
+  cudaEvent_t* ev = n->ev;
+  B2_CHECK_CUDA(cudaEventRecord(ev[0], st));                 // head done: dZ4, dW5 partials
+  B2_CHECK_CUDA(cudaStreamWaitEvent(sA, ev[0], 0));
+  {
+    NoPdlScope side;
+    B2_TRY(bwd_op(n, fs, rows, kFc1Wgrad, sA));
+    B2_TRY(optimizer_range(n, 3, 4, 1 | 2, rows, sA, "reduce_fc"));
+    B2_TRY(comm_xchg_range(n, 3, 4, 3, sA, "xchg_fc"));
+  }
+  B2_TRY(bwd_op(n, fs, rows, kFc1Dgrad, st));
+  B2_CHECK_CUDA(cudaEventRecord(ev[1], st));                 // W4 no longer needed
+  {
+    NoPdlScope side;
+    B2_CHECK_CUDA(cudaStreamWaitEvent(sA, ev[1], 0));
+    B2_TRY(umma_opt_fc1(n, rows, sA, true));
+    B2_TRY(optimizer_range(n, 4, 4, 4, rows, sA, "opt_fc2"));
+    B2_CHECK_CUDA(cudaStreamWaitEvent(sB, ev[1], 0));
+    B2_TRY(bwd_op(n, fs, rows, kConv3Wgrad, sB));
+    B2_TRY(optimizer_range(n, 2, 2, 1 | 2, rows, sB, "reduce_conv3"));
+    B2_TRY(comm_xchg_range(n, 2, 2, 2, sB, "xchg_conv3"));
+  }
+  B2_TRY(bwd_op(n, fs, rows, kConv3Dgrad, st));
+  B2_CHECK_CUDA(cudaEventRecord(ev[2], st));                 // W3 no longer needed
+  {
+    NoPdlScope side;
+    B2_CHECK_CUDA(cudaStreamWaitEvent(sB, ev[2], 0));
+    B2_TRY(umma_opt_conv(n, 2, rows, sB, "opt_conv3", true));
+    B2_CHECK_CUDA(cudaStreamWaitEvent(sC, ev[2], 0));
+    B2_TRY(bwd_op(n, fs, rows, kConv2Wgrad, sC));
+    B2_TRY(optimizer_range(n, 1, 1, 1 | 2, rows, sC, "reduce_conv2"));
+    B2_TRY(comm_xchg_range(n, 1, 1, 1, sC, "xchg_conv2"));
+  }
+  B2_TRY(bwd_op(n, fs, rows, kConv2Dgrad, st));
+  B2_CHECK_CUDA(cudaEventRecord(ev[3], st));                 // W2 no longer needed
+  {
+    NoPdlScope side;
+    B2_CHECK_CUDA(cudaStreamWaitEvent(sC, ev[3], 0));
+    B2_TRY(umma_opt_conv(n, 1, rows, sC, "opt_conv2", true));
+  }
+  B2_TRY(bwd_op(n, fs, rows, kConv1Wgrad, st));
+  {
+    NoPdlScope tail;
+    B2_TRY(optimizer_range(n, 0, 0, 1 | 2, rows, st, "reduce_conv1"));
+    B2_TRY(comm_xchg_range(n, 0, 0, 0, st, "xchg_conv1"));
+    B2_TRY(umma_opt_conv(n, 0, rows, st, "opt_conv1", true));
+  }
+  B2_CHECK_CUDA(cudaEventRecord(ev[4], sA));
+  B2_CHECK_CUDA(cudaEventRecord(ev[5], sB));
+  B2_CHECK_CUDA(cudaEventRecord(ev[6], sC));
+  B2_CHECK_CUDA(cudaStreamWaitEvent(st, ev[4], 0));
+  B2_CHECK_CUDA(cudaStreamWaitEvent(st, ev[5], 0));
+  B2_CHECK_CUDA(cudaStreamWaitEvent(st, ev[6], 0));
+  return B200DQN_OK;
+}
+
+// Default data-parallel schedule (comm_p2p.cuh): the step keeps the single-GPU shape.  fc1's gradient is never
+// exchanged — every rank gathers all learners' H3 / dZ4 rows (pushed by their producers' successors) and runs
+// fc1_wgrad over the global minibatch; the four small layers go through the one-shot LL all-reduce the moment
+// their wgrad is done.  Bytes received per step and rank: (W-1) x (0.47 MB planes + 0.64 MB LL lines).
+static int backward_and_update_gather(b200dqn_net* n, const FrameSource& fs, int rows, cudaStream_t st) {
+  cudaStream_t sA = n->side[0], sB = n->side[1], sC = n->side[2], sN = n->side[3];
+  cudaEvent_t* ev = n->ev;
+  B2_CHECK_CUDA(cudaEventRecord(ev[0], st));                 // head done: dZ4 planes, dW5 partials
+  B2_CHECK_CUDA(cudaStreamWaitEvent(sA, ev[0], 0));
+  {
+    NoPdlScope side;
+    B2_TRY(umma_push_dz4(n, sA));                            // peers' fc1_wgrad wait for these 64 KB
+    B2_CHECK_CUDA(cudaStreamWaitEvent(sA, ev[14], 0));       // own H3 push (forward, umma_push_h3) has been issued
+    B2_TRY(comm_wait_pushes(n, sA));
+    B2_TRY(umma_fc1_wgrad_gathered(n, sA));
+    // fc2 (8 KB) on the stream the H3 push has left idle: nothing later in the step reads W5
+    B2_CHECK_CUDA(cudaStreamWaitEvent(sN, ev[0], 0));
+    B2_TRY(optimizer_range(n, 4, 4, 1 | 2, rows, sN, "reduce_fc2"));
+    B2_TRY(comm_xll_layer(n, 4, sN, "xll_fc2"));
+    B2_TRY(optimizer_range(n, 4, 4, 4, rows, sN, "opt_fc2"));
+    B2_CHECK_CUDA(cudaEventRecord(ev[7], sN));
+  }
+  B2_TRY(bwd_op(n, fs, rows, kFc1Dgrad, st));
+  B2_CHECK_CUDA(cudaEventRecord(ev[1], st));                 // W4 no longer needed
+  {
+    NoPdlScope side;
+    B2_CHECK_CUDA(cudaStreamWaitEvent(sA, ev[1], 0));
+    B2_TRY(umma_opt_fc1(n, rows, sA));                       // dW4 is already the global sum
+    B2_CHECK_CUDA(cudaStreamWaitEvent(sB, ev[1], 0));
+    B2_TRY(bwd_op(n, fs, rows, kConv3Wgrad, sB));
+    B2_TRY(optimizer_range(n, 2, 2, 1 | 2, rows, sB, "reduce_conv3"));
+    B2_TRY(comm_xll_layer(n, 2, sB, "xll_conv3"));
+  }
+  B2_TRY(bwd_op(n, fs, rows, kConv3Dgrad, st));
+  B2_CHECK_CUDA(cudaEventRecord(ev[2], st));                 // W3 no longer needed
+  {
+    NoPdlScope side;
+    B2_CHECK_CUDA(cudaStreamWaitEvent(sB, ev[2], 0));
+    B2_TRY(umma_opt_conv(n, 2, rows, sB, "opt_conv3", true));
+    B2_CHECK_CUDA(cudaStreamWaitEvent(sC, ev[2], 0));
+    B2_TRY(bwd_op(n, fs, rows, kConv2Wgrad, sC));
+    B2_TRY(optimizer_range(n, 1, 1, 1 | 2, rows, sC, "reduce_conv2"));
+    B2_TRY(comm_xll_layer(n, 1, sC, "xll_conv2"));
+  }
+  B2_TRY(bwd_op(n, fs, rows, kConv2Dgrad, st));
+  B2_CHECK_CUDA(cudaEventRecord(ev[3], st));                 // W2 no longer needed
+  {
+    NoPdlScope side;
+    B2_CHECK_CUDA(cudaStreamWaitEvent(sC, ev[3], 0));
+    B2_TRY(umma_opt_conv(n, 1, rows, sC, "opt_conv2", true));
+  }
+  B2_TRY(bwd_op(n, fs, rows, kConv1Wgrad, st));
+  {
+    NoPdlScope tail;
+    B2_TRY(optimizer_range(n, 0, 0, 1 | 2, rows, st, "reduce_conv1"));
+    B2_TRY(comm_xll_layer(n, 0, st, "xll_conv1"));
+    B2_TRY(umma_opt_conv(n, 0, rows, st, "opt_conv1", true));
+  }
+  B2_CHECK_CUDA(cudaEventRecord(ev[4], sA));
+  B2_CHECK_CUDA(cudaEventRecord(ev[5], sB));
+  B2_CHECK_CUDA(cudaEventRecord(ev[6], sC));
+  B2_CHECK_CUDA(cudaStreamWaitEvent(st, ev[4], 0));
+  B2_CHECK_CUDA(cudaStreamWaitEvent(st, ev[5], 0));
+  B2_CHECK_CUDA(cudaStreamWaitEvent(st, ev[6], 0));
+  B2_CHECK_CUDA(cudaStreamWaitEvent(st, ev[7], 0));
+  return B200DQN_OK;
+}
+
 static int backward_and_update_multi(b200dqn_net* n, const FrameSource& fs, int rows, cudaStream_t st) {
+  if (comm_gather_active(n, st)) return backward_and_update_gather(n, fs, rows, st);
+  if (n->xchg_ok && n->xchg_sched == 1) return backward_and_update_xchg(n, fs, rows, st);
   cudaStream_t sA = n->side[0], sB = n->side[1], sC = n->side[2], sN = n->side[3];
   cudaEvent_t* ev = n->ev;
   B2_CHECK_CUDA(cudaEventRecord(ev[0], st));                 // head done: dZ4, dW5 partials
@@ -642,7 +772,15 @@ extern "C" int b200dqn_net_create(int device, const b200dqn_net_config* cfg, b20
     n->d_tw = n->d_w;  // deepqnetwork.py:72-73: the target model IS the online model
     n->d_ts = n->d_s;
   }
-  B2_CHECK_CUDA(fmalloc(&n->d_g, n->n_params));
+  // the gradient buffer is the one allocation peers map (comm.cu): their flag words sit behind it
+  B2_CHECK_CUDA(fmalloc(&n->d_g, n->n_params + kXFlagWords));
+  n->d_xflags = reinterpret_cast<uint32_t*>(n->d_g + n->n_params);
+  constexpr int kXWords = kXChannels * kXMaxBlocks + 1 + 2 * kXChannels + 2 * kXPushChannels;
+  B2_CHECK_CUDA(cudaMalloc(&n->d_xepoch, kXWords * sizeof(uint32_t)));
+  B2_CHECK_CUDA(cudaMemset(n->d_xepoch, 0, kXWords * sizeof(uint32_t)));
+  n->d_xerr = n->d_xepoch + kXChannels * kXMaxBlocks;
+  n->d_xll_epoch = n->d_xerr + 1;
+  n->d_xpush_epoch = n->d_xll_epoch + 2 * kXChannels;
   B2_CHECK_CUDA(fmalloc(&n->d_part, n->part_elems));
   for (int z = 0; z < 2; ++z) {
     B2_CHECK_CUDA(fmalloc(&n->d_h1[z], size_t(nb) * kP1 * kP1 * kC1));
@@ -702,7 +840,7 @@ extern "C" int b200dqn_net_destroy(b200dqn_net* n) {
   for (auto& sd : n->side) if (sd) cudaStreamDestroy(sd);
   for (auto& e : n->ev) if (e) cudaEventDestroy(e);
   if (n->d_tw != n->d_w) { cudaFree(n->d_tw); cudaFree(n->d_ts); }
-  cudaFree(n->d_w); cudaFree(n->d_s); cudaFree(n->d_g); cudaFree(n->d_part);
+  cudaFree(n->d_w); cudaFree(n->d_s); cudaFree(n->d_g); cudaFree(n->d_part); cudaFree(n->d_xepoch);
   for (int z = 0; z < 2; ++z) {
     cudaFree(n->d_h1[z]); cudaFree(n->d_h2[z]); cudaFree(n->d_h3[z]); cudaFree(n->d_h4[z]); cudaFree(n->d_q[z]);
   }
@@ -931,7 +1069,12 @@ extern "C" int b200dqn_net_train_fused(b200dqn_net* n, b200dqn_replay* r, int ns
       cudaGraph_t graph = nullptr;
       B2_CHECK_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
       const long long launches_before = g_launch_count;
-      rc = launch_sample(r, st);
+      {
+        const bool prev = g_pdl_suppressed;
+        if (ktrace_tick(st)) g_pdl_suppressed = true;   // the sampler must not start ahead of the tick
+        rc = launch_sample(r, st);
+        g_pdl_suppressed = prev;
+      }
       if (!rc) rc = train_on_ring(n, r, st);
       n->graph_launches = int(g_launch_count - launches_before);
       cudaError_t e = cudaStreamEndCapture(st, &graph);
@@ -1015,6 +1158,12 @@ extern "C" int b200dqn_net_get_grads(b200dqn_net* n, int layer, float* host_dW, 
   if (n->world == 1) {  // partials of the last step are still in scratch; sum them into d_g
     k_optimizer<<<cdiv(n4, 256), 256, 0, st>>>(n->lt, n->d_part, n->d_g, n->d_w, n->d_s, 0, n4, 1 | 2, 0.f, 0.f, 0.f,
                                                0.f, 0.f, KTrace{nullptr, 0});
+    B2_LAUNCH_CHECK();
+  } else if (n->xchg_ok && n->xchg_sched == 2 && n->d_xbuf && layer == 3) {
+    // gather schedule: fc1's global gradient was computed locally and never passed through d_g
+    const int64_t b4 = n->lt.off[3] / 4, e4 = n->lt.off[4] / 4;
+    k_optimizer<<<cdiv(e4 - b4, 256), 256, 0, st>>>(n->lt, n->d_part, n->d_g, n->d_w, n->d_s, b4, e4, 1 | 2, 0.f, 0.f,
+                                                    0.f, 0.f, 0.f, KTrace{nullptr, 0});
     B2_LAUNCH_CHECK();
   }
   return xfer_params(n, n->d_g, layer, host_dW, false, st);

@@ -4,6 +4,7 @@
 #include "common.cuh"
 #include "net_simt.cuh"
 #include "replay.cuh"
+#include "comm_p2p.cuh"
 
 namespace b200 {
 
@@ -82,4 +83,26 @@ struct b200dqn_net {
   // multi-GPU
   void* nccl_comm = nullptr;
   int rank = 0, world = 1;
+  // peer-memory gradient exchange (comm_p2p.cuh): d_g and its flag words as mapped from every rank
+  bool xchg_ok = false;
+  int xchg_flags = 0;             // k_xchg switches (comm_p2p.cuh), B200DQN_XCHG_FLAGS
+  int xchg_blocks = 0;            // CTA cap per exchange (0 = kXMaxBlocks), B200DQN_XCHG_BLOCKS
+  int xchg_sched = 2;             // 2: gather fc1's operands + LL all-reduce of the small layers (default),
+                                  // 1: two-shot exchange per layer, 0: two-shot, two collectives
+  float* xg[8] = {};              // [rank] = d_g
+  uint32_t* xflags[8] = {};       // [rank] = d_xflags (tail of the d_g allocation)
+  void* xopened[8] = {};          // cudaIpcOpenMemHandle results to close
+  uint32_t* d_xflags = nullptr;   // flag words written by the peers
+  uint32_t* d_xepoch = nullptr;   // local epoch counters [channel][block]
+  uint32_t* d_xerr = nullptr;     // sticky "a wait timed out" word
+  // gather / LL exchange: a second peer-mapped allocation, sized at comm_init for the world
+  //   [push flags 4 KB][LL lines: parity x source x lines][H3 gather: parity x (hi | lo)][dZ4 gather: same]
+  uint8_t* d_xbuf = nullptr;
+  uint8_t* xbuf[8] = {};          // [rank] = d_xbuf
+  void* xbuf_opened[8] = {};
+  int64_t x_ll_off = 0, x_ll_lines = 0;               // bytes; LL lines per (parity, source)
+  int64_t x_h3_off = 0, x_h3_parity = 0, x_h3_lo = 0;   // bytes; bytes per parity; lo plane offset in elements
+  int64_t x_dz_off = 0, x_dz_parity = 0, x_dz_lo = 0;
+  uint32_t* d_xll_epoch = nullptr;   // [kXChannels] epochs, then [kXChannels] tickets (LL exchange)
+  uint32_t* d_xpush_epoch = nullptr; // [kXPushChannels] epochs, then tickets (plane push)
 };

@@ -348,6 +348,31 @@ struct WFc1Wgrad {
   __device__ void store8(int, int m, int n0, const float v[8]) const { st8(dw4 + int64_t(m) * kHidden + n0, v); }
 };
 
+// Data-parallel variant: the rows are ALL learners' samples, read from the gather areas that every rank's
+// k_xpush fills (comm_p2p.cuh); the parity of the current push epoch selects the area.
+struct WFc1WgradGather {
+  static constexpr int kBN = 64, kStages = 2;
+  static constexpr bool kAExact = false, kARegs = false, kABulk = false, kFusedUpdate = false;
+  const __half* h3g;   // [parity][hi | lo][rows][3136]
+  const __half* dzg;   // [parity][hi | lo][rows][512]
+  int64_t h3_parity, h3_lo, dz_parity, dz_lo;   // elements
+  const uint32_t* epoch;   // [0] H3 pushes, [1] dZ4 pushes completed by this rank
+  float* dw4;
+  int rows;            // world x per-rank minibatch
+  __device__ int M(int) const { return kFlat; }
+  __device__ int N(int) const { return kHidden; }
+  __device__ void krange(int, int& kb, int& ke) const { kb = 0; ke = (rows + 63) / 64; }
+  __device__ umma_mn::PixCtx pix(int, int b) const { return {b, 0, 0, b < rows}; }
+  __device__ umma2::Planes a_planes(int) const { return {h3g + int64_t(epoch[0] & 1) * h3_parity, h3_lo}; }
+  __device__ bool a_run(int, const umma_mn::PixCtx& px, int mchunk, int64_t& off) const {
+    off = int64_t(px.n) * kFlat + mchunk * 64;
+    return mchunk * 64 < kFlat;
+  }
+  __device__ umma2::Planes b_planes(int) const { return {dzg + int64_t(epoch[1] & 1) * dz_parity, dz_lo}; }
+  __device__ int64_t b_off(int, const umma_mn::PixCtx& px) const { return int64_t(px.n) * kHidden; }
+  __device__ void store8(int, int m, int n0, const float v[8]) const { st8(dw4 + int64_t(m) * kHidden + n0, v); }
+};
+
 // fc1 wgrad with the optimizer fused into its epilogue (single GPU): the tile of dW4 never leaves the
 // SM — RMSProp is applied in place and both fp16 tile images of W4 are refreshed.  Must run after
 // fc1_dgrad (which still reads the old dgrad image).
@@ -787,6 +812,8 @@ int umma_forward(b200dqn_net* n, const uint8_t* const src[2], const int32_t* con
     }
     p.rows = rows;
     if ((rc = umma2::launch_umma2("conv3_fwd", p, rows * kP3 * kP3, kC3, nets, st))) return rc;
+    // data-parallel learners: this rank's H3 rows start travelling to every rank's fc1_wgrad now
+    if (nets == 2 && rows == n->nb && comm_gather_active(n, st) && (rc = umma_push_h3(n, st))) return rc;
   }
   {
     V2Fc1Fwd p;
@@ -865,6 +892,29 @@ int umma_fc1_wgrad_fused(b200dqn_net* n, int rows, cudaStream_t st, bool keep_gr
 
 int umma_fc1_splits() { return kUFc1Splits; }
 bool umma_has_backward() { return true; }
+// ---- gather schedule hooks (data-parallel learners, comm_p2p.cuh) ---------------------------------------
+int umma_push_h3(b200dqn_net* n, cudaStream_t st) {
+  UmmaState* u = ust(n);
+  cudaStream_t sN = n->side[3];
+  B2_CHECK_CUDA(cudaEventRecord(n->ev[13], st));          // conv3_fwd done: the online net's H3 planes are final
+  B2_CHECK_CUDA(cudaStreamWaitEvent(sN, n->ev[13], 0));
+  const int rc = comm_push_planes(n, 0, u->h16[2][0], u->h_elems[2], sN);
+  if (rc) return rc;
+  B2_CHECK_CUDA(cudaEventRecord(n->ev[14], sN));
+  return B200DQN_OK;
+}
+int umma_push_dz4(b200dqn_net* n, cudaStream_t st) {
+  UmmaState* u = ust(n);
+  return comm_push_planes(n, 1, u->dz16[0], u->dz_elems[0], st);
+}
+int umma_fc1_wgrad_gathered(b200dqn_net* n, cudaStream_t st) {
+  WFc1WgradGather p{reinterpret_cast<const __half*>(n->d_xbuf + n->x_h3_off),
+                    reinterpret_cast<const __half*>(n->d_xbuf + n->x_dz_off),
+                    n->x_h3_parity / 2, n->x_h3_lo, n->x_dz_parity / 2, n->x_dz_lo,
+                    n->d_xpush_epoch, n->d_part + n->lt.part_off[3], n->nb * n->world};
+  return umma_mn::launch_umma_mn("fc1_wgrad", p, kFlat, kHidden, 1, st);
+}
+
 int umma_forward_launches() { return 4; }
 int umma_backward_launches() { return 7; }
 

@@ -38,6 +38,15 @@ int umma_backward_launches();
 // NCCL glue (comm.cu)
 int comm_allreduce_grads(b200dqn_net* n, cudaStream_t st);
 int comm_allreduce_range(b200dqn_net* n, int l0, int l1, cudaStream_t st);
+int comm_xchg_range(b200dqn_net* n, int l0, int l1, int chan, cudaStream_t st, const char* label);
+bool comm_gather_active(const b200dqn_net* n, cudaStream_t st);
+int comm_xll_layer(b200dqn_net* n, int layer, cudaStream_t st, const char* label);
+int comm_push_planes(b200dqn_net* n, int chan, const void* hi, int64_t lo_off_elems, cudaStream_t st);
+int comm_wait_pushes(b200dqn_net* n, cudaStream_t st);
+// gather schedule hooks of the tcgen05 engine (net_umma.cu)
+int umma_push_h3(b200dqn_net* n, cudaStream_t st);       // after conv3_fwd: rows of the online net's H3 planes
+int umma_push_dz4(b200dqn_net* n, cudaStream_t st);      // after the head
+int umma_fc1_wgrad_gathered(b200dqn_net* n, cudaStream_t st);   // dW4 over all world x nb rows
 void comm_destroy(b200dqn_net* n);
 
 }  // namespace b200

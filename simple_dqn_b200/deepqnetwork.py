@@ -246,6 +246,13 @@ class DeepQNetwork:
     def comm_destroy(self):
         L.call("b200dqn_net_comm_destroy", self._h)
 
+    def comm_status(self):
+        """-> (mode, healthy): mode 'single' | 'nccl' | 'p2p' (peer-memory exchange); synchronises the device.
+        healthy is False when a peer wait timed out since comm_init (results since then are invalid)."""
+        mode, err = C.c_int(), C.c_int()
+        L.call("b200dqn_net_comm_status", self._h, C.byref(mode), C.byref(err))
+        return ("single", "nccl", "p2p")[mode.value], err.value == 0
+
     @staticmethod
     def comm_unique_id():
         buf = (C.c_char * 128)()

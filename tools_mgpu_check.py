@@ -24,15 +24,42 @@ say("objects up")
 uid = broadcast_unique_id(dist, DeepQNetwork.comm_unique_id, rank)
 say("uid ok")
 net.comm_init(uid, rank, world)
-say("comm up")
+say("comm up:", net.comm_status())
 random.seed(1); mem.seed_device_rng(random)
+if os.environ.get("GRADS"):
+    import zlib
+    net.train_fused(mem, 1); torch.cuda.synchronize()
+    for l, g in enumerate(net.get_grads()):
+        torch.cuda.synchronize()
+        say("layer %d grad crc %08x  sum %.9g  abs %.9g" % (l, zlib.crc32(g.tobytes()) & 0xffffffff,
+                                                             float(g.astype(np.float64).sum()),
+                                                             float(np.abs(g.astype(np.float64)).sum())))
+    say("status", net.comm_status())
+    dist.barrier(); net.comm_destroy(); dist.destroy_process_group(); sys.exit(0)
 net.train_fused(mem, 3); torch.cuda.synchronize()
 say("3 fused steps ok, costs", net.last_costs(3))
 w = net.get_weights(with_states=False)
+import zlib
+say("weights crc32 %08x" % (zlib.crc32(b"".join(np.ascontiguousarray(x).tobytes() for x in w)) & 0xffffffff))
 chk = torch.tensor([float(np.sum([np.abs(x).sum() for x in w]))], dtype=torch.float64)
 allc = [torch.zeros_like(chk) for _ in range(world)]
 dist.all_gather(allc, chk)
 say("weight checksums", [float(c) for c in allc])
 assert all(float(c) == float(allc[0]) for c in allc), "ranks diverged"
 t = time.time(); net.train_fused(mem, 500); torch.cuda.synchronize(); say("500 steps: %.1f us/step" % ((time.time() - t) / 500 * 1e6))
-dist.barrier(); say("done")
+say("comm status after run:", net.comm_status())
+if os.environ.get("TIMELINE"):
+    from simple_dqn_b200 import _lib as L
+    L.ktrace_begin(lr, step=12)
+    net.train_fused(mem, 16); torch.cuda.synchronize()
+    rows = L.ktrace_end()
+    for rr in range(world):
+        dist.barrier()
+        if rr == rank and rr < 2:
+            t0 = min(r[1] for r in rows if r[1] < 2 ** 63)
+            print("---- rank %d steady-state step" % rank)
+            for name, a, b in sorted(rows, key=lambda r: r[1]):
+                if a < 2 ** 63:
+                    print("%-14s %9.2f %9.2f %8.2f" % (name, (a - t0) / 1e3, (b - t0) / 1e3, (b - a) / 1e3))
+            sys.stdout.flush()
+dist.barrier(); net.comm_destroy(); dist.destroy_process_group(); say("done")

@@ -1,4 +1,4 @@
-"""Developer tool: GPU timeline of ONE fused train step inside the replayed CUDA graph (all branches, PDL)."""
+"""Developer tool: GPU timeline of ONE steady-state fused train step inside the replayed CUDA graph (all branches, PDL)."""
 import os, sys, random
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
@@ -15,8 +15,8 @@ net = DeepQNetwork(NUM_ACTIONS, make_args(32), stream=st, math_mode=os.environ.g
 net.update_target_network()
 random.seed(1); mem.seed_device_rng(random)
 net.train_fused(mem, 50); st.synchronize()
-L.ktrace_begin(0)
-net.train_fused(mem, 1); st.synchronize()      # re-captures with timing slots, runs one step
+L.ktrace_begin(0, step=12)
+net.train_fused(mem, 16); st.synchronize()     # re-captures with timing slots, records the 12th step of the batch
 rows = L.ktrace_end()
 t0 = min(r[1] for r in rows)
 print("%-14s %9s %9s %8s" % ("kernel", "start_us", "end_us", "dur_us"))
