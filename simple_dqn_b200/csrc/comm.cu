@@ -316,7 +316,22 @@ static int xchg_setup(b200dqn_net* n, cudaStream_t ws) {
   for (int64_t i = 0; i < kat && good; ++i) good = h[i] == float(W * (W + 1) / 2) + float(W) * float(i & 1023);
   B2_CHECK_CUDA(cudaMemsetAsync(n->d_g, 0, n->n_params * sizeof(float), ws));
   B2_CHECK_CUDA(cudaStreamSynchronize(ws));
-  B2_REQUIRE(good, B200DQN_ENCCL, "peer-memory gradient exchange failed its known-answer test (err word %u)", err);
+  // A failed known-answer test must not leave the ranks on different paths: agree, then all fall back to NCCL.
+  auto agree = [&](bool mine_ok, const char* what) -> int {
+    int32_t v = mine_ok ? 1 : 0, sum = 0;
+    B2_CHECK_CUDA(cudaMemcpyAsync(d_ok, &v, sizeof(v), cudaMemcpyHostToDevice, ws));
+    B2_CHECK_NCCL(g_nccl.AllReduce(d_ok, d_ok, 1, kNcclInt32, kNcclSum, comm, ws));
+    B2_CHECK_CUDA(cudaMemcpyAsync(&sum, d_ok, sizeof(sum), cudaMemcpyDeviceToHost, ws));
+    B2_CHECK_CUDA(cudaStreamSynchronize(ws));
+    if (sum == W) return B200DQN_OK;
+    fprintf(stderr, "b200dqn: rank %d: %s failed its known-answer test on %d of %d ranks (local: %s, err word %u); "
+                    "gradients will go through NCCL\n", n->rank, what, W - sum, W, mine_ok ? "ok" : "FAILED", err);
+    B2_CHECK_CUDA(cudaMemsetAsync(n->d_xerr, 0, sizeof(uint32_t), ws));
+    B2_CHECK_CUDA(cudaStreamSynchronize(ws));
+    xchg_close(n);
+    return 1;
+  };
+  if ((rc = agree(good, "the two-shot peer-memory exchange"))) return rc < 0 ? rc : B200DQN_OK;
 
   // known-answer tests of the LL all-reduce (conv1..3, fc2) and of the plane push, same pattern
   {
@@ -352,8 +367,7 @@ static int xchg_setup(b200dqn_net* n, cudaStream_t ws) {
       }
     B2_CHECK_CUDA(cudaMemsetAsync(n->d_g, 0, n->n_params * sizeof(float), ws));
     B2_CHECK_CUDA(cudaStreamSynchronize(ws));
-    B2_REQUIRE(ll_ok, B200DQN_ENCCL, "LL gradient exchange failed its known-answer test (err word %u)", err);
-    B2_REQUIRE(push_ok, B200DQN_ENCCL, "plane push failed its known-answer test (err word %u)", err);
+    if ((rc = agree(ll_ok && push_ok, ll_ok ? "the plane push" : "the LL all-reduce"))) return rc < 0 ? rc : B200DQN_OK;
   }
   return B200DQN_OK;
 }
