@@ -372,8 +372,10 @@ def run_b200(a, rank, world, local_rank):
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_total / a.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if a.math == "fp32" else "f16x3-split (fp32 accumulate)", "data": "synthetic",
-            "config": workload_config(a, world, {"p2p": "gradients all-reduced in place by one peer-memory kernel per "
-                                                        "layer (NVLink P2P loads/stores, comm_p2p.cuh)",
+            "config": workload_config(a, world, {"p2p": "NVLink peer memory, schedule '%s' (gather: fc1's operand rows "
+                                                        "pushed to every rank, fc1_wgrad over the global batch, LL "
+                                                        "one-shot all-reduce for conv1-3/fc2; comm_p2p.cuh)"
+                                                        % os.environ.get("B200DQN_P2P_SCHED", "gather"),
                                                  "nccl": "NCCL grad all-reduce"}.get(comm_mode, comm_mode)),
             "comm_healthy": bool(comm_ok), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
             "roofline": roof, "last_costs": [float(c) for c in cost_tail]}

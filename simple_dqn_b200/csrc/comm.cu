@@ -1,4 +1,6 @@
-// comm.cu — data-parallel learners: gradient all-reduce over NVLink 5 / NVSwitch through NCCL.
+// comm.cu — data-parallel learners over NVLink 5 / NVSwitch: communicator set-up, the peer-memory exchange
+// (kernels in comm_p2p.cuh: plane push + LL all-reduce of the default "gather" schedule, two-shot in-place
+// all-reduce of the "layer"/"tail" schedules) and the NCCL path (bootstrap, votes, fallback).
 // libnccl.so.2 is dlopen()ed (the process normally already holds torch's bundled copy), so the
 // library has no link-time NCCL dependency and single-GPU use never touches it.
 #include <dlfcn.h>
