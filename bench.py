@@ -338,6 +338,7 @@ def run_b200(a, rank, world, local_rank):
                 mem2.add(int(actions[j]), int(rewards[j]), frames[(4 * i + j) % 64], bool(terminals[j]))
             net.train(mem2.getMinibatch(), 0)
 
+    barrier()            # ring refill time differs per rank; peers wait inside exchange kernels only for bounded time
     e2e_loop(10)
     note("e2e warm-up done")
     barrier()

@@ -271,7 +271,7 @@ int b200dqn_net_comm_destroy(b200dqn_net* n);
  * other rank's exchange buffers (cudaIpc); fc1's operand rows are gathered with P2P stores so its
  * gradient is never reduced, the small layers use a one-shot LL all-reduce (csrc/comm_p2p.cuh;
  * B200DQN_P2P_SCHED=layer|tail selects the two-shot in-place exchange instead).  Chosen at comm_init
- * when all ranks can map each other, forced off with B200DQN_COMM=nccl.  *error != 0: a peer wait timed out (20 s) since comm_init — the learners
+ * when all ranks can map each other, forced off with B200DQN_COMM=nccl.  *error != 0: a peer wait timed out (60 s) since comm_init — the learners
  * are out of step and the results since then are invalid. */
 int b200dqn_net_comm_status(b200dqn_net* n, int* mode, int* error);
 /* Developer aid (mode 2 only, collective: every rank makes the same call): mean microseconds of `iters`

@@ -15,7 +15,7 @@
 // Barriers are per block index (no grid-wide sync, no co-residency requirement beyond in-order block
 // dispatch), epochs are monotonic counters kept in device memory so the kernel replays inside a CUDA graph
 // with constant arguments, and each call site owns a channel (its own flag words), so exchanges of
-// different layers may run concurrently on different streams.  A wait that lasts 20 s sets a sticky error
+// different layers may run concurrently on different streams.  A wait that lasts 60 s sets a sticky error
 // word and every later wait returns at once: a lost peer costs a bounded stall, never a hung GPU.
 #pragma once
 #include "common.cuh"
@@ -27,6 +27,7 @@ constexpr int kXMaxBlocks = 128;   // CTAs per exchange kernel (= flag rows per 
 constexpr int kXChannels = 6;      // concurrent call sites
 constexpr int kXThreads = 256;
 constexpr int kXUnroll = 2;        // float4 per thread per rank in flight
+constexpr unsigned long long kXTimeoutNs = 60ull * 1000 * 1000 * 1000;   // bound of every device-side wait
 constexpr int kXFlagWords = kXChannels * 2 * kXMaxBlocks * kXMaxWorld;
 
 // ---- the default schedule ("gather", csrc/net.cu::backward_and_update_gather) moves far fewer bytes:
@@ -111,7 +112,7 @@ __device__ __forceinline__ bool xwait(const uint32_t* flag, uint32_t e, uint32_t
       if (*reinterpret_cast<volatile uint32_t*>(err)) return false;
       const unsigned long long now = globaltimer_ns();
       if (t0 == 0) t0 = now;
-      if (now - t0 > 20000000000ull) {
+      if (now - t0 > kXTimeoutNs) {
         atomicExch(err, 1u);
         return false;
       }
@@ -220,7 +221,7 @@ __device__ __forceinline__ bool ll_wait(const uint4* line, uint32_t e, uint32_t*
       if (*reinterpret_cast<volatile uint32_t*>(err)) break;
       const unsigned long long now = globaltimer_ns();
       if (t0 == 0) t0 = now;
-      if (now - t0 > 20000000000ull) {
+      if (now - t0 > kXTimeoutNs) {
         atomicExch(err, 1u);
         break;
       }

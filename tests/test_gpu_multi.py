@@ -1,0 +1,65 @@
+"""Data-parallel learners on >= 2 GPUs of one node: ranks must stay bit-identical and the exchange healthy.
+
+Runs tools/mgpu_check.py under torch.distributed.run with one process per GPU — the same staged check used during
+development: communicator + peer-memory known-answer tests at comm_init, one fused step with per-layer gradient
+CRCs, three more steps with weight CRCs compared across ranks.  Skipped on boxes with a single GPU.
+"""
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _gpus():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+def _run(env_extra, port):
+    env = dict(os.environ, **env_extra)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tools", "mgpu_check.py")]
+    p = subprocess.run(cmd, env=env, cwd=ROOT, capture_output=True, text=True, timeout=240)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
+    return p.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(_gpus() < 2, reason="needs two GPUs")
+@pytest.mark.parametrize("env", [{}, {"B200DQN_P2P_SCHED": "layer"}, {"B200DQN_COMM": "nccl"}],
+                         ids=["p2p-gather", "p2p-two-shot", "nccl"])
+def test_ranks_stay_identical(env):
+    out = _run(env, 29610)
+    assert "ranks diverged" not in out
+    crcs = re.findall(r"weights crc32 ([0-9a-f]{8})", out)
+    assert len(crcs) == 2 and crcs[0] == crcs[1], crcs
+    status = re.findall(r"comm status after run: \('(\w+)', (True|False)\)", out)
+    assert status and all(ok == "True" for _, ok in status), status
+    want = "nccl" if env.get("B200DQN_COMM") == "nccl" else "p2p"
+    assert all(mode == want for mode, _ in status), status
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(_gpus() < 2, reason="needs two GPUs")
+def test_gather_gradients_match_nccl():
+    """Per-layer global gradients after one step: the LL-reduced layers are bit-identical to NCCL's at W = 2
+    (a + b commutes), fc1 (computed over the gathered rows instead of reduced) agrees to fp32 rounding."""
+    def grads(env, port):
+        out = _run(dict(env, GRADS="1"), port)
+        rows = re.findall(r"\[rank (\d) [^\]]*\] layer (\d) grad crc ([0-9a-f]{8})  sum (\S+)  abs (\S+)", out)
+        assert len(rows) == 10, out[-2000:]
+        return {(int(r), int(l)): (crc, float(s), float(a)) for r, l, crc, s, a in rows}
+    g, n = grads({}, 29611), grads({"B200DQN_COMM": "nccl"}, 29612)
+    for l in range(5):
+        assert g[(0, l)] == g[(1, l)], "ranks disagree on layer %d" % l
+        if l != 3:
+            assert g[(0, l)][0] == n[(0, l)][0], "layer %d differs from the NCCL sum" % l
+        else:
+            assert abs(g[(0, l)][2] - n[(0, l)][2]) <= 1e-5 * n[(0, l)][2]

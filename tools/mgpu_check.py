@@ -1,13 +1,14 @@
 """Developer tool: staged 2..N-rank check of the NCCL path with progress prints (run under torchrun)."""
 import os, sys, time, random
 import numpy as np, torch, torch.distributed as dist
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from bench import make_args, synthetic_meta, NUM_ACTIONS
 from simple_dqn_b200 import DeepQNetwork, ReplayMemory
 from simple_dqn_b200.parallel import broadcast_unique_id
 rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 def say(*a):
-    print("[rank %d %.1fs]" % (rank, time.time() - T0), *a, flush=True)
+    sys.stdout.write("[rank %d %.1fs] %s\n" % (rank, time.time() - T0, " ".join(str(x) for x in a)))
+    sys.stdout.flush()
 T0 = time.time()
 torch.cuda.set_device(lr)
 dist.init_process_group("cpu:gloo,cuda:nccl", rank=rank, world_size=world)

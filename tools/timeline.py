@@ -1,7 +1,7 @@
 """Developer tool: GPU timeline of ONE steady-state fused train step inside the replayed CUDA graph (all branches, PDL)."""
 import os, sys, random
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from bench import make_args, synthetic_meta, NUM_ACTIONS
 from simple_dqn_b200 import DeepQNetwork, ReplayMemory, Stream, _lib as L
 st = Stream()

@@ -1,7 +1,7 @@
 """Developer tool: print the in-kernel timeline of one tcgen05 kernel (B200DQN_TRACE_LABEL=conv3_fwd ...)."""
 import os, sys, types
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from simple_dqn_b200 import DeepQNetwork, _lib as L
 from bench import make_args
 label = os.environ.get("B200DQN_TRACE_LABEL", "conv3_fwd")

@@ -1,7 +1,7 @@
 """Developer tool: microbenchmark of the peer-memory gradient exchange kernel (run under torchrun, N >= 2)."""
 import os, sys, time, ctypes as C
 import torch, torch.distributed as dist
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from bench import make_args, NUM_ACTIONS
 from simple_dqn_b200 import DeepQNetwork, _lib as L
 from simple_dqn_b200.parallel import broadcast_unique_id
