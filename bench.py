@@ -382,6 +382,19 @@ def run_b200(a, rank, world, local_rank):
             "roofline": roof, "last_costs": [float(c) for c in cost_tail]}
     if world > 1:
         line["config"]["global_updates_per_s"] = a.steps / (ms_total * 1e-3)
+        # NVLink bytes each rank SENDS per step (SURVEY §8e asks for the fraction of 770 GB/s per direction)
+        n_params = 1683456 + 512 * NUM_ACTIONS
+        small = n_params - 3136 * 512                           # conv1..3 + fc2, floats
+        if comm_mode == "p2p" and os.environ.get("B200DQN_P2P_SCHED", "gather") == "gather":
+            sent = (world - 1) * (a.batch * (3136 + 512) * 2 * 2    # H3 + dZ4 rows, fp16 hi + lo planes
+                                  + small * 4 * 2)                  # LL lines: 8 B data + 8 B flags
+            how = "(W-1) x (H3/dZ4 hi+lo rows + LL lines of conv1-3, fc2)"
+        else:
+            sent = 2 * (world - 1) * n_params * 4 // world
+            how = "reduce-scatter + all-gather of the 6.74 MB gradient"
+        gbs = sent / (ms_total / a.steps * 1e-3) / 1e9
+        line["nvlink"] = {"sent_bytes_per_step_per_rank": int(sent), "what": how, "GBps_per_rank": gbs,
+                          "frac_of_770GBps_per_dir": gbs / 770.0}
     if world == 1 and not a.no_cpu:
         cb, _, _ = cpu_arm(10 ** 9, 3, a.replay, a.batch, max_seconds=a.cpu_seconds)
         line["cpu_baseline"] = cb
