@@ -96,7 +96,7 @@ bool comm_gather_active(const b200dqn_net* n, cudaStream_t st) {
 
 // One-shot LL all-reduce of one layer's gradient (fc1 excluded: its operands are gathered instead), in place
 // in d_g.  The layer IS the channel: a line's flag words only ever carry that layer's epoch sequence.
-int comm_xll_layer(b200dqn_net* n, int l, cudaStream_t st, const char* label) {
+int comm_xll_args(b200dqn_net* n, int l, XllArgs* out) {
   B2_REQUIRE(n->xchg_ok && n->d_xbuf, B200DQN_ESTATE, "LL exchange not initialised");
   B2_REQUIRE(l >= 0 && l < kLayers && l != 3 && l < kXChannels, B200DQN_EINVAL, "LL exchange: layer must be 0, 1, 2 or 4");
   const int64_t fc1_4 = (n->lt.off[4] - n->lt.off[3]) / 4;
@@ -109,6 +109,14 @@ int comm_xll_layer(b200dqn_net* n, int l, cudaStream_t st, const char* label) {
   a.n4 = (n->lt.off[l + 1] - n->lt.off[l]) / 4;
   a.lines_per_src = n->x_ll_lines;
   a.epoch = n->d_xll_epoch; a.ticket = n->d_xll_epoch + kXChannels; a.err = n->d_xerr;
+  *out = a;
+  return B200DQN_OK;
+}
+
+int comm_xll_layer(b200dqn_net* n, int l, cudaStream_t st, const char* label) {
+  XllArgs a{};
+  int rc_args = comm_xll_args(n, l, &a);
+  if (rc_args) return rc_args;
   const int cap = n->xchg_blocks > 0 ? std::min(n->xchg_blocks, kXMaxBlocks) : 64;
   const int nblk = int(std::min<int64_t>(cap, std::max<int64_t>(1, (a.n4 + kXThreads - 1) / kXThreads)));
   NoPdlScope plain;

@@ -69,7 +69,7 @@ struct XPeers {
   uint32_t* flags[kXMaxWorld];  // rank p's flag words
 };
 
-#if defined(__CUDACC__) && defined(B200_COMM_P2P_KERNELS)   // comm.cu owns the kernel
+#ifdef __CUDACC__
 __device__ __forceinline__ int xflag(int chan, int phase, int block, int src) {
   return ((chan * 2 + phase) * kXMaxBlocks + block) * kXMaxWorld + src;
 }
@@ -120,6 +120,41 @@ __device__ __forceinline__ bool xwait(const uint32_t* flag, uint32_t e, uint32_t
   }
 }
 
+__device__ __forceinline__ void st_ll(uint4* p, uint32_t a, uint32_t b, uint32_t e) {
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(e), "r"(b), "r"(e) : "memory");
+}
+__device__ __forceinline__ uint4 ld_ll(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+// poll one line until both flag words carry epoch e; returns {data1, data2}
+__device__ __forceinline__ bool ll_wait(const uint4* line, uint32_t e, uint32_t* err, float& a, float& b) {
+  unsigned long long t0 = 0;
+  for (uint32_t spins = 0;; ++spins) {
+    const uint4 v = ld_ll(line);
+    if (v.y == e && v.w == e) {
+      a = __uint_as_float(v.x);
+      b = __uint_as_float(v.z);
+      return true;
+    }
+    if ((spins & 63) == 63) {
+      if (*reinterpret_cast<volatile uint32_t*>(err)) break;
+      const unsigned long long now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > kXTimeoutNs) {
+        atomicExch(err, 1u);
+        break;
+      }
+    }
+  }
+  a = b = 0.f;
+  return false;
+}
+
+#endif  // __CUDACC__
+
+#if defined(__CUDACC__) && defined(B200_COMM_P2P_KERNELS)   // comm.cu owns the kernels
 __device__ __forceinline__ float4 ld_weak_f4(const float4* p) {
   float4 v;
   asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
@@ -199,38 +234,6 @@ __global__ void __launch_bounds__(kXThreads) k_xchg(XPeers pp, int rank, int wor
 }
 
 // ---- one-shot LL all-reduce ------------------------------------------------------------------------------
-__device__ __forceinline__ void st_ll(uint4* p, uint32_t a, uint32_t b, uint32_t e) {
-  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(e), "r"(b), "r"(e) : "memory");
-}
-__device__ __forceinline__ uint4 ld_ll(const uint4* p) {
-  uint4 v;
-  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
-  return v;
-}
-// poll one line until both flag words carry epoch e; returns {data1, data2}
-__device__ __forceinline__ bool ll_wait(const uint4* line, uint32_t e, uint32_t* err, float& a, float& b) {
-  unsigned long long t0 = 0;
-  for (uint32_t spins = 0;; ++spins) {
-    const uint4 v = ld_ll(line);
-    if (v.y == e && v.w == e) {
-      a = __uint_as_float(v.x);
-      b = __uint_as_float(v.z);
-      return true;
-    }
-    if ((spins & 63) == 63) {
-      if (*reinterpret_cast<volatile uint32_t*>(err)) break;
-      const unsigned long long now = globaltimer_ns();
-      if (t0 == 0) t0 = now;
-      if (now - t0 > kXTimeoutNs) {
-        atomicExch(err, 1u);
-        break;
-      }
-    }
-  }
-  a = b = 0.f;
-  return false;
-}
-
 __global__ void __launch_bounds__(kXThreads) k_xll(XllArgs a, KTrace kt) {
   kt_begin(kt);
   const int t = threadIdx.x;

@@ -454,6 +454,8 @@ static int backward_and_update_xchg(b200dqn_net* n, const FrameSource& fs, int r
 static int backward_and_update_gather(b200dqn_net* n, const FrameSource& fs, int rows, cudaStream_t st) {
   cudaStream_t sA = n->side[0], sB = n->side[1], sC = n->side[2], sN = n->side[3];
   cudaEvent_t* ev = n->ev;
+  // experimental: one launch per conv layer for reduce + LL exchange + RMSProp (umma_opt_conv_xll), off by default
+  static const bool fused_xll = getenv("B200DQN_FUSED_XLL") != nullptr;
   B2_CHECK_CUDA(cudaEventRecord(ev[0], st));                 // head done: dZ4 planes, dW5 partials
   B2_CHECK_CUDA(cudaStreamWaitEvent(sA, ev[0], 0));
   {
@@ -477,33 +479,43 @@ static int backward_and_update_gather(b200dqn_net* n, const FrameSource& fs, int
     B2_TRY(umma_opt_fc1(n, rows, sA));                       // dW4 is already the global sum
     B2_CHECK_CUDA(cudaStreamWaitEvent(sB, ev[1], 0));
     B2_TRY(bwd_op(n, fs, rows, kConv3Wgrad, sB));
-    B2_TRY(optimizer_range(n, 2, 2, 1 | 2, rows, sB, "reduce_conv3"));
-    B2_TRY(comm_xll_layer(n, 2, sB, "xll_conv3"));
+    if (!fused_xll) {
+      B2_TRY(optimizer_range(n, 2, 2, 1 | 2, rows, sB, "reduce_conv3"));
+      B2_TRY(comm_xll_layer(n, 2, sB, "xll_conv3"));
+    }
   }
   B2_TRY(bwd_op(n, fs, rows, kConv3Dgrad, st));
   B2_CHECK_CUDA(cudaEventRecord(ev[2], st));                 // W3 no longer needed
   {
     NoPdlScope side;
     B2_CHECK_CUDA(cudaStreamWaitEvent(sB, ev[2], 0));
-    B2_TRY(umma_opt_conv(n, 2, rows, sB, "opt_conv3", true));
+    if (fused_xll) B2_TRY(umma_opt_conv_xll(n, 2, rows, sB, "optx_conv3"));
+    else B2_TRY(umma_opt_conv(n, 2, rows, sB, "opt_conv3", true));
     B2_CHECK_CUDA(cudaStreamWaitEvent(sC, ev[2], 0));
     B2_TRY(bwd_op(n, fs, rows, kConv2Wgrad, sC));
-    B2_TRY(optimizer_range(n, 1, 1, 1 | 2, rows, sC, "reduce_conv2"));
-    B2_TRY(comm_xll_layer(n, 1, sC, "xll_conv2"));
+    if (!fused_xll) {
+      B2_TRY(optimizer_range(n, 1, 1, 1 | 2, rows, sC, "reduce_conv2"));
+      B2_TRY(comm_xll_layer(n, 1, sC, "xll_conv2"));
+    }
   }
   B2_TRY(bwd_op(n, fs, rows, kConv2Dgrad, st));
   B2_CHECK_CUDA(cudaEventRecord(ev[3], st));                 // W2 no longer needed
   {
     NoPdlScope side;
     B2_CHECK_CUDA(cudaStreamWaitEvent(sC, ev[3], 0));
-    B2_TRY(umma_opt_conv(n, 1, rows, sC, "opt_conv2", true));
+    if (fused_xll) B2_TRY(umma_opt_conv_xll(n, 1, rows, sC, "optx_conv2"));
+    else B2_TRY(umma_opt_conv(n, 1, rows, sC, "opt_conv2", true));
   }
   B2_TRY(bwd_op(n, fs, rows, kConv1Wgrad, st));
   {
     NoPdlScope tail;
-    B2_TRY(optimizer_range(n, 0, 0, 1 | 2, rows, st, "reduce_conv1"));
-    B2_TRY(comm_xll_layer(n, 0, st, "xll_conv1"));
-    B2_TRY(umma_opt_conv(n, 0, rows, st, "opt_conv1", true));
+    if (fused_xll) {
+      B2_TRY(umma_opt_conv_xll(n, 0, rows, st, "optx_conv1"));
+    } else {
+      B2_TRY(optimizer_range(n, 0, 0, 1 | 2, rows, st, "reduce_conv1"));
+      B2_TRY(comm_xll_layer(n, 0, st, "xll_conv1"));
+      B2_TRY(umma_opt_conv(n, 0, rows, st, "opt_conv1", true));
+    }
   }
   B2_CHECK_CUDA(cudaEventRecord(ev[4], sA));
   B2_CHECK_CUDA(cudaEventRecord(ev[5], sB));

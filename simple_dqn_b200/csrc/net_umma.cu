@@ -492,16 +492,21 @@ struct PackConvDgrad { // B operand of a conv dgrad, one tile per output-parity 
 // + refresh of the layer's fp16 tile images (forward B operand; dgrad B operand for conv2/conv3).
 // Replaces three launches (optimizer, pack fwd, pack dgrad) on the tail of the step.
 // ------------------------------------------------------------------------------------------
-template <int KR, int N, bool DGRAD, int C, int R, int ST>
+// XCHG (data-parallel learners, experimental — see umma_opt_conv_xll): between the reduction and the update the
+// 8 lanes of an element exchange it with the other ranks in the LL protocol of comm_p2p.cuh — lane p pushes this
+// rank's float4 to rank p and polls rank p's line — and the W contributions are added in rank order.
+template <int KR, int N, bool DGRAD, int C, int R, int ST, bool XCHG = false>
 __global__ void __launch_bounds__(256)
 k_opt_conv(const float* __restrict__ part, int splits, float* __restrict__ w, float* __restrict__ sst,
            uint8_t* __restrict__ img_fwd, uint8_t* __restrict__ img_dgr, float inv_bsz, float lr, float decay,
-           float one_m_decay, float eps, const KTrace kt) {
+           float one_m_decay, float eps, const XllArgs x, const KTrace kt) {
   constexpr int64_t kSize = int64_t(KR) * N;
   kt_begin(kt);
   pdl_wait();
   pdl_launch_dependents();
   const int tid = threadIdx.x, lane8 = tid & 7;
+  uint32_t epoch = 0;
+  if constexpr (XCHG) epoch = *reinterpret_cast<volatile uint32_t*>(x.epoch + x.chan) + 1;
   const int64_t e4 = blockIdx.x * 32 + (tid >> 3);
   const int64_t i = e4 * 4;
   const bool live = i < kSize;
@@ -523,6 +528,27 @@ k_opt_conv(const float* __restrict__ part, int splits, float* __restrict__ w, fl
     g.y += __shfl_xor_sync(0xffffffffu, g.y, o);
     g.z += __shfl_xor_sync(0xffffffffu, g.z, o);
     g.w += __shfl_xor_sync(0xffffffffu, g.w, o);
+  }
+  if constexpr (XCHG) {
+    float4 v = lane8 == x.rank ? g : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live && lane8 < x.world && lane8 != x.rank) {
+      const int64_t par = int64_t(epoch & 1) * x.world * x.lines_per_src, el = (x.ll4 + e4) * 2;
+      uint4* dst = x.recv[lane8] + par + int64_t(x.rank) * x.lines_per_src + el;
+      st_ll(dst, __float_as_uint(g.x), __float_as_uint(g.y), epoch);
+      st_ll(dst + 1, __float_as_uint(g.z), __float_as_uint(g.w), epoch);
+      const uint4* src = x.recv[x.rank] + par + int64_t(lane8) * x.lines_per_src + el;
+      ll_wait(src, epoch, x.err, v.x, v.y);
+      ll_wait(src + 1, epoch, x.err, v.z, v.w);
+    }
+    __syncwarp();
+    const int base = (tid & 31) & ~7;
+    g = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int p = 0; p < x.world; ++p) {   // rank order, the same on every rank
+      const float a = __shfl_sync(0xffffffffu, v.x, base + p), b = __shfl_sync(0xffffffffu, v.y, base + p);
+      const float c = __shfl_sync(0xffffffffu, v.z, base + p), d = __shfl_sync(0xffffffffu, v.w, base + p);
+      if (p == 0) g = make_float4(a, b, c, d);
+      else { g.x += a; g.y += b; g.z += c; g.w += d; }
+    }
   }
   if (live && lane8 == 0) {
     float4 wv = *reinterpret_cast<float4*>(w + i);
@@ -561,6 +587,17 @@ k_opt_conv(const float* __restrict__ part, int splits, float* __restrict__ w, fl
       uint8_t* base = img_dgr + (int64_t(z) * NKB + kd / 64) * (C * 256) + umma::sw128_off(c, (kd % 64) / 8) + (kd % 8) * 2;
       *reinterpret_cast<uint2*>(base) = *reinterpret_cast<const uint2*>(hi);
       *reinterpret_cast<uint2*>(base + C * 128) = *reinterpret_cast<const uint2*>(lo);
+    }
+  }
+  if constexpr (XCHG) {   // the last block to finish publishes the layer's new epoch (as in k_xll)
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      if (atomicAdd(x.ticket + x.chan, 1u) == gridDim.x - 1) {
+        x.ticket[x.chan] = 0;
+        __threadfence();
+        *reinterpret_cast<volatile uint32_t*>(x.epoch + x.chan) = epoch;
+      }
     }
   }
   kt_end(kt);
@@ -631,15 +668,49 @@ int umma_opt_conv(b200dqn_net* n, int l, int rows, cudaStream_t st, const char* 
   const int64_t size = lt.off[l + 1] - lt.off[l];
   const dim3 grid(unsigned((size / 4 + 31) / 32)), block(256);
   cudaError_t e;
+  const XllArgs none{};
   if (l == 0)
     e = launch_pdl(k_opt_conv<kK1, kC1, false, 4, 8, 4>, grid, block, 0, st, part, nsplits, w, s, u->img_fwd[0][0],
-                   (uint8_t*)nullptr, inv_bsz, lr, decay, omd, eps, ktrace_slot(label));
+                   (uint8_t*)nullptr, inv_bsz, lr, decay, omd, eps, none, ktrace_slot(label));
   else if (l == 1)
     e = launch_pdl(k_opt_conv<kK2, kC2, true, kC1, 4, 2>, grid, block, 0, st, part, nsplits, w, s, u->img_fwd[0][1],
-                   u->img_dgr[2], inv_bsz, lr, decay, omd, eps, ktrace_slot(label));
+                   u->img_dgr[2], inv_bsz, lr, decay, omd, eps, none, ktrace_slot(label));
   else
     e = launch_pdl(k_opt_conv<kK3, kC3, true, kC2, 3, 1>, grid, block, 0, st, part, nsplits, w, s, u->img_fwd[0][2],
-                   u->img_dgr[1], inv_bsz, lr, decay, omd, eps, ktrace_slot(label));
+                   u->img_dgr[1], inv_bsz, lr, decay, omd, eps, none, ktrace_slot(label));
+  B2_CHECK_CUDA(e);
+  B2_PROF(label, st);
+  return B200DQN_OK;
+}
+
+// EXPERIMENTAL (B200DQN_FUSED_XLL=1; written after round 1's GPU budget was spent, not yet run on hardware):
+// split-K reduction + LL all-reduce across the learners + RMSProp + image refresh of conv layer l in ONE launch
+// instead of three (reduce, k_xll, k_opt_conv) on the tail of the data-parallel step.
+int umma_opt_conv_xll(b200dqn_net* n, int l, int rows, cudaStream_t st, const char* label) {
+  UmmaState* u = ust(n);
+  const LayerTable& lt = n->lt;
+  const float inv_bsz = 1.0f / float(rows * n->world);
+  const float lr = float(n->cfg.learning_rate), decay = float(n->cfg.decay_rate);
+  const float omd = float(1.0 - n->cfg.decay_rate), eps = 1e-6f;
+  B2_REQUIRE(l >= 0 && l < 3 && lt.splits[l] <= 64 && n->world <= 8, B200DQN_EINVAL, "opt_conv_xll: bad layer / world");
+  XllArgs x{};
+  int rc = comm_xll_args(n, l, &x);
+  if (rc) return rc;
+  const float* part = n->d_part + lt.part_off[l];
+  float* w = n->d_w + lt.off[l];
+  float* s = n->d_s + lt.off[l];
+  const int64_t size = lt.off[l + 1] - lt.off[l];
+  const dim3 grid(unsigned((size / 4 + 31) / 32)), block(256);
+  cudaError_t e;
+  if (l == 0)
+    e = launch_pdl(k_opt_conv<kK1, kC1, false, 4, 8, 4, true>, grid, block, 0, st, part, lt.splits[l], w, s,
+                   u->img_fwd[0][0], (uint8_t*)nullptr, inv_bsz, lr, decay, omd, eps, x, ktrace_slot(label));
+  else if (l == 1)
+    e = launch_pdl(k_opt_conv<kK2, kC2, true, kC1, 4, 2, true>, grid, block, 0, st, part, lt.splits[l], w, s,
+                   u->img_fwd[0][1], u->img_dgr[2], inv_bsz, lr, decay, omd, eps, x, ktrace_slot(label));
+  else
+    e = launch_pdl(k_opt_conv<kK3, kC3, true, kC2, 3, 1, true>, grid, block, 0, st, part, lt.splits[l], w, s,
+                   u->img_fwd[0][2], u->img_dgr[1], inv_bsz, lr, decay, omd, eps, x, ktrace_slot(label));
   B2_CHECK_CUDA(e);
   B2_PROF(label, st);
   return B200DQN_OK;

@@ -4,6 +4,7 @@
 #include <cuda_fp16.h>
 
 #include "common.cuh"
+#include "comm_p2p.cuh"
 
 struct b200dqn_net;
 
@@ -41,6 +42,8 @@ int comm_allreduce_range(b200dqn_net* n, int l0, int l1, cudaStream_t st);
 int comm_xchg_range(b200dqn_net* n, int l0, int l1, int chan, cudaStream_t st, const char* label);
 bool comm_gather_active(const b200dqn_net* n, cudaStream_t st);
 int comm_xll_layer(b200dqn_net* n, int layer, cudaStream_t st, const char* label);
+int comm_xll_args(b200dqn_net* n, int layer, XllArgs* out);   // launch arguments of layer's LL exchange
+int umma_opt_conv_xll(b200dqn_net* n, int l, int rows, cudaStream_t st, const char* label);   // experimental, fused
 int comm_push_planes(b200dqn_net* n, int chan, const void* hi, int64_t lo_off_elems, cudaStream_t st);
 int comm_wait_pushes(b200dqn_net* n, cudaStream_t st);
 // gather schedule hooks of the tcgen05 engine (net_umma.cu)

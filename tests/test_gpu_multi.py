@@ -33,8 +33,8 @@ def _run(env_extra, port):
 
 @pytest.mark.gpu
 @pytest.mark.skipif(_gpus() < 2, reason="needs two GPUs")
-@pytest.mark.parametrize("env", [{}, {"B200DQN_P2P_SCHED": "layer"}, {"B200DQN_COMM": "nccl"}],
-                         ids=["p2p-gather", "p2p-two-shot", "nccl"])
+@pytest.mark.parametrize("env", [{}, {"B200DQN_FUSED_XLL": "1"}, {"B200DQN_P2P_SCHED": "layer"}, {"B200DQN_COMM": "nccl"}],
+                         ids=["p2p-gather", "p2p-gather-fused-conv-exchange", "p2p-two-shot", "nccl"])
 def test_ranks_stay_identical(env):
     out = _run(env, 29610)
     assert "ranks diverged" not in out
