@@ -1,4 +1,5 @@
-"""Developer tool: staged 2..N-rank check of the NCCL path with progress prints (run under torchrun)."""
+"""Developer tool: staged 2..N-rank check of the data-parallel step (peer-memory or NCCL exchange) with progress prints; run under torchrun.
+Env: GRADS=1 (one step, per-layer gradient CRCs, exit), TIMELINE=1 (steady-state in-graph timeline per rank)."""
 import os, sys, time, random
 import numpy as np, torch, torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
