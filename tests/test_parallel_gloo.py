@@ -80,6 +80,44 @@ def test_two_rank_sharding_matches_single_process_oracle(tmp_path):
         assert rel_l2(a - w0[l], ref.weights[l] - w0[l]) <= 1e-3, l
 
 
+def _gather_worker(rank, port, out_dir):
+    """fc1 in the default peer-memory schedule: dW4 is not all-reduced; every rank gathers all ranks'
+    rows of its two operands (H3 = `flat`, dZ4) and multiplies over the global minibatch."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=WORLD)
+    torch.set_num_threads(1)
+    ring = _ring()
+    rng = MT19937.from_python(random.Random(5))
+    net = O.DQNOracle(A, batch_size=B, seed=9)
+    pre, act, rew, post, term = ring.getMinibatch(rng)
+    lo, hi = rank_slice(rank, WORLD, B)
+    postq = O.forward(net.target_weights, post[lo:hi])
+    preq, acts = O.forward(net.weights, pre[lo:hi], keep=True)
+    targets = O.td_targets(preq, postq.max(axis=1), act[lo:hi], rew[lo:hi], term[lo:hi])
+    deltas = np.clip(preq - targets, -1, 1).astype(np.float32)
+    reduced = torch.from_numpy(O.backward(net.weights, acts, deltas)[3].copy())
+    dist.all_reduce(reduced, op=dist.ReduceOp.SUM)                    # what NCCL / the two-shot exchange deliver
+    dz4 = ((deltas @ net.weights[4]) * (acts["h4"] > 0)).astype(np.float32)
+    rows_h3 = [torch.zeros(B, acts["flat"].shape[1]) for _ in range(WORLD)]
+    rows_dz = [torch.zeros(B, dz4.shape[1]) for _ in range(WORLD)]
+    dist.all_gather(rows_h3, torch.from_numpy(np.ascontiguousarray(acts["flat"])))   # k_xpush, channel 0
+    dist.all_gather(rows_dz, torch.from_numpy(dz4))                                  # k_xpush, channel 1
+    gathered = (torch.cat(rows_dz).T @ torch.cat(rows_h3)).numpy()   # fc1_wgrad over all world x B rows
+    np.savez(os.path.join(out_dir, "fc1_rank%d.npz" % rank), reduced=reduced.numpy(), gathered=gathered)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_fc1_gradient_from_gathered_operands_equals_the_reduced_gradient(tmp_path):
+    port = _free_port()
+    mp.spawn(_gather_worker, args=(port, str(tmp_path)), nprocs=WORLD, join=True)
+    r0 = np.load(tmp_path / "fc1_rank0.npz")
+    r1 = np.load(tmp_path / "fc1_rank1.npz")
+    assert (r0["gathered"] == r1["gathered"]).all(), "same operands in the same order: identical bits on every rank"
+    assert np.abs(r0["reduced"]).max() > 0
+    assert rel_l2(r0["gathered"], r0["reduced"]) <= 1e-6
+
+
 def test_rank_slice_partition():
     for world in (1, 2, 4, 8):
         spans = [rank_slice(r, world, 32) for r in range(world)]
