@@ -39,7 +39,13 @@ struct KtState {
 }  // namespace
 
 KTrace ktrace_slot(const char* label) {
-  if (!g_kt.on || g_kt.n >= kKtCap) return KTrace{nullptr, 0};
+  if (!g_kt.on) return KTrace{nullptr, 0};
+  // a gated trace records one step only, so launches of later steps (eager replay re-launches every kernel)
+  // share the slot of their label instead of exhausting the table
+  if (g_kt.gated)
+    for (int i = 0; i < g_kt.n; ++i)
+      if (strncmp(g_kt.names[i], label, 31) == 0) return KTrace{g_kt.d_buf, i};
+  if (g_kt.n >= kKtCap) return KTrace{nullptr, 0};
   const int slot = g_kt.n++;
   strncpy(g_kt.names[slot], label, 31);
   g_kt.names[slot][31] = 0;

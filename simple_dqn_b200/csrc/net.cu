@@ -1099,7 +1099,11 @@ extern "C" int b200dqn_net_train_fused(b200dqn_net* n, b200dqn_replay* r, int ns
     for (int i = 0; i < nsteps; ++i) B2_CHECK_CUDA(cudaGraphLaunch(n->graph_exec, st));
   } else {
     for (int i = 0; i < nsteps; ++i) {
-      if ((rc = launch_sample(r, st))) return rc;
+      const bool prev = g_pdl_suppressed;
+      if (ktrace_tick(st)) g_pdl_suppressed = true;
+      rc = launch_sample(r, st);
+      g_pdl_suppressed = prev;
+      if (rc) return rc;
       if ((rc = train_on_ring(n, r, st))) return rc;
     }
   }
