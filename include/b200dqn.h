@@ -44,6 +44,13 @@ enum {
   B200DQN_MATH_TCGEN05 = 1    /* tcgen05.mma kind::f16, fp16 hi/lo split operands (3 MMAs), fp32 TMEM */
 };
 
+/* optimizer of b200dqn_net_config — src/deepqnetwork.py:50-61 (--optimizer rmsprop|adam|adadelta, main.py:40) */
+enum {
+  B200DQN_OPT_RMSPROP = 0,  /* RMSProp(learning_rate, decay_rate), epsilon 1e-6; one state array per W       */
+  B200DQN_OPT_ADAM = 1,     /* Adam(learning_rate), beta_1 0.9, beta_2 0.999, epsilon 1e-8; states [m, v]    */
+  B200DQN_OPT_ADADELTA = 2  /* Adadelta(decay = decay_rate), epsilon 1e-6; states [E[g^2], E[dx^2], dx]      */
+};
+
 typedef struct b200dqn_replay b200dqn_replay; /* replaces class ReplayMemory, src/replay_memory.py:6  */
 typedef struct b200dqn_net b200dqn_net;       /* replaces class DeepQNetwork, src/deepqnetwork.py:15 */
 typedef struct b200dqn_statebuf b200dqn_statebuf; /* replaces class StateBuffer, src/state_buffer.py:3 */
@@ -173,6 +180,7 @@ typedef struct b200dqn_net_config {
   int max_reward;        /* :25  */
   int target_steps;      /* :65  0 ⇒ the target network aliases the online network (:72-73) */
   int math_mode;         /* B200DQN_MATH_*                                                */
+  int optimizer;         /* B200DQN_OPT_*  (:50-61; args.optimizer, main.py:40)           */
 } b200dqn_net_config;
 
 int b200dqn_net_config_default(b200dqn_net_config* cfg, int num_actions);
@@ -190,6 +198,12 @@ int b200dqn_net_set_weights(b200dqn_net* n, int which, int layer, const float* h
                             void* stream);
 int b200dqn_net_get_weights(b200dqn_net* n, int which, int layer, float* host_W, float* host_S, void* stream);
 int b200dqn_net_layer_shape(const b200dqn_net* n, int layer, int* rows, int* cols);
+/* Optimizer state plane k of `layer` (Neon's `states[k]`: RMSProp k = 0; Adam k = 0 m, 1 v; Adadelta k = 0..2),
+ * NEON layout like the weights.  b200dqn_net_num_states returns how many planes the configured optimizer keeps.
+ * Both synchronise. */
+int b200dqn_net_num_states(const b200dqn_net* n, int* count);
+int b200dqn_net_set_state(b200dqn_net* n, int which, int layer, int k, const float* host_S, void* stream);
+int b200dqn_net_get_state(b200dqn_net* n, int which, int layer, int k, float* host_S, void* stream);
 
 /* DeepQNetwork.update_target_network — src/deepqnetwork.py:102-105 (weights and optimizer state). */
 int b200dqn_net_sync_target(b200dqn_net* n, void* stream);

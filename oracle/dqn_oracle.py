@@ -135,19 +135,53 @@ def rmsprop_update(weights, states, grads, batch_size, lr=0.00025, decay=0.95, e
         w[...] = w - (g * F32(lr)) / (np.sqrt(s + F32(eps)) + F32(eps))
 
 
+def adam_update(weights, states, grads, batch_size, t, lr=0.00025, beta_1=0.9, beta_2=0.999, eps=1e-8):
+    """Neon ``Adam.optimize`` (deepqnetwork.py:54-56, :165) [neon-recall, parity unpinned], fp32, in place;
+    ``states[l] = [m, v]``, ``t`` = number of optimize() calls including this one (Adam.t after ``self.t += 1``):
+      l = lr * sqrt(1 - beta_2**t) / (1 - beta_1**t)        (Python doubles -> fp32 scalars, fp32 sqrt/divide)
+      g = dW / bsz;  m = m*beta_1 + (1-beta_1)*g;  v = v*beta_2 + (1-beta_2)*g*g;  W = W - (l*m) / (sqrt(v) + eps)"""
+    l = F32(lr) * np.sqrt(F32(1.0 - beta_2 ** t)) / F32(1.0 - beta_1 ** t)
+    for w, (m, v), g in zip(weights, states, grads):
+        g = g / F32(batch_size)
+        m[...] = m * F32(beta_1) + F32(1.0 - beta_1) * g
+        v[...] = v * F32(beta_2) + F32(1.0 - beta_2) * g * g
+        w[...] = w - (F32(l) * m) / (np.sqrt(v) + F32(eps))
+
+
+def adadelta_update(weights, states, grads, batch_size, decay=0.95, eps=1e-6):
+    """Neon ``Adadelta.optimize`` (deepqnetwork.py:57-59, :165) [neon-recall, parity unpinned], fp32, in place;
+    ``states[l] = [E[g^2], E[dx^2], dx]``:
+      g = dW / bsz;  s0 = s0*decay + (1-decay)*g*g;  s2 = sqrt((s1 + eps) / (s0 + eps)) * g;
+      s1 = s1*decay + (1-decay)*s2*s2;  W = W - s2"""
+    for w, (s0, s1, s2), g in zip(weights, states, grads):
+        g = g / F32(batch_size)
+        s0[...] = s0 * F32(decay) + F32(1.0 - decay) * g * g
+        s2[...] = np.sqrt((s1 + F32(eps)) / (s0 + F32(eps))) * g
+        s1[...] = s1 * F32(decay) + F32(1.0 - decay) * s2 * s2
+        w[...] = w - s2
+
+
+OPT_STATES = {"rmsprop": 1, "adam": 2, "adadelta": 3}
+
+
 class DQNOracle:
     """Drop-in-shaped restatement of ``DeepQNetwork`` (deepqnetwork.py:15-192) on the CPU."""
 
     def __init__(self, num_actions, batch_size=32, discount_rate=0.99, learning_rate=0.00025,
                  decay_rate=0.95, clip_error=1.0, min_reward=-1, max_reward=1, seed=1, weights=None,
-                 states=None, target_steps=10000):
+                 states=None, target_steps=10000, optimizer="rmsprop"):
         self.num_actions = num_actions
         self.batch_size = batch_size
         self.discount_rate, self.learning_rate, self.decay_rate = discount_rate, learning_rate, decay_rate
         self.clip_error, self.min_reward, self.max_reward = clip_error, min_reward, max_reward
         self.weights = [w.astype(F32).copy() for w in (weights or xavier_init(num_actions, seed))]
-        self.states = [np.zeros_like(w) if states is None else states[i].astype(F32).copy()
-                       for i, w in enumerate(self.weights)]
+        self.optimizer = optimizer
+        if optimizer == "rmsprop":
+            self.states = [np.zeros_like(w) if states is None else states[i].astype(F32).copy()
+                           for i, w in enumerate(self.weights)]
+        else:   # adam: [m, v]; adadelta: [E[g^2], E[dx^2], dx] per layer
+            self.states = [[np.zeros_like(w) for _ in range(OPT_STATES[optimizer])] if states is None
+                           else [a.astype(F32).copy() for a in states[i]] for i, w in enumerate(self.weights)]
         # deepqnetwork.py:63-73: a separate target model when target_steps != 0 else an alias
         self.target_weights = [w.copy() for w in self.weights] if target_steps else self.weights
         self.train_iterations = 0
@@ -178,8 +212,13 @@ class DQNOracle:
         if self.clip_error:
             deltas = np.clip(deltas, -self.clip_error, self.clip_error)         # :158-159
         grads = backward(self.weights, acts, deltas.astype(F32))                # :162
-        rmsprop_update(self.weights, self.states, grads, prestates.shape[0],
-                       self.learning_rate, self.decay_rate)                     # :165
+        if self.optimizer == "rmsprop":                                         # :165
+            rmsprop_update(self.weights, self.states, grads, prestates.shape[0], self.learning_rate, self.decay_rate)
+        elif self.optimizer == "adam":
+            adam_update(self.weights, self.states, grads, prestates.shape[0], self.train_iterations + 1,
+                        self.learning_rate)
+        else:
+            adadelta_update(self.weights, self.states, grads, prestates.shape[0], self.decay_rate)
         self.train_iterations += 1                                              # :168
         self.last = dict(preq=preq, postq=postq, targets=targets, deltas=deltas, grads=grads, cost=cost)
         if self.callback:

@@ -8,6 +8,7 @@ LIB_PATH = os.path.join(HERE, "libb200dqn.so")
 
 OK, EINVAL, ECUDA, ENOTIMPL, ENCCL, ESTATE = 0, -1, -2, -3, -4, -5
 MATH_FP32_SIMT, MATH_TCGEN05 = 0, 1
+OPT_RMSPROP, OPT_ADAM, OPT_ADADELTA = 0, 1, 2
 
 (PTR_SCREENS, PTR_ACTIONS, PTR_REWARDS, PTR_TERMINALS, PTR_PRESTATES, PTR_POSTSTATES, PTR_MB_ACTIONS,
  PTR_MB_REWARDS, PTR_MB_TERMINALS, PTR_INDEXES, PTR_WORDS_CONSUMED, PTR_MT_STATE) = range(12)
@@ -26,7 +27,7 @@ class NetConfig(C.Structure):
                 ("screen_h", C.c_int), ("screen_w", C.c_int), ("discount_rate", C.c_double),
                 ("learning_rate", C.c_double), ("decay_rate", C.c_double), ("clip_error", C.c_double),
                 ("min_reward", C.c_int), ("max_reward", C.c_int), ("target_steps", C.c_int),
-                ("math_mode", C.c_int)]
+                ("math_mode", C.c_int), ("optimizer", C.c_int)]
 
 
 _P = C.c_void_p
@@ -77,6 +78,9 @@ SIGNATURES = {
     "b200dqn_net_set_weights": [_P, C.c_int, C.c_int, _P, _P, _P],
     "b200dqn_net_get_weights": [_P, C.c_int, C.c_int, _P, _P, _P],
     "b200dqn_net_layer_shape": [_P, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)],
+    "b200dqn_net_num_states": [_P, C.POINTER(C.c_int)],
+    "b200dqn_net_set_state": [_P, C.c_int, C.c_int, C.c_int, _P, _P],
+    "b200dqn_net_get_state": [_P, C.c_int, C.c_int, C.c_int, _P, _P],
     "b200dqn_net_sync_target": [_P, _P],
     "b200dqn_net_predict": [_P, _P, _P, _P],
     "b200dqn_net_predict_device": [_P, _P, C.c_int, _P, _P],

@@ -39,6 +39,10 @@ struct HeadTrainArgs {
   float* dw5_rows;    // [rows][512][A] per-row partials of dW5 (summed in row order by the optimizer)
   __half* dz4_hi;     // fp16 hi / scaled-lo planes of dZ4 for the tcgen05 dgrad (nullptr in fp32 mode)
   int64_t dz4_lo_off;
+  float* adam_l;      // Adam only: this step's scalar l = lr*sqrt(1-beta_2^t)/(1-beta_1^t) for the optimizer kernels
+  float adam_lr;
+  int num_actions;    // actions[] >= num_actions would index q / W5 out of bounds: flagged in err, clamped
+  uint32_t* err;
 };
 
 __global__ void __launch_bounds__(kHidden)
@@ -60,6 +64,16 @@ k_head(const float* __restrict__ part, int splits, int rows, float* h4_online, f
     td_a = td.actions[mi];
     td_r = td.rewards[mi];
     td_term = td.terminals[mi];
+    if (td_a >= td.num_actions) {   // the reference would raise IndexError (deepqnetwork.py:141); here: sticky flag
+      atomicExch(td.err, 1u);
+      td_a = td.num_actions - 1;
+    }
+  }
+  if (td.enable && td.adam_l && b == 0 && z == 0 && t == 32) {
+    // Adam.optimize: self.t += 1;  l = lr * sqrt(1 - beta_2**t) / (1 - beta_1**t)  (Python doubles, fp32 tensor ops)
+    const double tt = double(*td.step) + 1.0;
+    const float a = float(1.0 - pow(0.999, tt)), c = float(1.0 - pow(0.9, tt));
+    *td.adam_l = __fdiv_rn(__fmul_rn(td.adam_lr, __fsqrt_rn(a)), c);
   }
   float h = 0.f;
   for (int s = 0; s < splits; ++s) h += part[((z * splits + s) * rows + b) * kHidden + t];
@@ -146,8 +160,8 @@ k_head(const float* __restrict__ part, int splits, int rows, float* h4_online, f
 }
 
 // ------------------------------------------------------------------------------------------
-// K6: gradient reduction + Neon RMSProp (src/deepqnetwork.py:51-53,165):
-//   g = dW / bsz;  s = decay*s + g*g*(1-decay);  W = W - (g*lr) / (sqrt(s + eps) + eps)
+// K6: gradient reduction + the configured Neon optimizer (src/deepqnetwork.py:50-61,165; rules in optim.cuh).
+// RMSProp:  g = dW / bsz;  s = decay*s + g*g*(1-decay);  W = W - (g*lr) / (sqrt(s + eps) + eps)
 // The split-K partials of every layer are summed here in fixed order (deterministic), so the
 // wgrad kernels never need atomics.  mode bit0: sum partials (else read g_buf); bit1: write the
 // summed gradient to g_buf (all-reduce input / get_grads); bit2: apply the update.
@@ -156,8 +170,7 @@ k_head(const float* __restrict__ part, int splits, int rows, float* h4_online, f
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_optimizer(const LayerTable lt, const float* __restrict__ part, float* __restrict__ g_buf, float* __restrict__ w,
-            float* __restrict__ s, int64_t b4, int64_t e4, int mode, float inv_bsz, float lr, float decay,
-            float one_m_decay, float eps, const KTrace kt) {
+            float* __restrict__ s, int64_t b4, int64_t e4, int mode, const OptArgs opt, const KTrace kt) {
   const int64_t i4 = b4 + blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
   kt_begin(kt);
   pdl_wait();
@@ -198,21 +211,8 @@ k_optimizer(const LayerTable lt, const float* __restrict__ part, float* __restri
   }
   if (mode & 2) *reinterpret_cast<float4*>(g_buf + i) = g;
   if (mode & 4) {
-    float4 wv = *reinterpret_cast<float4*>(w + i);
-    float4 sv = *reinterpret_cast<float4*>(s + i);
-    float* gp = reinterpret_cast<float*>(&g);
-    float* wp = reinterpret_cast<float*>(&wv);
-    float* sp = reinterpret_cast<float*>(&sv);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float gg = __fmul_rn(gp[j], inv_bsz);
-      const float ns = __fadd_rn(__fmul_rn(decay, sp[j]), __fmul_rn(__fmul_rn(gg, gg), one_m_decay));
-      const float den = __fadd_rn(__fsqrt_rn(__fadd_rn(ns, eps)), eps);
-      wp[j] = __fsub_rn(wp[j], __fdiv_rn(__fmul_rn(gg, lr), den));
-      sp[j] = ns;
-    }
-    *reinterpret_cast<float4*>(w + i) = wv;
-    *reinterpret_cast<float4*>(s + i) = sv;
+    float nw[4];
+    opt_update_vec<4>(opt, opt_step_scalar(opt), reinterpret_cast<const float*>(&g), nw, w + i, s + i);
   }
   kt_end(kt);
 }
@@ -350,14 +350,30 @@ static int bwd_op(b200dqn_net* n, const FrameSource& fs, int rows, BwdOp op, cud
 }
 
 // RMSProp (or gradient reduction) over layers [l0, l1] on stream st; mode bits as in k_optimizer.
+// The optimizer constants of this net (src/deepqnetwork.py:50-59; Neon's defaults for what the reference leaves unset)
+OptArgs make_opt_args(const b200dqn_net* n, int rows) {
+  OptArgs o{};
+  o.kind = n->cfg.optimizer;
+  o.nstates = n->n_states;
+  o.bsz = float(rows * n->world);
+  o.lr = float(n->cfg.learning_rate);
+  o.decay = float(n->cfg.decay_rate);
+  o.one_m_decay = float(1.0 - n->cfg.decay_rate);
+  o.eps = 1e-6f;
+  o.b1 = float(0.9); o.one_m_b1 = float(1.0 - 0.9);
+  o.b2 = float(0.999); o.one_m_b2 = float(1.0 - 0.999);
+  o.adam_eps = 1e-8f;
+  o.adam_l = n->d_optscal;
+  o.plane = n->n_params;
+  return o;
+}
+
+// optimizer update (or gradient reduction) over layers [l0, l1] on stream st; mode bits as in k_optimizer.
 static int optimizer_range(b200dqn_net* n, int l0, int l1, int mode, int rows, cudaStream_t st, const char* label) {
   const LayerTable& lt = n->lt;
   const int64_t b4 = lt.off[l0] / 4, e4 = lt.off[l1 + 1] / 4;
-  const float inv_bsz = 1.0f / float(rows * n->world);
-  const float lr = float(n->cfg.learning_rate), decay = float(n->cfg.decay_rate);
-  const float omd = float(1.0 - n->cfg.decay_rate), eps = 1e-6f;
   B2_CHECK_CUDA(launch_pdl(k_optimizer, dim3(cdiv(e4 - b4, 256)), dim3(256), 0, st, lt, (const float*)n->d_part, n->d_g,
-                           n->d_w, n->d_s, b4, e4, mode, inv_bsz, lr, decay, omd, eps, ktrace_slot(label)));
+                           n->d_w, n->d_s, b4, e4, mode, make_opt_args(n, rows), ktrace_slot(label)));
   B2_PROF(label, st);
   if (mode & 4) return umma_pack_layers(n, 0, l0, l1, st);   // refresh the fp16 tile images of the updated layers
   return B200DQN_OK;
@@ -669,7 +685,9 @@ static int train_step(b200dqn_net* n, const FrameSource& fs, const uint8_t* acti
   const int rows = n->nb;
   HeadTrainArgs td{1, actions, rewards, terminals, midx, n->cfg.discount_rate, n->cfg.min_reward, n->cfg.max_reward,
                    float(n->cfg.clip_error), n->d_delta, n->d_cost, n->d_step, n->d_ticket, n->d_rowcost, n->d_dz4,
-                   n->d_part + n->lt.part_off[4], nullptr, 0};
+                   n->d_part + n->lt.part_off[4], nullptr, 0,
+                   n->cfg.optimizer == B200DQN_OPT_ADAM ? n->d_optscal : nullptr, float(n->cfg.learning_rate), n->A,
+                   reinterpret_cast<uint32_t*>(n->d_cost + kCostRing + 1)};
   umma_dz4_planes(n, &td.dz4_hi, &td.dz4_lo_off);
   B2_TRY(forward(n, fs, 2, rows, st, td));
   return backward_and_update(n, fs, rows, st, true);
@@ -722,6 +740,7 @@ extern "C" int b200dqn_net_config_default(b200dqn_net_config* cfg, int num_actio
   cfg->max_reward = 1;           // main.py:44
   cfg->target_steps = 10000;     // main.py:63
   cfg->math_mode = B200DQN_MATH_FP32_SIMT;
+  cfg->optimizer = B200DQN_OPT_RMSPROP;   // main.py:40
   return B200DQN_OK;
 }
 
@@ -736,10 +755,14 @@ extern "C" int b200dqn_net_create(int device, const b200dqn_net_config* cfg, b20
              cfg->screen_h, cfg->screen_w, cfg->history_length);
   B2_REQUIRE(cfg->math_mode == B200DQN_MATH_FP32_SIMT || cfg->math_mode == B200DQN_MATH_TCGEN05, B200DQN_EINVAL,
              "net_create: unknown math_mode %d", cfg->math_mode);
+  B2_REQUIRE(cfg->optimizer >= B200DQN_OPT_RMSPROP && cfg->optimizer <= B200DQN_OPT_ADADELTA, B200DQN_EINVAL,
+             "net_create: unknown optimizer %d", cfg->optimizer);   // deepqnetwork.py:61 `assert false, "Unknown optimizer"`
   DeviceGuard g(device);
   auto* n = new (std::nothrow) b200dqn_net();
   B2_REQUIRE(n, B200DQN_EINVAL, "out of host memory");
+  n->n_states = cfg->optimizer == B200DQN_OPT_ADAM ? 2 : cfg->optimizer == B200DQN_OPT_ADADELTA ? 3 : 1;
   n->device = device;
+  B2_CHECK_CUDA(cudaDeviceGetAttribute(&n->sm_count, cudaDevAttrMultiProcessorCount, device));
   n->cfg = *cfg;
   n->nb = cfg->batch_size;
   n->A = cfg->num_actions;
@@ -776,10 +799,11 @@ extern "C" int b200dqn_net_create(int device, const b200dqn_net_config* cfg, b20
     return e;
   };
   B2_CHECK_CUDA(fmalloc(&n->d_w, n->n_params));
-  B2_CHECK_CUDA(fmalloc(&n->d_s, n->n_params));
+  B2_CHECK_CUDA(fmalloc(&n->d_s, n->n_params * n->n_states));
+  B2_CHECK_CUDA(fmalloc(&n->d_optscal, 4));
   if (cfg->target_steps) {
     B2_CHECK_CUDA(fmalloc(&n->d_tw, n->n_params));
-    B2_CHECK_CUDA(fmalloc(&n->d_ts, n->n_params));
+    B2_CHECK_CUDA(fmalloc(&n->d_ts, n->n_params * n->n_states));
   } else {
     n->d_tw = n->d_w;  // deepqnetwork.py:72-73: the target model IS the online model
     n->d_ts = n->d_s;
@@ -807,7 +831,7 @@ extern "C" int b200dqn_net_create(int device, const b200dqn_net_config* cfg, b20
   B2_CHECK_CUDA(fmalloc(&n->d_dz3, size_t(nb) * kFlat));
   B2_CHECK_CUDA(fmalloc(&n->d_dz2, size_t(nb) * kP2 * kP2 * kC2));
   B2_CHECK_CUDA(fmalloc(&n->d_dz1, size_t(nb) * kP1 * kP1 * kC1));
-  B2_CHECK_CUDA(fmalloc(&n->d_cost, kCostRing + 1));
+  B2_CHECK_CUDA(fmalloc(&n->d_cost, kCostRing + 2));   // ring, "latest" slot, action-range flag word
   B2_CHECK_CUDA(cudaMalloc(&n->d_step, sizeof(uint32_t)));
   B2_CHECK_CUDA(cudaMemset(n->d_step, 0, sizeof(uint32_t)));
   B2_CHECK_CUDA(cudaMalloc(&n->d_ticket, (nb + 1) * sizeof(uint32_t)));
@@ -852,6 +876,7 @@ extern "C" int b200dqn_net_destroy(b200dqn_net* n) {
   for (auto& sd : n->side) if (sd) cudaStreamDestroy(sd);
   for (auto& e : n->ev) if (e) cudaEventDestroy(e);
   if (n->d_tw != n->d_w) { cudaFree(n->d_tw); cudaFree(n->d_ts); }
+  cudaFree(n->d_optscal);
   cudaFree(n->d_w); cudaFree(n->d_s); cudaFree(n->d_g); cudaFree(n->d_part); cudaFree(n->d_xepoch);
   for (int z = 0; z < 2; ++z) {
     cudaFree(n->d_h1[z]); cudaFree(n->d_h2[z]); cudaFree(n->d_h3[z]); cudaFree(n->d_h4[z]); cudaFree(n->d_q[z]);
@@ -913,13 +938,34 @@ extern "C" int b200dqn_net_get_weights(b200dqn_net* n, int which, int layer, flo
   return B200DQN_OK;
 }
 
+extern "C" int b200dqn_net_num_states(const b200dqn_net* n, int* count) {
+  B2_REQUIRE(n && count, B200DQN_EINVAL, "net_num_states: null argument");
+  *count = n->n_states;
+  return B200DQN_OK;
+}
+
+extern "C" int b200dqn_net_set_state(b200dqn_net* n, int which, int layer, int k, const float* host_S, void* stream) {
+  B2_REQUIRE(n && host_S && layer >= 0 && layer < kLayers && (which == 0 || which == 1) && k >= 0 && k < n->n_states,
+             B200DQN_EINVAL, "net_set_state: bad argument");
+  DeviceGuard g(n->device);
+  return xfer_params(n, (which ? n->d_ts : n->d_s) + int64_t(k) * n->n_params, layer, const_cast<float*>(host_S), true,
+                     as_stream(stream));
+}
+
+extern "C" int b200dqn_net_get_state(b200dqn_net* n, int which, int layer, int k, float* host_S, void* stream) {
+  B2_REQUIRE(n && host_S && layer >= 0 && layer < kLayers && (which == 0 || which == 1) && k >= 0 && k < n->n_states,
+             B200DQN_EINVAL, "net_get_state: bad argument");
+  DeviceGuard g(n->device);
+  return xfer_params(n, (which ? n->d_ts : n->d_s) + int64_t(k) * n->n_params, layer, host_S, false, as_stream(stream));
+}
+
 extern "C" int b200dqn_net_sync_target(b200dqn_net* n, void* stream) {
   B2_REQUIRE(n, B200DQN_EINVAL, "null net");
   if (n->d_tw == n->d_w) return B200DQN_OK;  // target_steps == 0: alias
   DeviceGuard g(n->device);
   cudaStream_t st = as_stream(stream);
   B2_CHECK_CUDA(cudaMemcpyAsync(n->d_tw, n->d_w, n->n_params * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  B2_CHECK_CUDA(cudaMemcpyAsync(n->d_ts, n->d_s, n->n_params * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  B2_CHECK_CUDA(cudaMemcpyAsync(n->d_ts, n->d_s, n->n_params * n->n_states * sizeof(float), cudaMemcpyDeviceToDevice, st));
   return umma_target_synced(n, st);
 }
 
@@ -1056,9 +1102,11 @@ extern "C" int b200dqn_net_train_sampled_cost(b200dqn_net* n, b200dqn_replay* r,
   DeviceGuard g(n->device);
   cudaStream_t st = as_stream(stream);
   float* pin = reinterpret_cast<float*>(n->h_pin);
-  B2_CHECK_CUDA(cudaMemcpyAsync(pin, n->d_cost + kCostRing, sizeof(float), cudaMemcpyDeviceToHost, st));
+  B2_CHECK_CUDA(cudaMemcpyAsync(pin, n->d_cost + kCostRing, 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
   B2_CHECK_CUDA(cudaStreamSynchronize(st));
   *host_cost = pin[0];
+  B2_REQUIRE(reinterpret_cast<uint32_t*>(pin)[1] == 0, B200DQN_EINVAL,
+             "train: a sampled action is >= num_actions %d (IndexError at deepqnetwork.py:141 in the reference)", n->A);
   return B200DQN_OK;
 }
 
@@ -1119,9 +1167,11 @@ extern "C" int b200dqn_net_read_costs(b200dqn_net* n, int count, float* host_cos
   uint32_t step = 0;
   // the pinned block is reused: wait for anything in flight first
   B2_CHECK_CUDA(cudaStreamSynchronize(st));
-  B2_CHECK_CUDA(cudaMemcpyAsync(ring, n->d_cost, kCostRing * sizeof(float), cudaMemcpyDeviceToHost, st));
+  B2_CHECK_CUDA(cudaMemcpyAsync(ring, n->d_cost, (kCostRing + 2) * sizeof(float), cudaMemcpyDeviceToHost, st));
   B2_CHECK_CUDA(cudaMemcpyAsync(&step, n->d_step, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   B2_CHECK_CUDA(cudaStreamSynchronize(st));
+  B2_REQUIRE(reinterpret_cast<uint32_t*>(ring)[kCostRing + 1] == 0, B200DQN_EINVAL,
+             "train: a sampled action is >= num_actions %d (IndexError at deepqnetwork.py:141 in the reference)", n->A);
   B2_REQUIRE(uint32_t(count) <= step, B200DQN_ESTATE, "net_read_costs: only %u steps have run", step);
   for (int i = 0; i < count; ++i) host_costs[i] = ring[(step - count + i) % kCostRing];
   return B200DQN_OK;
@@ -1172,14 +1222,14 @@ extern "C" int b200dqn_net_get_grads(b200dqn_net* n, int layer, float* host_dW, 
   cudaStream_t st = as_stream(stream);
   const int64_t n4 = n->n_params / 4;
   if (n->world == 1) {  // partials of the last step are still in scratch; sum them into d_g
-    k_optimizer<<<cdiv(n4, 256), 256, 0, st>>>(n->lt, n->d_part, n->d_g, n->d_w, n->d_s, 0, n4, 1 | 2, 0.f, 0.f, 0.f,
-                                               0.f, 0.f, KTrace{nullptr, 0});
+    k_optimizer<<<cdiv(n4, 256), 256, 0, st>>>(n->lt, n->d_part, n->d_g, n->d_w, n->d_s, 0, n4, 1 | 2, OptArgs{},
+                                               KTrace{nullptr, 0});
     B2_LAUNCH_CHECK();
   } else if (n->xchg_ok && n->xchg_sched == 2 && n->d_xbuf && layer == 3) {
     // gather schedule: fc1's global gradient was computed locally and never passed through d_g
     const int64_t b4 = n->lt.off[3] / 4, e4 = n->lt.off[4] / 4;
-    k_optimizer<<<cdiv(e4 - b4, 256), 256, 0, st>>>(n->lt, n->d_part, n->d_g, n->d_w, n->d_s, b4, e4, 1 | 2, 0.f, 0.f,
-                                                    0.f, 0.f, 0.f, KTrace{nullptr, 0});
+    k_optimizer<<<cdiv(e4 - b4, 256), 256, 0, st>>>(n->lt, n->d_part, n->d_g, n->d_w, n->d_s, b4, e4, 1 | 2, OptArgs{},
+                                                    KTrace{nullptr, 0});
     B2_LAUNCH_CHECK();
   }
   return xfer_params(n, n->d_g, layer, host_dW, false, st);

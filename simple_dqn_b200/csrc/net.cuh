@@ -5,6 +5,7 @@
 #include "net_simt.cuh"
 #include "replay.cuh"
 #include "comm_p2p.cuh"
+#include "optim.cuh"
 
 namespace b200 {
 
@@ -25,6 +26,7 @@ struct LayerTable {
 
 struct b200dqn_net {
   int device = 0;
+  int sm_count = 148;      // queried at create; sizes the capped elementwise grids
   b200dqn_net_config cfg{};
   int nb = 0;  // per-rank minibatch
   int A = 0;
@@ -33,7 +35,9 @@ struct b200dqn_net {
 
   // parameters (internal layout, all layers contiguous)
   float* d_w = nullptr;   // online weights
-  float* d_s = nullptr;   // online RMSProp state
+  float* d_s = nullptr;   // online optimizer state: n_states planes of n_params (RMSProp 1, Adam 2, Adadelta 3)
+  int n_states = 1;
+  float* d_optscal = nullptr;  // [0] Adam's step scalar l of the current step (written by the head kernel)
   float* d_tw = nullptr;  // target weights (== d_w when target_steps == 0)
   float* d_ts = nullptr;  // target optimizer state (copied for fidelity with :102-105)
   float* d_g = nullptr;   // summed gradients (all-reduce buffer / get_grads)

@@ -387,7 +387,7 @@ struct WFc1WgradFused {
   uint8_t* img_fwd;   // [4 n-tiles][49 kb][hi 128x128 | lo]
   uint8_t* img_dgr;   // [25 m-tiles][8 kb][hi 128x128 | lo]
   int rows;
-  float inv_bsz, lr, decay, one_m_decay, eps;
+  OptArgs opt;
   __device__ int M(int) const { return kFlat; }
   __device__ int N(int) const { return kHidden; }
   __device__ void krange(int, int& kb, int& ke) const { kb = 0; ke = (rows + 63) / 64; }
@@ -400,24 +400,11 @@ struct WFc1WgradFused {
   __device__ umma2::Planes b_planes(int) const { return {dz4_16.hi, dz4_16.lo_off}; }
   __device__ int64_t b_off(int, const umma_mn::PixCtx& px) const { return int64_t(px.n) * kHidden; }
   __device__ void store8(int, int, int, const float*) const {}
-  __device__ void load_ws(int, int m, int n0, float wv[8], float sv[8]) const {
-    const int64_t i = int64_t(m) * kHidden + n0;
-    ld8(w + i, wv);
-    ld8(s + i, sv);
-  }
-  __device__ void update8(int, int m, int n0, const float g[8], const float wv[8], float sv[8], float nw[8]) const {
+  __device__ float step_scalar() const { return opt_step_scalar(opt); }
+  __device__ void update8(int, int m, int n0, float l, const float g[8], float nw[8]) const {
     const int64_t i = int64_t(m) * kHidden + n0;
     if (dw_out) st8(dw_out + i, g);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {   // Neon RMSProp, same operation order as k_optimizer
-      const float gg = __fmul_rn(g[j], inv_bsz);
-      const float ns = __fadd_rn(__fmul_rn(decay, sv[j]), __fmul_rn(__fmul_rn(gg, gg), one_m_decay));
-      const float den = __fadd_rn(__fsqrt_rn(__fadd_rn(ns, eps)), eps);
-      nw[j] = __fsub_rn(wv[j], __fdiv_rn(__fmul_rn(gg, lr), den));
-      sv[j] = ns;
-    }
-    st8(w + i, nw);
-    st8(s + i, sv);
+    opt_update_vec<8>(opt, l, g, nw, w + i, s + i);   // the configured Neon optimizer (optim.cuh)
     uint4 hi, lo;
     umma::split8(nw, hi, lo);
     uint8_t* base = img_dgr + (int64_t(m / 128) * (kHidden / 64) + n0 / 64) * (128 * 256) +
@@ -498,8 +485,8 @@ struct PackConvDgrad { // B operand of a conv dgrad, one tile per output-parity 
 template <int KR, int N, bool DGRAD, int C, int R, int ST, bool XCHG = false>
 __global__ void __launch_bounds__(256)
 k_opt_conv(const float* __restrict__ part, int splits, float* __restrict__ w, float* __restrict__ sst,
-           uint8_t* __restrict__ img_fwd, uint8_t* __restrict__ img_dgr, float inv_bsz, float lr, float decay,
-           float one_m_decay, float eps, const XllArgs x, const KTrace kt) {
+           uint8_t* __restrict__ img_fwd, uint8_t* __restrict__ img_dgr, const OptArgs opt, const XllArgs x,
+           const KTrace kt) {
   constexpr int64_t kSize = int64_t(KR) * N;
   kt_begin(kt);
   pdl_wait();
@@ -551,23 +538,11 @@ k_opt_conv(const float* __restrict__ part, int splits, float* __restrict__ w, fl
     }
   }
   if (live && lane8 == 0) {
-    float4 wv = *reinterpret_cast<float4*>(w + i);
-    float4 sv = *reinterpret_cast<float4*>(sst + i);
-    float* gp = reinterpret_cast<float*>(&g);
-    float* wp = reinterpret_cast<float*>(&wv);
-    float* sp = reinterpret_cast<float*>(&sv);
+    float wp[4];
+    opt_update_vec<4>(opt, opt_step_scalar(opt), reinterpret_cast<const float*>(&g), wp, w + i, sst + i);
     __half hi[4], lo[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float gg = __fmul_rn(gp[j], inv_bsz);
-      const float ns = __fadd_rn(__fmul_rn(decay, sp[j]), __fmul_rn(__fmul_rn(gg, gg), one_m_decay));
-      const float den = __fadd_rn(__fsqrt_rn(__fadd_rn(ns, eps)), eps);
-      wp[j] = __fsub_rn(wp[j], __fdiv_rn(__fmul_rn(gg, lr), den));
-      sp[j] = ns;
-      umma2::split1(wp[j], hi[j], lo[j]);
-    }
-    *reinterpret_cast<float4*>(w + i) = wv;
-    *reinterpret_cast<float4*>(sst + i) = sv;
+    for (int j = 0; j < 4; ++j) umma2::split1(wp[j], hi[j], lo[j]);
     const int k = int(i / N), n0 = int(i % N);
     {  // forward image: rows = output channel n, 8-element chunks along k
       uint8_t* base = img_fwd + int64_t(k / 64) * (N * 256) + (k % 8) * 2;
@@ -610,28 +585,18 @@ k_opt_conv(const float* __restrict__ part, int splits, float* __restrict__ w, fl
 // co-reside with the tcgen05 kernels of the critical chain instead of locking them out of the SMs.
 __global__ void __launch_bounds__(256)
 k_opt_fc1(const float* __restrict__ dw, float* __restrict__ w, float* __restrict__ sst, uint8_t* __restrict__ img_dgr,
-          float inv_bsz, float lr, float decay, float one_m_decay, float eps, const KTrace kt) {
+          const OptArgs opt, const KTrace kt) {
   kt_begin(kt);
   pdl_wait();
   pdl_launch_dependents();
   constexpr int kNB = kHidden / 8;
+  const float l_step = opt_step_scalar(opt);
   for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < kFlat * kNB; id += gridDim.x * blockDim.x) {
     const int m = id / kNB, n0 = (id % kNB) * 8;
     const int64_t i = int64_t(m) * kHidden + n0;
-    float g[8], wv[8], sv[8];
+    float g[8], wv[8];
     ld8(dw + i, g);
-    ld8(w + i, wv);
-    ld8(sst + i, sv);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {                        // Neon RMSProp, operation order of k_optimizer
-      const float gg = __fmul_rn(g[j], inv_bsz);
-      const float ns = __fadd_rn(__fmul_rn(decay, sv[j]), __fmul_rn(__fmul_rn(gg, gg), one_m_decay));
-      const float den = __fadd_rn(__fsqrt_rn(__fadd_rn(ns, eps)), eps);
-      wv[j] = __fsub_rn(wv[j], __fdiv_rn(__fmul_rn(gg, lr), den));
-      sv[j] = ns;
-    }
-    st8(w + i, wv);
-    st8(sst + i, sv);
+    opt_update_vec<8>(opt, l_step, g, wv, w + i, sst + i);   // the configured Neon optimizer (optim.cuh)
     uint4 hi, lo;
     umma::split8(wv, hi, lo);
     uint8_t* base = img_dgr + (int64_t(m / 128) * (kHidden / 64) + n0 / 64) * (128 * 256) +
@@ -646,20 +611,17 @@ int umma_opt_fc1(b200dqn_net* n, int rows, cudaStream_t st, bool from_g) {
   UmmaState* u = ust(n);
   const LayerTable& lt = n->lt;
   const float* dw = from_g ? n->d_g + lt.off[3] : n->d_part + lt.part_off[3];
-  B2_CHECK_CUDA(launch_pdl(k_opt_fc1, dim3(2 * 148), dim3(256), 0, st, dw, n->d_w + lt.off[3], n->d_s + lt.off[3],
-                           u->img_dgr[0], 1.0f / float(rows * n->world), float(n->cfg.learning_rate),
-                           float(n->cfg.decay_rate), float(1.0 - n->cfg.decay_rate), 1e-6f, ktrace_slot("opt_fc1")));
+  B2_CHECK_CUDA(launch_pdl(k_opt_fc1, dim3(2 * n->sm_count), dim3(256), 0, st, dw, n->d_w + lt.off[3],
+                           n->d_s + lt.off[3], u->img_dgr[0], make_opt_args(n, rows), ktrace_slot("opt_fc1")));
   B2_PROF("opt_fc1", st);
-  return umma2::launch_pack("pack_fc1f", PackFc1Fwd{n->d_w + lt.off[3]}, u->img_fwd[0][3], st, 2 * 148);
+  return umma2::launch_pack("pack_fc1f", PackFc1Fwd{n->d_w + lt.off[3]}, u->img_fwd[0][3], st, 2 * n->sm_count);
 }
 
 // RMSProp + image refresh of conv layer l (0..2), fused (single-GPU path of the tcgen05 engine).
 int umma_opt_conv(b200dqn_net* n, int l, int rows, cudaStream_t st, const char* label, bool from_g) {
   UmmaState* u = ust(n);
   const LayerTable& lt = n->lt;
-  const float inv_bsz = 1.0f / float(rows * n->world);
-  const float lr = float(n->cfg.learning_rate), decay = float(n->cfg.decay_rate);
-  const float omd = float(1.0 - n->cfg.decay_rate), eps = 1e-6f;
+  const OptArgs opt = make_opt_args(n, rows);
   const float* part = from_g ? n->d_g + lt.off[l] : n->d_part + lt.part_off[l];
   const int nsplits = from_g ? 1 : lt.splits[l];
   float* w = n->d_w + lt.off[l];
@@ -671,13 +633,13 @@ int umma_opt_conv(b200dqn_net* n, int l, int rows, cudaStream_t st, const char* 
   const XllArgs none{};
   if (l == 0)
     e = launch_pdl(k_opt_conv<kK1, kC1, false, 4, 8, 4>, grid, block, 0, st, part, nsplits, w, s, u->img_fwd[0][0],
-                   (uint8_t*)nullptr, inv_bsz, lr, decay, omd, eps, none, ktrace_slot(label));
+                   (uint8_t*)nullptr, opt, none, ktrace_slot(label));
   else if (l == 1)
     e = launch_pdl(k_opt_conv<kK2, kC2, true, kC1, 4, 2>, grid, block, 0, st, part, nsplits, w, s, u->img_fwd[0][1],
-                   u->img_dgr[2], inv_bsz, lr, decay, omd, eps, none, ktrace_slot(label));
+                   u->img_dgr[2], opt, none, ktrace_slot(label));
   else
     e = launch_pdl(k_opt_conv<kK3, kC3, true, kC2, 3, 1>, grid, block, 0, st, part, nsplits, w, s, u->img_fwd[0][2],
-                   u->img_dgr[1], inv_bsz, lr, decay, omd, eps, none, ktrace_slot(label));
+                   u->img_dgr[1], opt, none, ktrace_slot(label));
   B2_CHECK_CUDA(e);
   B2_PROF(label, st);
   return B200DQN_OK;
@@ -689,9 +651,7 @@ int umma_opt_conv(b200dqn_net* n, int l, int rows, cudaStream_t st, const char* 
 int umma_opt_conv_xll(b200dqn_net* n, int l, int rows, cudaStream_t st, const char* label) {
   UmmaState* u = ust(n);
   const LayerTable& lt = n->lt;
-  const float inv_bsz = 1.0f / float(rows * n->world);
-  const float lr = float(n->cfg.learning_rate), decay = float(n->cfg.decay_rate);
-  const float omd = float(1.0 - n->cfg.decay_rate), eps = 1e-6f;
+  const OptArgs opt = make_opt_args(n, rows);
   B2_REQUIRE(l >= 0 && l < 3 && lt.splits[l] <= 64 && n->world <= 8, B200DQN_EINVAL, "opt_conv_xll: bad layer / world");
   XllArgs x{};
   int rc = comm_xll_args(n, l, &x);
@@ -704,13 +664,13 @@ int umma_opt_conv_xll(b200dqn_net* n, int l, int rows, cudaStream_t st, const ch
   cudaError_t e;
   if (l == 0)
     e = launch_pdl(k_opt_conv<kK1, kC1, false, 4, 8, 4, true>, grid, block, 0, st, part, lt.splits[l], w, s,
-                   u->img_fwd[0][0], (uint8_t*)nullptr, inv_bsz, lr, decay, omd, eps, x, ktrace_slot(label));
+                   u->img_fwd[0][0], (uint8_t*)nullptr, opt, x, ktrace_slot(label));
   else if (l == 1)
     e = launch_pdl(k_opt_conv<kK2, kC2, true, kC1, 4, 2, true>, grid, block, 0, st, part, lt.splits[l], w, s,
-                   u->img_fwd[0][1], u->img_dgr[2], inv_bsz, lr, decay, omd, eps, x, ktrace_slot(label));
+                   u->img_fwd[0][1], u->img_dgr[2], opt, x, ktrace_slot(label));
   else
     e = launch_pdl(k_opt_conv<kK3, kC3, true, kC2, 3, 1, true>, grid, block, 0, st, part, lt.splits[l], w, s,
-                   u->img_fwd[0][2], u->img_dgr[1], inv_bsz, lr, decay, omd, eps, x, ktrace_slot(label));
+                   u->img_fwd[0][2], u->img_dgr[1], opt, x, ktrace_slot(label));
   B2_CHECK_CUDA(e);
   B2_PROF(label, st);
   return B200DQN_OK;
@@ -956,8 +916,7 @@ int umma_fc1_wgrad_fused(b200dqn_net* n, int rows, cudaStream_t st, bool keep_gr
   const LayerTable& lt = n->lt;
   WFc1WgradFused p{PlanePair{u->h16[2][0], u->h_elems[2]}, PlanePair{u->dz16[0], u->dz_elems[0]},
                    n->d_w + lt.off[3], n->d_s + lt.off[3], keep_grads ? n->d_part + lt.part_off[3] : nullptr,
-                   u->img_fwd[0][3], u->img_dgr[0], rows, 1.0f / float(rows * n->world),
-                   float(n->cfg.learning_rate), float(n->cfg.decay_rate), float(1.0 - n->cfg.decay_rate), 1e-6f};
+                   u->img_fwd[0][3], u->img_dgr[0], rows, make_opt_args(n, rows)};
   return umma_mn::launch_umma_mn("fc1_wgrad+opt", p, kFlat, kHidden, 1, st);
 }
 

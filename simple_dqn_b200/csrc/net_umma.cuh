@@ -5,10 +5,13 @@
 
 #include "common.cuh"
 #include "comm_p2p.cuh"
+#include "optim.cuh"
 
 struct b200dqn_net;
 
 namespace b200 {
+
+OptArgs make_opt_args(const b200dqn_net* n, int rows);   // net.cu: optimizer constants of this net
 
 // tcgen05 engine (net_umma.cu)
 int umma_net_init(b200dqn_net* n);                      // allocate operand images etc. (no-op in SIMT mode)

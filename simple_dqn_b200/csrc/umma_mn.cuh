@@ -251,13 +251,7 @@ __global__ void __launch_bounds__(kThreads2, 1) k_umma_mn(const P p, const KTrac
         //         back into the smem tile and into the row-oriented (dgrad) tile image;
         // pass 2, thread <-> (column n, 8 consecutive m): the column-oriented (forward) tile image.
         constexpr int kIt = kBM * kChunksPerRow / kLoadThreads;
-        float wv[kIt][8], sv[kIt][8];
-#pragma unroll
-        for (int i = 0; i < kIt; ++i) {   // all parameter loads in flight before any arithmetic
-          const int id = tid + i * kLoadThreads;
-          const int r = id / kChunksPerRow, cc = id % kChunksPerRow;
-          if (m0 + r < M && n0 + cc * 8 < N) p.load_ws(z, m0 + r, n0 + cc * 8, wv[i], sv[i]);
-        }
+        const float l_step = p.step_scalar();
 #pragma unroll
         for (int i = 0; i < kIt; ++i) {
           const int id = tid + i * kLoadThreads;
@@ -267,7 +261,7 @@ __global__ void __launch_bounds__(kThreads2, 1) k_umma_mn(const P p, const KTrac
           const float g[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
           if (m0 + r < M && n0 + cc * 8 < N) {
             float nw[8];
-            p.update8(z, m0 + r, n0 + cc * 8, g, wv[i], sv[i], nw);
+            p.update8(z, m0 + r, n0 + cc * 8, l_step, g, nw);
             *reinterpret_cast<float4*>(src) = make_float4(nw[0], nw[1], nw[2], nw[3]);
             *reinterpret_cast<float4*>(src + 4) = make_float4(nw[4], nw[5], nw[6], nw[7]);
           }

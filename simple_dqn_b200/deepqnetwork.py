@@ -14,6 +14,8 @@ logger = logging.getLogger(__name__)
 
 # (R, S, K, stride) of deepqnetwork.py:83-87
 _CONV = [(8, 8, 32, 4), (4, 4, 64, 2), (3, 3, 64, 1)]
+# --optimizer (main.py:40, deepqnetwork.py:50-61) -> (library code, number of Neon state arrays per W)
+_OPTIMIZERS = {"rmsprop": (L.OPT_RMSPROP, 1), "adam": (L.OPT_ADAM, 2), "adadelta": (L.OPT_ADADELTA, 3)}
 
 
 def _arg(args, name, default):
@@ -35,8 +37,8 @@ class DeepQNetwork:
         # flags of the reference this build accepts but does not implement (SURVEY §8 a17 note)
         if self.batch_norm:
             raise NotImplementedError("--batch_norm is not implemented on the B200 path")
-        if _arg(args, "optimizer", "rmsprop") != "rmsprop":
-            raise NotImplementedError("only --optimizer rmsprop is implemented on the B200 path")
+        self.optimizer = _arg(args, "optimizer", "rmsprop")
+        assert self.optimizer in _OPTIMIZERS, "Unknown optimizer"       # :60-61
         if np.dtype(_arg(args, "datatype", "float32")) != np.float32:
             raise NotImplementedError("only --datatype float32 is implemented on the B200 path")
         if _arg(args, "stochastic_round", False):
@@ -60,6 +62,7 @@ class DeepQNetwork:
         if math_mode is None:
             math_mode = _arg(args, "math_mode", "fp32")
         cfg.math_mode = {"fp32": L.MATH_FP32_SIMT, "tcgen05": L.MATH_TCGEN05}[math_mode]
+        cfg.optimizer, self.num_states = _OPTIMIZERS[self.optimizer]
         self.math_mode = math_mode
         h = C.c_void_p()
         L.call("b200dqn_net_create", self.device, C.byref(cfg), C.byref(h))
@@ -102,8 +105,22 @@ class DeepQNetwork:
         L.call("b200dqn_net_set_weights", self._h, which, layer, L.np_ptr(w), L.np_ptr(s), self._stream)
 
     def set_weights(self, weights, states=None, which=0):
+        """states: per layer either ONE array (Neon's ``states[0]``, all RMSProp needs) or the list of the
+        optimizer's state arrays (Adam [m, v], Adadelta [E[g^2], E[dx^2], dx])."""
         for layer, w in enumerate(weights):
-            self._set_layer(which, layer, w, None if states is None else states[layer])
+            st = None if states is None else states[layer]
+            if isinstance(st, (list, tuple)):
+                self._set_layer(which, layer, w, None)
+                self._set_states(which, layer, st)
+            else:
+                self._set_layer(which, layer, w, st)
+
+    def _set_states(self, which, layer, arrays):
+        assert len(arrays) <= self.num_states, (len(arrays), self.num_states)
+        for k, a in enumerate(arrays):
+            a = np.ascontiguousarray(a, dtype=np.float32)
+            assert a.shape == self.layer_shapes()[layer]
+            L.call("b200dqn_net_set_state", self._h, which, layer, k, L.np_ptr(a), self._stream)
 
     def get_weights(self, which=0, with_states=True):
         ws, ss = [], []
@@ -114,6 +131,18 @@ class DeepQNetwork:
             ws.append(w)
             ss.append(s)
         return (ws, ss) if with_states else ws
+
+    def get_states(self, which=0):
+        """Every optimizer state array per layer, like Neon's ``states`` lists."""
+        out = []
+        for layer, shp in enumerate(self.layer_shapes()):
+            planes = []
+            for k in range(self.num_states):
+                a = np.empty(shp, dtype=np.float32)
+                L.call("b200dqn_net_get_state", self._h, which, layer, k, L.np_ptr(a), self._stream)
+                planes.append(a)
+            out.append(planes)
+        return out
 
     def keep_grads(self, keep=True):
         """Make the fused optimizers keep a copy of dW so :meth:`get_grads` works (tests / debugging)."""
@@ -218,23 +247,69 @@ class DeepQNetwork:
         return q                                                        # (batch, A) == qvalues.T (:186)
 
     def load_weights(self, load_path):
-        """Model.load_params (:188-189): both pickle layouts found in the reference's snapshots/."""
+        """Model.load_params (:188-189): both pickle layouts found in the reference's snapshots/ —
+        the pre-1.0 ``layer_params_states`` list (breakout/pong; src/util/convert_weights.py:10-12) and the
+        neon-1.3.0 ``model.config.layers`` list (seaquest/space_invaders).  Weights AND optimizer states
+        are restored (Model.load_params(load_states=True) is Neon's default)."""
         with open(load_path, "rb") as f:
             d = pickle.load(f, encoding="latin1")
-        if "layer_params_states" in d:                                  # pre-1.0 layout (convert_weights.py:10-12)
+        if "layer_params_states" in d:
             ls = d["layer_params_states"]
-        else:                                                           # neon 1.3.0 layout
+        else:
             ls = [l for l in d["model"]["config"]["layers"] if "params" in l]
+        assert len(ls) == 5, "checkpoint does not hold the five weight layers of deepqnetwork.py:77-92"
         ws = [np.asarray(l["params"]["W"], dtype=np.float32) for l in ls]
-        ss = [np.asarray(l["states"][0], dtype=np.float32) if l.get("states") else np.zeros_like(w)
-              for l, w in zip(ls, ws)]
-        self.set_weights(ws, ss)
+        for layer, (l, w) in enumerate(zip(ls, ws)):
+            assert w.shape == self.layer_shapes()[layer], \
+                "layer %d: checkpoint shape %s, network shape %s" % (layer, w.shape, self.layer_shapes()[layer])
+            st = [np.asarray(a, dtype=np.float32) for a in (l.get("states") or [])][:self.num_states]
+            self._set_layer(0, layer, w, None)
+            if st:
+                self._set_states(0, layer, st)
+            if len(st) < self.num_states:        # states the checkpoint's optimizer did not keep start at zero
+                self._set_states(0, layer, st + [np.zeros_like(w)] * (self.num_states - len(st)))
 
-    def save_weights(self, save_path):
-        """Model.save_params (:191-192), written in the pre-1.0 layout the loader above reads."""
-        ws, ss = self.get_weights()
-        d = {"epoch_index": 0,
-             "layer_params_states": [{"params": {"W": w}, "states": [s]} for w, s in zip(ws, ss)]}
+    def save_weights(self, save_path, layout="neon-1.3.0"):
+        """Model.save_params (:191-192).  ``layout="neon-1.3.0"`` (default) writes the structure the reference's
+        current Neon writes and reads (same keys, layer list and type strings as snapshots/seaquest_178.pkl);
+        ``layout="pre-1.0"`` writes the older ``layer_params_states`` list.  :meth:`load_weights` reads both."""
+        ws = self.get_weights(with_states=False)
+        ss = self.get_states()
+        if layout == "pre-1.0":
+            d = {"epoch_index": 0,
+                 "layer_params_states": [{"params": {"W": w}, "states": list(s)} for w, s in zip(ws, ss)]}
+        else:
+            assert layout == "neon-1.3.0", layout
+            layers = []
+            for i, (w, s) in enumerate(zip(ws, ss)):
+                if i < 3:
+                    r, _, k, stride = _CONV[i]
+                    layers.append({"type": "neon.layers.layer.Convolution",
+                                   "config": {"fshape": (r, r, k), "strides": stride, "name": "Convolution_%d" % i,
+                                              "parallelism": "Disabled",
+                                              "init": {"type": "neon.initializers.initializer.Xavier",
+                                                       "config": {"local": True}}},
+                                   "params": {"W": w}, "states": list(s)})
+                else:
+                    layers.append({"type": "neon.layers.layer.Linear",
+                                   "config": {"nout": int(w.shape[0]), "name": "Linear_%d" % (i - 3),
+                                              "init": {"type": "neon.initializers.initializer.Xavier",
+                                                       "config": {"local": False}}},
+                                   "params": {"W": w}, "states": list(s)})
+                if i < 4:                                            # Rectlin after the first four (:83-89)
+                    name = layers[-1]["config"]["name"]
+                    layers.append({"type": "neon.layers.layer.Activation",
+                                   "config": {"name": name + "_Rectlin",
+                                              "transform": {"type": "neon.transforms.activation.Rectlin",
+                                                            "config": {"name": "Rectlin_%d" % i}}}})
+            d = {"neon_version": "1.3.0+344372b", "epoch_index": 0,
+                 "train_input_shape": (self.history_length,) + self.screen_dim,
+                 "backend": {"type": "b200dqn", "compat_mode": "neon", "rng_seed": None},
+                 "cost": {"type": "neon.layers.layer.GeneralizedCost",
+                          "config": {"name": "GeneralizedCost_0",
+                                     "costfunc": {"type": "neon.transforms.cost.SumSquared", "config": {}}}},
+                 "model": {"type": "neon.layers.container.Sequential", "container": True,
+                           "config": {"name": "Sequential_0", "layers": layers}}}
         with open(save_path, "wb") as f:
             pickle.dump(d, f, protocol=2)
 

@@ -33,19 +33,35 @@ def _net(num_actions, mode, stream=None, **kw):
         pytest.skip(str(e))
 
 
-def _paired(num_actions, mode, seed=3, batch=32, stream=None):
+def _stream(sched):
+    """"serial": legacy default stream (plain serial launches, generic k_optimizer); "branches": a library
+    stream, i.e. the PRODUCTION schedule — side-stream branches, PDL chain, fused per-layer optimizers."""
+    from simple_dqn_b200 import Stream
+    return Stream() if sched == "branches" else None
+
+
+SCHEDS = ["serial", "branches"]
+
+
+def _paired(num_actions, mode, seed=3, batch=32, stream=None, optimizer="rmsprop"):
     """A device net and an oracle net holding identical fp32 weights (trained-looking scale)."""
-    net = _net(num_actions, mode, stream=stream, batch_size=batch, random_seed=seed)
+    net = _net(num_actions, mode, stream=stream, batch_size=batch, random_seed=seed, optimizer=optimizer)
     ws, ss = net.get_weights()
     # Xavier weights give Q ~ 1e-2; scale the last layers so Q ~ O(1) like a trained net
     ws[3] = ws[3] * np.float32(3.0)
     ws[4] = ws[4] * np.float32(3.0)
     rs = np.random.RandomState(seed)
     ss = [np.abs(rs.randn(*w.shape)).astype(np.float32) * np.float32(1e-4) for w in ws]
+    f = lambda scale, w, absolute=False: ((np.abs(rs.randn(*w.shape)) if absolute else rs.randn(*w.shape)) *
+                                          scale).astype(np.float32)
+    if optimizer == "adam":         # Neon states [m, v]
+        ss = [[f(1e-3, w), f(1e-5, w, True)] for w in ws]
+    elif optimizer == "adadelta":   # Neon states [E[g^2], E[dx^2], dx]
+        ss = [[f(1e-5, w, True), f(1e-9, w, True), f(1e-4, w)] for w in ws]
     net.set_weights(ws, ss)
     net.update_target_network()
     net.keep_grads(True)            # the fused optimizers otherwise never materialise dW4
-    orc = O.DQNOracle(num_actions, batch_size=batch, weights=ws, states=ss)
+    orc = O.DQNOracle(num_actions, batch_size=batch, weights=ws, states=ss, optimizer=optimizer)
     return net, orc
 
 
@@ -60,16 +76,18 @@ def test_xavier_init_matches_oracle_draw_order(mode):
 
 
 @pytest.mark.parametrize("mode", MODES)
-@pytest.mark.parametrize("num_actions", [4, 18])
-def test_predict_parity(mode, num_actions):
-    net, orc = _paired(num_actions, mode)
-    states = random_minibatch(32, num_actions, 1)[0]
+@pytest.mark.parametrize("num_actions,batch", [(4, 32), (18, 32), (4, 1), (6, 8), (4, 40), (4, 256)])
+def test_predict_parity(mode, num_actions, batch):
+    """net_create takes any batch 1..4096 (tile tails, partial M tiles): every size is held to the same bar."""
+    net, orc = _paired(num_actions, mode, batch=batch)
+    states = random_minibatch(batch, num_actions, 1)[0]
     q = net.predict(states)
     ref = orc.predict(states)
-    assert q.shape == (32, num_actions) and q.dtype == np.float32
+    assert q.shape == (batch, num_actions) and q.dtype == np.float32
     assert np.abs(q - ref).max() <= 1e-3 * np.abs(ref).max(), np.abs(q - ref).max() / np.abs(ref).max()
-    with pytest.raises(AssertionError):
-        net.predict(states[:5])                                 # deepqnetwork.py:176
+    if batch > 5:
+        with pytest.raises(AssertionError):
+            net.predict(states[:5])                             # deepqnetwork.py:176
 
 
 @pytest.mark.parametrize("mode", MODES)
@@ -85,11 +103,15 @@ def test_forward_activations_layer_by_layer(mode):
 
 
 @pytest.mark.parametrize("mode", MODES)
-def test_train_step_parity(mode):
-    net, orc = _paired(4, mode)
+@pytest.mark.parametrize("sched", SCHEDS)
+@pytest.mark.parametrize("batch", [32, 1, 8, 40, 256])
+def test_train_step_parity(mode, sched, batch):
+    if mode == "fp32" and not (batch == 32 or (batch == 8 and sched == "serial")):
+        pytest.skip("the SIMT twin is swept at batch 8 and 32 only (it is the cross-check, not the product)")
+    net, orc = _paired(4, mode, batch=batch, stream=_stream(sched))
     costs = []
     net.callback = type("CB", (), {"on_train": staticmethod(lambda c: costs.append(c))})()
-    mb = random_minibatch(32, 4, 2)
+    mb = random_minibatch(batch, 4, 2)
     w0 = [w.copy() for w in orc.weights]
     net.train(mb, 0)
     ref_cost = orc.train(mb)
@@ -111,10 +133,12 @@ def test_train_step_parity(mode):
 
 
 @pytest.mark.parametrize("mode", MODES)
-def test_rmsprop_bit_exact_given_same_gradient(mode):
+@pytest.mark.parametrize("sched", SCHEDS)
+def test_rmsprop_bit_exact_given_same_gradient(mode, sched):
     """The optimizer arithmetic itself (Neon RMSProp order of operations) is bit-exact vs the
-    oracle when fed the device's own gradient."""
-    net, orc = _paired(4, mode)
+    oracle when fed the device's own gradient — in the generic k_optimizer (serial) and in the fused
+    per-layer optimizers of the production schedule (k_opt_conv / k_opt_fc1)."""
+    net, orc = _paired(4, mode, stream=_stream(sched))
     mb = random_minibatch(32, 4, 5)
     w0, s0 = net.get_weights()
     net.train(mb, 0)
@@ -138,9 +162,10 @@ def test_trajectory_20_steps_with_target_sync(mode):
     device must stay within 3x of how far the two CPU implementations drift apart; the first
     5 steps are held to an absolute 2e-2."""
     from oracle.dqn_torch import TorchDQN
-    net, orc = _paired(6, mode)
+    net, orc = _paired(6, mode, stream=_stream("branches"))
     tor = TorchDQN(orc.weights, orc.states)
     w0 = [w.copy() for w in orc.weights]
+    ref_costs = []
     for i in range(20):
         mb = random_minibatch(32, 6, 100 + i, terminal_p=0.1)
         if i % 7 == 0:
@@ -148,7 +173,7 @@ def test_trajectory_20_steps_with_target_sync(mode):
             orc.update_target_network()
             tor.update_target_network()
         net.train(mb, 0)
-        orc.train(mb)
+        ref_costs.append(float(orc.train(mb)))
         tor.train(mb)
         if i == 4:
             ws = net.get_weights(with_states=False)
@@ -162,6 +187,10 @@ def test_trajectory_20_steps_with_target_sync(mode):
         assert rel_l2(ws[l], orc.weights[l]) <= 3e-2, l           # and the weights themselves stay close
     c = net.last_costs(20)
     assert c.shape == (20,) and np.isfinite(c).all()
+    # per-step cost trace: tight while the trajectories coincide, bounded by the weight drift afterwards
+    rel = np.abs(c - np.array(ref_costs)) / np.abs(ref_costs)
+    assert rel[:5].max() <= 2e-3, rel[:5]
+    assert rel.max() <= 5e-2, rel
 
 
 @pytest.mark.parametrize("mode", MODES)
@@ -242,10 +271,12 @@ def test_state_buffer_predict_fast_path(mode):
 
 def test_reference_flags_not_implemented_raise():
     from simple_dqn_b200 import DeepQNetwork
-    for kw in (dict(batch_norm=True), dict(optimizer="adam"), dict(datatype="float16"), dict(stochastic_round=True),
+    for kw in (dict(batch_norm=True), dict(datatype="float16"), dict(stochastic_round=True),
                dict(screen_height=52, screen_width=40)):
         with pytest.raises(NotImplementedError):
             DeepQNetwork(4, make_args(**kw))
+    with pytest.raises(AssertionError):                          # deepqnetwork.py:60-61
+        DeepQNetwork(4, make_args(optimizer="sgd"))
 
 
 def test_target_steps_zero_aliases_online():
@@ -257,14 +288,18 @@ def test_target_steps_zero_aliases_online():
     assert all((x == y).all() for x, y in zip(a, b))            # deepqnetwork.py:72-73
 
 
-def test_snapshot_roundtrip_old_layout(tmp_path):
+@pytest.mark.parametrize("layout", ["pre-1.0", "neon-1.3.0"])
+def test_snapshot_roundtrip(tmp_path, layout):
     net = _net(4, "fp32", random_seed=2)
     mb = random_minibatch(32, 4, 3)
     net.train(mb, 0)
     path = str(tmp_path / "w_1.prm")
-    net.save_weights(path)
+    net.save_weights(path, layout=layout)
     d = pickle.load(open(path, "rb"))
-    assert set(d) == {"epoch_index", "layer_params_states"} and len(d["layer_params_states"]) == 5
+    if layout == "pre-1.0":
+        assert set(d) == {"epoch_index", "layer_params_states"} and len(d["layer_params_states"]) == 5
+    else:
+        assert len(d["model"]["config"]["layers"]) == 9
     net2 = _net(4, "fp32", random_seed=99)
     net2.load_weights(path)
     for (a, sa), (b, sb) in zip(zip(*net.get_weights()), zip(*net2.get_weights())):

@@ -7,11 +7,12 @@ from simple_dqn_b200 import DeepQNetwork, ReplayMemory, Stream, _lib as L
 st = Stream()
 replay = 50000
 base, actions, rewards, terminals = synthetic_meta(replay)
-mem = ReplayMemory(replay, make_args(32), stream=st, rng="device")
+B = int(os.environ.get("BATCH", "32"))
+mem = ReplayMemory(replay, make_args(B), stream=st, rng="device")
 for s in range(0, replay, 10000):
     mem.add_batch(actions[s:s + 10000], rewards[s:s + 10000], base, terminals[s:s + 10000])
 mem.set_cursor(replay, 1234)
-net = DeepQNetwork(NUM_ACTIONS, make_args(32), stream=st, math_mode=os.environ.get("MATH", "tcgen05"))
+net = DeepQNetwork(NUM_ACTIONS, make_args(B), stream=st, math_mode=os.environ.get("MATH", "tcgen05"))
 net.update_target_network()
 random.seed(1); mem.seed_device_rng(random)
 net.train_fused(mem, 50); st.synchronize()
