@@ -192,7 +192,7 @@ class DeepQNetwork:
                 cost = C.c_float()
                 L.call("b200dqn_net_train_sampled_cost", self._h, minibatch._mem._h, C.byref(cost), self._stream)
                 self.train_iterations += 1
-                self.callback.on_train(cost.value)                      # :171-172
+                self.callback.on_train(np.float32(cost.value))          # :171-172 (cost[0,0] is a numpy float32)
             else:
                 L.call("b200dqn_net_train_sampled", self._h, minibatch._mem._h, self._stream)
                 self.train_iterations += 1
@@ -216,7 +216,7 @@ class DeepQNetwork:
                L.np_ptr(term), C.byref(cost), self._stream)
         self.train_iterations += 1                                      # :168
         if self.callback:
-            self.callback.on_train(cost.value)                          # :171-172
+            self.callback.on_train(np.float32(cost.value))              # :171-172 (cost[0,0] is a numpy float32)
 
     def train_fused(self, mem, nsteps=1):
         """`nsteps` x (mem.getMinibatch(); self.train(...)) of agent.py:112-114 with no host round trip
