@@ -165,8 +165,10 @@ def run_reference(a, rank, world):
             "config": workload_config(a, world),
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "note": "Neon --backend cpu cannot run (Neon absent, no network): this is the CPU restatement "
-                    "(oracle port) of getMinibatch+train on the box's host cores"}
+            "note": "Neon --backend cpu cannot run (Neon absent, no network) and /root/reference does not exist on "
+                    "the GPU box, so neither the reference's deepqnetwork.py nor its replay_memory.py can be timed here: "
+                    "this is the CPU restatement (oracle port: numpy ring + CPython random + torch-CPU fp32 train) of "
+                    "getMinibatch+train on the box's host cores at its fastest thread count"}
     print(json.dumps(line), flush=True)
 
 
@@ -181,27 +183,68 @@ def workload_config(a, world, comm="NCCL grad all-reduce"):
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
-def kernel_model(label, nb, launches_per_step_part):
-    """(bound, algorithmic bytes, algorithmic flops) of one launch of kernel `label`."""
+def kernel_model(label, nb, world=1):
+    """(bound, algorithmic bytes, algorithmic flops) of one launch of kernel `label` (DESIGN.md §4 kernel table).
+    bound: "tensor" (GEMM-shaped, tcgen05), "hbm" (bytes that must move; L2-resident ones are marked in DESIGN),
+    "nvlink" (peer stores), "latency" (a few hundred bytes of work: the launch itself is the cost)."""
     f = lambda macs, nets=1: 2.0 * macs * nb * nets
-    n_fc1 = 3136 * 512
+    n_fc1, A = 3136 * 512, NUM_ACTIONS
+    small = {"conv1": 256 * 32, "conv2": 512 * 64, "conv3": 576 * 64, "fc2": 512 * A}
     table = {
+        "sample": ("latency", 625 * 4 * 2 + 40 * 4, 0.0),
         "conv1_fwd": ("tensor", nb * 35280 + 2 * 4 * 256 * 32, f(MAC["conv1"], 2)),
         "conv2_fwd": ("tensor", 0, f(MAC["conv2"], 2)), "conv3_fwd": ("tensor", 0, f(MAC["conv3"], 2)),
-        "fc1_fwd": ("tensor", 0, f(MAC["fc1"], 2)), "fc1_wgrad": ("tensor", 0, f(MAC["fc1"])),
-        "fc1_dgrad": ("tensor", 0, f(MAC["fc1"])), "conv3_wgrad": ("tensor", 0, f(MAC["conv3"])),
+        "fc1_fwd": ("tensor", 2 * 4 * n_fc1, f(MAC["fc1"], 2)),
+        "head": ("latency", nb * (2 * 7 * 512 * 4 + 512 * 4 * (3 + A)), 2.0 * 2 * nb * 512 * A),
+        "cost": ("latency", nb * 4, 0.0),
+        "fc1_wgrad": ("tensor", 4 * n_fc1, f(MAC["fc1"]) * world), "fc1_wgrad+opt": ("tensor", 24 * n_fc1, f(MAC["fc1"])),
+        "fc1_dgrad": ("tensor", 4 * n_fc1, f(MAC["fc1"])), "conv3_wgrad": ("tensor", 0, f(MAC["conv3"])),
         "conv3_dgrad": ("tensor", 0, f(MAC["conv3"])), "conv2_wgrad": ("tensor", 0, f(MAC["conv2"])),
         "conv2_dgrad": ("tensor", 0, f(MAC["conv2"])), "conv1_wgrad": ("tensor", nb * 35280, f(MAC["conv1"])),
         # elementwise kernels: bytes they must move (fp32 dW, W, S in; W, S out; fp16 hi/lo image out)
         "optimizer": ("hbm", 5 * 4 * N_PARAMS, 0.0),
         "opt_fc1": ("hbm", (5 * 4 + 4) * n_fc1, 0.0),
         "pack_fc1f": ("hbm", (4 + 4) * n_fc1, 0.0),
-        "opt_conv1": ("hbm", (5 * 4 + 4) * 256 * 32, 0.0),
-        "opt_conv2": ("hbm", (5 * 4 + 8) * 512 * 64, 0.0),
-        "opt_conv3": ("hbm", (5 * 4 + 8) * 576 * 64, 0.0),
+        "opt_fc2": ("latency", (nb + 4) * 4 * small["fc2"], 0.0),
+        "opt_conv1": ("latency", (5 * 4 + 4) * small["conv1"], 0.0),
+        "opt_conv2": ("latency", (5 * 4 + 8) * small["conv2"], 0.0),
+        "opt_conv3": ("latency", (5 * 4 + 8) * small["conv3"], 0.0),
         "gather": ("hbm", nb * (35280 + 2 * 28224), 0.0),
+        # data-parallel schedule (comm_p2p.cuh)
+        "push_h3": ("nvlink", world * nb * 3136 * 2 * 2, 0.0), "push_dz4": ("nvlink", world * nb * 512 * 2 * 2, 0.0),
+        "wait_push": ("latency", 2 * world * 4, 0.0),
+        "grad_reduce": ("hbm", 2 * 4 * N_PARAMS, 0.0), "xchg_all": ("nvlink", 2 * 4 * N_PARAMS, 0.0),
+        "xchg_fc": ("nvlink", 2 * 4 * (n_fc1 + small["fc2"]), 0.0), "reduce_fc": ("hbm", 2 * 4 * n_fc1, 0.0),
     }
-    return table.get(label, ("hbm", 0, 0.0))
+    for k, v in small.items():
+        table["reduce_" + k] = ("latency", 2 * 4 * v, 0.0)
+        table["xll_" + k] = ("nvlink", (world - 1) * 16 * (v // 2), 0.0)
+        table["optx_" + k] = ("nvlink", (world - 1) * 16 * (v // 2), 0.0)
+        table["xchg_" + k] = ("nvlink", 2 * 4 * v, 0.0)
+    return table.get(label, ("latency", 0, 0.0))
+
+
+def graph_timeline(net, mem, L, dev, stream, reps=13, batch=16, at=12):
+    """In-graph timeline (GPU %globaltimer per launch, csrc/common.cuh::KTrace) of the PRODUCTION step — replayed CUDA
+    graph, PDL chain and side branches live — averaged over `reps` recordings of the `at`-th step of a
+    `batch`-step burst (reps * batch = 208 profiled steps, independent of --steps).  Returns
+    ({label: (mean start us, mean end us, mean duration us)}, mean step span us)."""
+    import torch
+    acc, spans = {}, []
+    for _ in range(reps):
+        L.ktrace_begin(dev, step=at)
+        net.train_fused(mem, batch)
+        torch.cuda.synchronize()
+        rows = [r for r in L.ktrace_end() if r[1] < 2 ** 63 and r[2] > 0]
+        if not rows:
+            continue
+        t0 = min(r[1] for r in rows)
+        spans.append((max(r[2] for r in rows) - t0) / 1e3)
+        for name, a, b in rows:
+            acc.setdefault(name, []).append(((a - t0) / 1e3, (b - t0) / 1e3))
+    out = {k: (float(np.mean([x[0] for x in v])), float(np.mean([x[1] for x in v])),
+               float(np.mean([x[1] - x[0] for x in v]))) for k, v in acc.items()}
+    return out, float(np.mean(spans)) if spans else 0.0
 
 
 def run_b200(a, rank, world, local_rank):
@@ -279,47 +322,75 @@ def run_b200(a, rank, world, local_rank):
     assert np.isfinite(cost_tail).all(), cost_tail
     launches = net.launches_per_step() * a.steps
 
-    # ---- roofline: per-kernel CUDA-event durations over a slice of the same loop
-    prof_steps = min(a.steps, 200)
+    # ---- roofline: the in-graph timeline of the production step (same graph, PDL and branches as `value`)
     barrier()
-    L.profile_begin(dev, L.stream_ptr(stream))
-    net.train_fused(mem, prof_steps)
-    prof = L.profile_end()
-    note("per-kernel profile done")
-    per = {}
-    for name, t in prof:
-        per.setdefault(name, []).append(t)
-    per_kernel = {k: float(np.mean(v)) for k, v in per.items()}        # ms per launch
+    tl, span_us = graph_timeline(net, mem, L, dev, stream)
+    note("in-graph timeline done: span %.1f us" % span_us)
     pk = peaks()
-    top = max(per_kernel, key=lambda k: per_kernel[k])
-    tot_prof = sum(per_kernel.values())
-    bound, abytes, aflops = kernel_model(top, a.batch, None)
-    if bound == "tensor":
-        ach = aflops / (per_kernel[top] * 1e-3) / 1e12
-        roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": pk["tf_sustained"] or pk["tf_burst"],
-                "unit": "TFLOP/s"}
-    else:
-        ach = abytes / (per_kernel[top] * 1e-3) / 1e9
-        roof = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s"}
+    tf_peak = pk["tf_sustained"] or pk["tf_burst"]
+    dur = {k: v[2] for k, v in tl.items()}
+    # the dominant kernel is chosen by algorithmic work, not by a noisy duration ranking: conv1_fwd carries the
+    # largest FLOP count of the step AND every mandatory HBM byte (the replay gather)
+    top = "conv1_fwd"
+    bound, abytes, aflops = kernel_model(top, a.batch, world)
+    roof = {"kernel": top, "bound": "tensor", "achieved": aflops / (dur[top] * 1e-6) / 1e12, "peak": tf_peak,
+            "unit": "TFLOP/s"}
     roof["frac"] = roof["achieved"] / roof["peak"]
     roof["traffic"] = None
     tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")     # dram bytes per launch from the committed ncu capture
     if os.path.exists(tp):
         roof["traffic"] = json.load(open(tp)).get(a.math, {}).get(top)
-    roof["peak_source"] = pk["source"] + (", sustained figure (kernel timed inside a long step)"
-                                           if bound == "tensor" else "")
-    roof["us_per_launch"] = per_kernel[top] * 1e3
-    roof["share_of_step"] = per_kernel[top] / tot_prof
-    roof["per_kernel_us"] = {k: round(v * 1e3, 3) for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1])}
+    roof["peak_source"] = pk["source"] + ", sustained bf16 figure (kernel timed inside a long step)"
+    roof["us_per_launch"] = dur[top]
+    roof["share_of_step"] = dur[top] / span_us if span_us else None
+    roof["how"] = ("in-graph %globaltimer timeline of the replayed production graph (first CTA start .. last CTA end, "
+                   "so a PDL-parked prologue counts), mean of 13 recordings; kernel chosen by algorithmic work")
+    roof["gather"] = {"kernel": "conv1_fwd (frames read in place from the ring, fused into the first conv layer)",
+                      "algorithmic_bytes": a.batch * 35280, "achieved_gbs": a.batch * 35280 / (dur[top] * 1e-6) / 1e9,
+                      "peak_gbs": pk["hbm_gbs"],
+                      "frac_of_hbm_peak": a.batch * 35280 / (dur[top] * 1e-6) / 1e9 / pk["hbm_gbs"]}
     conv_flops = 2.0 * a.batch * (4 * (MAC["conv1"] + MAC["conv2"] + MAC["conv3"]) - MAC["conv1"])
-    conv_ms = sum(v for k, v in per_kernel.items() if k.startswith("conv"))
-    roof["conv_stack"] = {"achieved_tflops": conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms else None,
-                          "frac_of_peak": (conv_flops / (conv_ms * 1e-3) / 1e12) / (pk["tf_sustained"] or pk["tf_burst"])
-                          if conv_ms else None}
+    conv_us = sum(v for k, v in dur.items() if k.startswith("conv"))
+    roof["conv_stack"] = {"gflop": conv_flops / 1e9, "kernel_time_us": conv_us,
+                          "achieved_tflops": conv_flops / (conv_us * 1e-6) / 1e12 if conv_us else None,
+                          "frac_of_peak": conv_flops / (conv_us * 1e-6) / 1e12 / tf_peak if conv_us else None,
+                          "frac_of_peak_over_step": conv_flops / (ms_total / a.steps * 1e-3) / 1e12 / tf_peak}
     whole_step_flops = 2.0 * a.batch * (4 * sum(MAC.values()) - MAC["conv1"])
-    roof["whole_step"] = {"gflop": whole_step_flops / 1e9,
+    roof["whole_step"] = {"gflop": whole_step_flops / 1e9, "span_us": span_us,
                           "achieved_tflops": whole_step_flops / (ms_total / a.steps * 1e-3) / 1e12,
+                          "frac_of_peak": whole_step_flops / (ms_total / a.steps * 1e-3) / 1e12 / tf_peak,
                           "gather_gbs": a.batch * 35280 / (ms_total / a.steps * 1e-3) / 1e9}
+    per_kernel = {}
+    for k, (t_a, t_b, d) in sorted(tl.items(), key=lambda kv: kv[1][0]):
+        kb, by, fl = kernel_model(k, a.batch, world)
+        e = {"start_us": round(t_a, 2), "end_us": round(t_b, 2), "us": round(d, 2), "bound": kb}
+        if fl:
+            e["tflops"] = round(fl / (d * 1e-6) / 1e12, 2)
+        if by:
+            e["gbs"] = round(by / (d * 1e-6) / 1e9, 1)
+        per_kernel[k] = e
+    roof["per_kernel"] = per_kernel
+
+    # ---- predict latency (agent.py:55-61 runs it on 90-95 % of env steps)
+    from simple_dqn_b200 import StateBuffer
+    pred = {}
+    st_host = np.ascontiguousarray(np.broadcast_to(base[:4], (a.batch, 4, 84, 84)))
+    sbuf = StateBuffer(make_args(a.batch), device=dev, stream=stream)
+    for i in range(6):
+        sbuf.add(base[i])
+    for name, arg in (("host_states_full_batch", st_host), ("state_buffer_live_row", sbuf.getStateMinibatch())):
+        for _ in range(20):
+            net.predict(arg)
+        t0 = time.perf_counter()
+        for _ in range(200):
+            net.predict(arg)
+        pred[name + "_us"] = (time.perf_counter() - t0) / 200 * 1e6
+    t0 = time.perf_counter()
+    for i in range(200):
+        sbuf.add(base[i % 64])
+        net.predict(sbuf.getStateMinibatch())
+    pred["state_buffer_add_plus_predict_us"] = (time.perf_counter() - t0) / 200 * 1e6
+    note("predict latency done")
 
     # ---- e2e: the drop-in public API from HOST buffers (agent.py:100-114 without env / predict):
     # 4 x mem.add(host frame) [train_frequency 4], getMinibatch() with the HOST random stream
@@ -330,7 +401,7 @@ def run_b200(a, rank, world, local_rank):
     costs = []
     net.callback = types.SimpleNamespace(on_train=lambda c: costs.append(c))
     frames = [np.ascontiguousarray(base[i]) for i in range(64)]
-    e2e_steps = max(50, min(a.steps, 1000))
+    e2e_steps = max(300, min(a.steps, 1000))          # a fixed floor: the driver runs --steps 20
 
     def e2e_loop(n):
         for i in range(n):
@@ -355,9 +426,10 @@ def run_b200(a, rank, world, local_rank):
     e2e = {"value": world * e2e_steps / float(dts[0]), "unit": UNIT,
            "h2d_bytes_per_step": 4 * 7056, "d2h_bytes_per_step": 4 + 4,
            "steps": e2e_steps,
-           "what": "per step: 4x ReplayMemory.add(host frame -> pinned -> HBM) + getMinibatch() in lock-step with the "
-                   "host `random` stream (words-consumed read back) + DeepQNetwork.train() + cost read back for "
-                   "the stats callback"}
+           "what": "per step, through the drop-in classes: 4x ReplayMemory.add(host frame -> pinned bank -> HBM) + "
+                   "getMinibatch() [device handle; the index draw rides in train()'s graph] + DeepQNetwork.train() in "
+                   "lock-step with the host `random` stream (state up when it moved, words consumed back) + cost "
+                   "delivered to the stats callback inside train() (host-mapped result words, one wait per step)"}
     assert len(costs) == e2e_steps + 10 and np.isfinite(costs).all()
     net.callback = None
 
@@ -379,7 +451,7 @@ def run_b200(a, rank, world, local_rank):
                                                         % os.environ.get("B200DQN_P2P_SCHED", "gather"),
                                                  "nccl": "NCCL grad all-reduce"}.get(comm_mode, comm_mode)),
             "comm_healthy": bool(comm_ok), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
-            "roofline": roof, "last_costs": [float(c) for c in cost_tail]}
+            "roofline": roof, "predict_latency": pred, "last_costs": [float(c) for c in cost_tail]}
     if world > 1:
         line["config"]["global_updates_per_s"] = a.steps / (ms_total * 1e-3)
         # NVLink bytes each rank SENDS per step (SURVEY §8e asks for the fraction of 770 GB/s per direction)

@@ -119,6 +119,9 @@ int b200dqn_replay_get_state(b200dqn_replay* r, int64_t index, uint8_t* host_out
  * the advanced state (synchronises) so the host can random.setstate() and stay in lock-step. */
 int b200dqn_replay_set_rng(b200dqn_replay* r, const uint32_t host_mt625[625], void* stream);
 int b200dqn_replay_get_rng(b200dqn_replay* r, uint32_t host_mt625[625], void* stream);
+/* set_rng without the stream synchronisation, key words and position passed separately (they are separate fields of
+ * CPython's generator object): staged through a small pinned ring, asynchronous. */
+int b200dqn_replay_set_rng_parts(b200dqn_replay* r, const uint32_t* host_key624, uint32_t host_pos, void* stream);
 
 /* The sampling loop of ReplayMemory.getMinibatch — src/replay_memory.py:55-69 — on the device:
  * draws py3 randint(hist, count-1) trials from the MT19937 stream, applies the two rejection
@@ -239,6 +242,17 @@ int b200dqn_net_train_sampled(b200dqn_net* n, b200dqn_replay* r, void* stream);
 /* Same, then copies cost[0,0] of this step to host_cost (4-byte D2H; synchronises) for the
  * `callback.on_train(cost)` of src/deepqnetwork.py:171-172. */
 int b200dqn_net_train_sampled_cost(b200dqn_net* n, b200dqn_replay* r, float* host_cost, void* stream);
+/* src/agent.py:102-114 as ONE call, for a caller that drives the loop itself (one host->device hop per train step):
+ *   nframes x ReplayMemory.add (the env steps since the last train; frames are (h,w) u8, back to back), then
+ *   train_repeat x (ReplayMemory.getMinibatch sampling + DeepQNetwork.train) as captured CUDA graphs.
+ * host_key624 != NULL: the caller drew from its `random` since the last call — the MT19937 state (624 key words,
+ * position) is adopted first.  host_costs (train_repeat floats) / host_words_consumed (MT words the samplings
+ * consumed, so the caller can advance its `random`) arrive through host-mapped memory written by the kernels: no
+ * memcpy, one wait.  Both NULL: the call is asynchronous.  train_repeat = 0 only appends the frames. */
+int b200dqn_net_step_host(b200dqn_net* n, b200dqn_replay* r, int nframes, const uint8_t* host_actions,
+                          const int64_t* host_rewards, const uint8_t* host_frames, const uint8_t* host_terminals,
+                          int train_repeat, const uint32_t* host_key624, uint32_t host_pos, float* host_costs,
+                          uint32_t* host_words_consumed, void* stream);
 /* The last `count` (<= 1024) per-step costs, oldest first.  Synchronises. */
 int b200dqn_net_read_costs(b200dqn_net* n, int count, float* host_costs, void* stream);
 /* train_iterations — src/deepqnetwork.py:168 */

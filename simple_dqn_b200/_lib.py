@@ -60,6 +60,7 @@ SIGNATURES = {
     "b200dqn_replay_get_state": [_P, C.c_int64, _P, _P],
     "b200dqn_replay_set_rng": [_P, _P, _P],
     "b200dqn_replay_get_rng": [_P, _P, _P],
+    "b200dqn_replay_set_rng_parts": [_P, _P, C.c_uint32, _P],
     "b200dqn_replay_sample": [_P, _P],
     "b200dqn_replay_sample_sync": [_P, _u32p, _P],
     "b200dqn_replay_set_indexes": [_P, _P, _P],
@@ -89,6 +90,7 @@ SIGNATURES = {
     "b200dqn_net_train_sampled": [_P, _P, _P],
     "b200dqn_net_train_sampled_cost": [_P, _P, _f32p, _P],
     "b200dqn_net_train_fused": [_P, _P, C.c_int, _P],
+    "b200dqn_net_step_host": [_P, _P, C.c_int, _P, _P, _P, _P, C.c_int, _P, C.c_uint32, _P, _P, _P],
     "b200dqn_net_read_costs": [_P, C.c_int, _P, _P],
     "b200dqn_net_train_iterations": [_P, _i64p],
     "b200dqn_net_device_ptr": [_P, C.c_int, C.POINTER(_P), C.POINTER(C.c_size_t)],

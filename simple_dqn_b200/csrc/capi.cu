@@ -13,6 +13,26 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+int poll_mapped_seq(const volatile uint32_t* seq, uint32_t want, cudaStream_t st, const char* what) {
+  for (uint32_t spins = 1;; ++spins) {
+    if (int32_t(*seq - want) >= 0) return B200DQN_OK;
+    if ((spins & 0x3ffu) == 0) {
+      const cudaError_t e = cudaStreamQuery(st);
+      if (e == cudaSuccess) {              // the stream has drained: the value is there now or will never be
+        if (int32_t(*seq - want) >= 0) return B200DQN_OK;
+        B2_REQUIRE(false, B200DQN_ESTATE, "%s: the stream finished without publishing result %u (have %u)", what, want, *seq);
+      }
+      if (e != cudaErrorNotReady) {
+        set_error("%s: %s", what, cudaGetErrorString(e));
+        return B200DQN_ECUDA;
+      }
+    }
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#endif
+  }
+}
+
 bool g_prof_on = false;
 bool g_use_pdl = getenv("B200DQN_NO_PDL") == nullptr;
 thread_local bool g_pdl_suppressed = false;

@@ -45,6 +45,12 @@ struct DeviceGuard {
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// Results the host waits for (cost of a train step, MT words a sampling consumed) are written by the producing
+// kernel straight into host-mapped pinned memory: [0] = a sequence number published last (after a system fence).
+// The host polls that word — no memcpy, no cudaStreamSynchronize — and checks the stream every ~1k spins so that a
+// failed launch turns into an error instead of a spin forever.
+int poll_mapped_seq(const volatile uint32_t* seq, uint32_t want, cudaStream_t st, const char* what);
+
 // Per-launch CUDA-event profiler (b200dqn_profile_begin/_end): when armed, every launch site
 // drops an event on its stream right after the kernel, labelled with the kernel's role.
 void prof_mark(const char* label, cudaStream_t st);

@@ -14,12 +14,13 @@ namespace b200 {
 
 // ------------------------------------------------------------------------------------------
 // K2e + K3 + K4a/K5a ("head"): finish fc1 (sum split-K partials, Rectlin), run fc2 (Affine
-// nout=A, no activation) for both networks, and — in the last CTA to finish (ticket counter) —
-// the TD target / delta / cost / clip of src/deepqnetwork.py:124-159 and the fc2 backward:
+// nout=A, no activation) for both networks of ONE sample per CTA, then — same CTA, no inter-CTA
+// hand-off — the TD target / delta / cost / clip of src/deepqnetwork.py:124-159 and the fc2 backward:
 //   dZ4[b][k] = (sum_a delta[b][a] W5[k][a]) * (H4[b][k] > 0),  dW5[k][a] = sum_b H4[b][k] delta[b][a].
 // The reference forms the target on the host in Python floats (double) and stores it into a
-// float32 array; we do the same arithmetic in fp64 and round once.  cost is the batch mean of
-// 0.5*sum_a delta^2 BEFORE the clip.  grid = (rows, nets), block = 512 (one thread per hidden unit).
+// float32 array; we do the same arithmetic in fp64 and round once.  The per-sample cost
+// 0.5*sum_a delta^2 (BEFORE the clip) goes to row_cost; the batch mean is formed off the critical
+// chain by k_cost_finish.  grid = rows, block = 512 (one thread per hidden unit).
 // ------------------------------------------------------------------------------------------
 struct HeadTrainArgs {
   int enable;
@@ -31,9 +32,7 @@ struct HeadTrainArgs {
   int min_reward, max_reward;
   float clip;
   float* delta;       // [rows][A]
-  float* cost_ring;
-  uint32_t* step;
-  uint32_t* ticket;   // [rows + 1]: per-row pair tickets, then the all-rows ticket
+  const uint32_t* step;   // completed train steps (k_cost_finish increments it)
   float* row_cost;    // [rows]
   float* dz4;         // [rows][512]
   float* dw5_rows;    // [rows][512][A] per-row partials of dW5 (summed in row order by the optimizer)
@@ -46,17 +45,17 @@ struct HeadTrainArgs {
 };
 
 __global__ void __launch_bounds__(kHidden)
-k_head(const float* __restrict__ part, int splits, int rows, float* h4_online, float* h4_target,
+k_head(const float* __restrict__ part, int splits, int rows, int nets, float* h4_online, float* h4_target,
        const float* __restrict__ w5_online, const float* __restrict__ w5_target, float* q_online,
        float* q_target, int A, const HeadTrainArgs td, const KTrace kt) {
-  __shared__ float red[kHidden / 32][kMaxActions];
-  __shared__ int s_last;
-  const int b = blockIdx.x, z = blockIdx.y, t = threadIdx.x;
+  __shared__ float red[2][kHidden / 32][kMaxActions];
+  __shared__ float s_q[2][kMaxActions];
+  __shared__ float s_d;
+  __shared__ int s_a;
+  const int b = blockIdx.x, t = threadIdx.x;
   kt_begin(kt);
-  pdl_wait();
-  pdl_launch_dependents();
-  // the TD scalars of this sample do not depend on the forward pass: fetch them now (thread 0), so the
-  // dependent index -> action/reward/terminal loads are off the tail of the kernel
+  // The TD scalars of this sample depend only on the sampler (several kernels upstream, complete by now):
+  // fetch them before the dependency wait, off the tail of the kernel.
   int td_a = 0, td_term = 0;
   int64_t td_r = 0;
   if (td.enable && t == 0) {
@@ -69,51 +68,59 @@ k_head(const float* __restrict__ part, int splits, int rows, float* h4_online, f
       td_a = td.num_actions - 1;
     }
   }
-  if (td.enable && td.adam_l && b == 0 && z == 0 && t == 32) {
+  if (td.enable && td.adam_l && b == 0 && t == 32) {
     // Adam.optimize: self.t += 1;  l = lr * sqrt(1 - beta_2**t) / (1 - beta_1**t)  (Python doubles, fp32 tensor ops)
     const double tt = double(*td.step) + 1.0;
     const float a = float(1.0 - pow(0.999, tt)), c = float(1.0 - pow(0.9, tt));
     *td.adam_l = __fdiv_rn(__fmul_rn(td.adam_lr, __fsqrt_rn(a)), c);
   }
-  float h = 0.f;
-  for (int s = 0; s < splits; ++s) h += part[((z * splits + s) * rows + b) * kHidden + t];
-  h = fmaxf(h, 0.f);
-  (z ? h4_target : h4_online)[b * kHidden + t] = h;
-  const float* w5 = z ? w5_target : w5_online;
-  for (int a = 0; a < A; ++a) {
-    float v = h * w5[t * A + a];
+  pdl_wait();
+  pdl_launch_dependents();
+  float h[2] = {0.f, 0.f};
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if ((t & 31) == 0) red[t >> 5][a] = v;
+  for (int z = 0; z < 2; ++z) {
+    if (z < nets) {
+      float acc = 0.f;
+      for (int s = 0; s < splits; ++s) acc += part[((z * splits + s) * rows + b) * kHidden + t];
+      h[z] = fmaxf(acc, 0.f);
+      (z ? h4_target : h4_online)[b * kHidden + t] = h[z];
+    }
+  }
+#pragma unroll
+  for (int z = 0; z < 2; ++z) {
+    if (z < nets) {
+      const float* w5 = z ? w5_target : w5_online;
+      for (int a = 0; a < A; ++a) {
+        float v = h[z] * w5[t * A + a];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((t & 31) == 0) red[z][t >> 5][a] = v;
+      }
+    }
   }
   __syncthreads();
-  if (t < A) {
+  if (t < nets * A) {
+    const int z = t / A, a = t % A;
     float v = 0.f;
 #pragma unroll
-    for (int wI = 0; wI < kHidden / 32; ++wI) v += red[wI][t];
-    (z ? q_target : q_online)[b * A + t] = v;
+    for (int wI = 0; wI < kHidden / 32; ++wI) v += red[z][wI][a];
+    (z ? q_target : q_online)[b * A + a] = v;
+    s_q[z][a] = v;
   }
-  kt_end(kt);
-  if (!td.enable) return;
-
-  // ---- the second CTA of the (online, target) pair of row b to get here owns that row's TD + fc2 backward
-  __threadfence();
+  if (!td.enable) {
+    kt_end(kt);
+    return;
+  }
   __syncthreads();
-  if (t == 0) s_last = (atomicAdd(td.ticket + b, 1u) == gridDim.y - 1) ? 1 : 0;
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  __shared__ float s_d;
-  __shared__ int s_a;
   if (t == 0) {
     const int a = td_a;
     int64_t r = td_r;
     r = r < td.min_reward ? td.min_reward : (r > td.max_reward ? td.max_reward : r);     // np.clip (:136)
-    float maxq = __ldcg(q_target + b * A);
-    for (int j = 1; j < A; ++j) maxq = fmaxf(maxq, __ldcg(q_target + b * A + j));        // be.max(postq) (:124)
+    float maxq = s_q[1][0];
+    for (int j = 1; j < A; ++j) maxq = fmaxf(maxq, s_q[1][j]);                            // be.max(postq) (:124)
     const double y = td_term ? double(r) : double(r) + td.discount * double(maxq);          // :140-143
     const float target = static_cast<float>(y);
-    float d = __ldcg(q_online + b * A + a) - target;                                      // SumSquared grad (:149)
+    float d = s_q[0][a] - target;                                                         // SumSquared grad (:149)
     td.row_cost[b] = 0.5f * d * d;                                                        // :154, before the clip
     if (td.clip > 0.f) d = fminf(fmaxf(d, -td.clip), td.clip);                            // :158-159
     for (int j = 0; j < A; ++j) td.delta[b * A + j] = (j == a) ? d : 0.f;
@@ -124,7 +131,7 @@ k_head(const float* __restrict__ part, int splits, int rows, float* h4_online, f
   {
     const float d = s_d;
     const int a = s_a;
-    const float hv = __ldcg(h4_online + b * kHidden + t);
+    const float hv = h[0];
     const float o = hv > 0.f ? d * w5_online[t * A + a] : 0.f;      // delta is non-zero only at the taken action
     td.dz4[b * kHidden + t] = o;
     if (td.dz4_hi) {
@@ -136,26 +143,73 @@ k_head(const float* __restrict__ part, int splits, int rows, float* h4_online, f
     for (int j = 0; j < A; ++j) dw[j] = (j == a) ? hv * d : 0.f;
   }
   kt_end(kt);
-  // ---- the last row to finish publishes the batch-mean cost and re-arms the tickets
-  __threadfence();
-  __syncthreads();
-  if (t == 0) s_last = (atomicAdd(td.ticket + rows, 1u) == uint32_t(rows) - 1) ? 1 : 0;
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  // batch cost: all loads in flight at once, then summed in row order by one thread (deterministic)
-  const bool staged = rows <= kHidden;
-  if (staged && t < rows) red[t >> 5][t & 31] = __ldcg(td.row_cost + t);
-  __syncthreads();
-  if (t == 0) {
-    float tot = 0.f;
-    for (int bb = 0; bb < rows; ++bb) tot += staged ? red[bb >> 5][bb & 31] : __ldcg(td.row_cost + bb);
-    const uint32_t sidx = *td.step;
-    td.cost_ring[sidx % kCostRing] = tot / float(rows);
-    td.cost_ring[kCostRing] = tot / float(rows);   // "latest" slot: one 4-byte read for the stats callback
-    *td.step = sidx + 1;
+}
+
+// cost = mean over the batch of the per-sample costs (GeneralizedCost.get_cost, src/deepqnetwork.py:154), summed in
+// row order by one thread (deterministic); advances the cost ring and the step counter.  Runs off the critical
+// chain (the stream of the fc2 optimizer): nothing on the device waits for the scalar.
+__global__ void __launch_bounds__(256)
+k_cost_finish(const float* __restrict__ row_cost, int rows, float* cost_ring, uint32_t* step,
+              volatile uint32_t* host_res, const KTrace kt) {
+  __shared__ float s_c[1024];
+  kt_begin(kt);
+  float tot = 0.f;
+  for (int base = 0; base < rows; base += 1024) {
+    const int n = min(1024, rows - base);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s_c[i] = row_cost[base + i];
+    __syncthreads();
+    if (threadIdx.x == 0)
+      for (int i = 0; i < n; ++i) tot += s_c[i];
+    __syncthreads();
   }
-  for (int i = t; i <= rows; i += kHidden) td.ticket[i] = 0;
+  if (threadIdx.x == 0) {
+    const uint32_t sidx = *step;
+    const float cost = tot / float(rows);
+    cost_ring[sidx % kCostRing] = cost;
+    cost_ring[kCostRing] = cost;   // "latest" slot
+    *step = sidx + 1;
+    if (host_res) {                // the host polls [0]: data first, system fence, then the sequence number
+      host_res[4 + sidx % kHostCosts] = __float_as_uint(cost);
+      host_res[1] = __float_as_uint(cost_ring[kCostRing + 1]);   // action-range flag word
+      __threadfence_system();
+      host_res[0] = sidx + 1;
+    }
+  }
+  kt_end(kt);
+}
+
+// Small-layer optimizer without tile images (fc2: 512 x A parameters, CUDA-core layer): 8 lanes per float4 sum the
+// split partials (lane l takes partials l, l+8, ... in order; fixed xor tree across lanes — the summation order of
+// k_optimizer, bit-identical) and lane 0 applies the configured update.
+__global__ void __launch_bounds__(256)
+k_opt_small(const float* __restrict__ part, int splits, int64_t size, float* __restrict__ w, float* __restrict__ sst,
+            const OptArgs opt, const KTrace kt) {
+  kt_begin(kt);
+  pdl_wait();
+  pdl_launch_dependents();
+  const int tid = threadIdx.x, lane8 = tid & 7;
+  const int64_t i = (int64_t(blockIdx.x) * 32 + (tid >> 3)) * 4;
+  const bool live = i < size;
+  float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (live) {
+    const float* p = part + i;
+#pragma unroll 4
+    for (int sp = lane8; sp < splits; sp += 8) {
+      const float4 v = *reinterpret_cast<const float4*>(p + int64_t(sp) * size);
+      g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w;
+    }
+  }
+#pragma unroll
+  for (int o = 1; o < 8; o <<= 1) {
+    g.x += __shfl_xor_sync(0xffffffffu, g.x, o);
+    g.y += __shfl_xor_sync(0xffffffffu, g.y, o);
+    g.z += __shfl_xor_sync(0xffffffffu, g.z, o);
+    g.w += __shfl_xor_sync(0xffffffffu, g.w, o);
+  }
+  if (live && lane8 == 0) {
+    float nw[4];
+    opt_update_vec<4>(opt, opt_step_scalar(opt), reinterpret_cast<const float*>(&g), nw, w + i, sst + i);
+  }
   kt_end(kt);
 }
 
@@ -291,7 +345,7 @@ static int forward(b200dqn_net* n, const FrameSource& fs, int nets, int rows, cu
     }
   }
   const int fc1_splits = n->cfg.math_mode == B200DQN_MATH_TCGEN05 ? umma_fc1_splits() : kFc1Splits;
-  B2_CHECK_CUDA(launch_pdl(k_head, dim3(rows, nets), dim3(kHidden), 0, st, (const float*)n->d_fc1part, fc1_splits, rows,
+  B2_CHECK_CUDA(launch_pdl(k_head, dim3(rows), dim3(kHidden), 0, st, (const float*)n->d_fc1part, fc1_splits, rows, nets,
                            n->d_h4[0], n->d_h4[1], w[0] + lt.off[4], w[1] + lt.off[4], n->d_q[0], n->d_q[1], n->A,
                            td, ktrace_slot("head")));
   B2_PROF(td.enable ? "head(fc2+td+fc2_bwd)" : "fc2_fwd", st);
@@ -379,6 +433,26 @@ static int optimizer_range(b200dqn_net* n, int l0, int l1, int mode, int rows, c
   return B200DQN_OK;
 }
 
+// batch-mean cost -> cost ring, step counter + 1 (once per train step, after the head, on any stream behind it)
+static int cost_finish_on(b200dqn_net* n, int rows, cudaStream_t s) {
+  NoPdlScope plain;
+  B2_CHECK_CUDA(launch_pdl(k_cost_finish, dim3(1), dim3(256), 0, s, (const float*)n->d_rowcost, rows, n->d_cost, n->d_step,
+                           n->h_res, ktrace_slot("cost")));
+  B2_PROF("cost", s);
+  return B200DQN_OK;
+}
+
+// fc2 update from the head's per-row partials (single-GPU schedules): 8-lane reduction, no image
+static int opt_fc2_small(b200dqn_net* n, int rows, cudaStream_t s) {
+  const LayerTable& lt = n->lt;
+  const int64_t size = lt.off[5] - lt.off[4];
+  B2_CHECK_CUDA(launch_pdl(k_opt_small, dim3(cdiv(size / 4, 32)), dim3(256), 0, s, (const float*)n->d_part + lt.part_off[4],
+                           lt.splits[4], size, n->d_w + lt.off[4], n->d_s + lt.off[4], make_opt_args(n, rows),
+                           ktrace_slot("opt_fc2")));
+  B2_PROF("opt_fc2", s);
+  return B200DQN_OK;
+}
+
 #define B2_TRY(expr)          \
   do {                        \
     int rc__ = (expr);        \
@@ -414,6 +488,7 @@ static int backward_and_update_xchg(b200dqn_net* n, const FrameSource& fs, int r
   {
     NoPdlScope side;
     B2_TRY(bwd_op(n, fs, rows, kFc1Wgrad, sA));
+    B2_TRY(cost_finish_on(n, rows, sA));
     B2_TRY(optimizer_range(n, 3, 4, 1 | 2, rows, sA, "reduce_fc"));
     B2_TRY(comm_xchg_range(n, 3, 4, 3, sA, "xchg_fc"));
   }
@@ -482,6 +557,7 @@ static int backward_and_update_gather(b200dqn_net* n, const FrameSource& fs, int
     B2_TRY(umma_fc1_wgrad_gathered(n, sA));
     // fc2 (8 KB) on the stream the H3 push has left idle: nothing later in the step reads W5
     B2_CHECK_CUDA(cudaStreamWaitEvent(sN, ev[0], 0));
+    B2_TRY(cost_finish_on(n, rows, sN));
     B2_TRY(optimizer_range(n, 4, 4, 1 | 2, rows, sN, "reduce_fc2"));
     B2_TRY(comm_xll_layer(n, 4, sN, "xll_fc2"));
     B2_TRY(optimizer_range(n, 4, 4, 4, rows, sN, "opt_fc2"));
@@ -553,6 +629,7 @@ static int backward_and_update_multi(b200dqn_net* n, const FrameSource& fs, int 
   {
     NoPdlScope side;
     B2_TRY(bwd_op(n, fs, rows, kFc1Wgrad, sA));
+    B2_TRY(cost_finish_on(n, rows, sA));
     B2_TRY(optimizer_range(n, 3, 4, 1 | 2, rows, sA, "reduce_fc"));        // partials -> d_g[fc1, fc2]
     B2_CHECK_CUDA(cudaEventRecord(ev[7], sA));
     B2_CHECK_CUDA(cudaStreamWaitEvent(sN, ev[7], 0));
@@ -616,6 +693,7 @@ static int backward_and_update(b200dqn_net* n, const FrameSource& fs, int rows, 
   const bool branches = update && n->world == 1 && n->use_branches && (st != nullptr || g_prof_on);
   if (!branches) {
     for (int op = kFc1Wgrad; op <= kConv1Wgrad; ++op) B2_TRY(bwd_op(n, fs, rows, BwdOp(op), st));
+    B2_TRY(cost_finish_on(n, rows, st));
     if (!update) return B200DQN_OK;
     if (n->world > 1) {
       B2_TRY(optimizer_range(n, 0, kLayers - 1, 1 | 2, rows, st, "grad_reduce"));
@@ -628,15 +706,20 @@ static int backward_and_update(b200dqn_net* n, const FrameSource& fs, int rows, 
     return B200DQN_OK;
   }
   cudaStream_t sA = g_prof_on ? st : n->side[0], sB = g_prof_on ? st : n->side[1], sC = g_prof_on ? st : n->side[2];
+  cudaStream_t sN = g_prof_on ? st : n->side[3];
   cudaEvent_t* ev = n->ev;
   const bool tc = n->cfg.math_mode == B200DQN_MATH_TCGEN05;
   static const bool fc1_fused_epilogue = getenv("B200DQN_FC1_FUSED") != nullptr;   // experimental alternative
-  B2_CHECK_CUDA(cudaEventRecord(ev[0], st));                 // dZ4 and the dW5 partials are ready
+  B2_CHECK_CUDA(cudaEventRecord(ev[0], st));                 // dZ4, the dW5 partials and the per-sample costs are ready
   B2_CHECK_CUDA(cudaStreamWaitEvent(sA, ev[0], 0));
+  B2_CHECK_CUDA(cudaStreamWaitEvent(sN, ev[0], 0));
   {
     NoPdlScope side;
     if (!(tc && fc1_fused_epilogue)) B2_TRY(bwd_op(n, fs, rows, kFc1Wgrad, sA));   // overlaps fc1_dgrad (few CTAs)
-    if (tc) B2_TRY(optimizer_range(n, 4, 4, 1 | 4, rows, sA, "opt_fc2"));          // tiny; must not delay the wgrad
+    // fourth branch: the scalar cost and the 512 x A layer — nothing later in the step reads W5, and nothing here
+    // sits in front of the fc1 optimizer any more
+    B2_TRY(cost_finish_on(n, rows, sN));
+    if (tc) B2_TRY(opt_fc2_small(n, rows, sN));
   }
   B2_TRY(bwd_op(n, fs, rows, kFc1Dgrad, st));
   B2_CHECK_CUDA(cudaEventRecord(ev[1], st));                 // dZ3 ready, W4 no longer needed
@@ -673,9 +756,11 @@ static int backward_and_update(b200dqn_net* n, const FrameSource& fs, int rows, 
   B2_CHECK_CUDA(cudaEventRecord(ev[4], sA));
   B2_CHECK_CUDA(cudaEventRecord(ev[5], sB));
   B2_CHECK_CUDA(cudaEventRecord(ev[6], sC));
+  B2_CHECK_CUDA(cudaEventRecord(ev[7], sN));
   B2_CHECK_CUDA(cudaStreamWaitEvent(st, ev[4], 0));
   B2_CHECK_CUDA(cudaStreamWaitEvent(st, ev[5], 0));
   B2_CHECK_CUDA(cudaStreamWaitEvent(st, ev[6], 0));
+  B2_CHECK_CUDA(cudaStreamWaitEvent(st, ev[7], 0));
   return B200DQN_OK;
 }
 
@@ -684,7 +769,7 @@ static int train_step(b200dqn_net* n, const FrameSource& fs, const uint8_t* acti
                       const uint8_t* terminals, const int32_t* midx, cudaStream_t st) {
   const int rows = n->nb;
   HeadTrainArgs td{1, actions, rewards, terminals, midx, n->cfg.discount_rate, n->cfg.min_reward, n->cfg.max_reward,
-                   float(n->cfg.clip_error), n->d_delta, n->d_cost, n->d_step, n->d_ticket, n->d_rowcost, n->d_dz4,
+                   float(n->cfg.clip_error), n->d_delta, n->d_step, n->d_rowcost, n->d_dz4,
                    n->d_part + n->lt.part_off[4], nullptr, 0,
                    n->cfg.optimizer == B200DQN_OPT_ADAM ? n->d_optscal : nullptr, float(n->cfg.learning_rate), n->A,
                    reinterpret_cast<uint32_t*>(n->d_cost + kCostRing + 1)};
@@ -834,8 +919,6 @@ extern "C" int b200dqn_net_create(int device, const b200dqn_net_config* cfg, b20
   B2_CHECK_CUDA(fmalloc(&n->d_cost, kCostRing + 2));   // ring, "latest" slot, action-range flag word
   B2_CHECK_CUDA(cudaMalloc(&n->d_step, sizeof(uint32_t)));
   B2_CHECK_CUDA(cudaMemset(n->d_step, 0, sizeof(uint32_t)));
-  B2_CHECK_CUDA(cudaMalloc(&n->d_ticket, (nb + 1) * sizeof(uint32_t)));
-  B2_CHECK_CUDA(cudaMemset(n->d_ticket, 0, (nb + 1) * sizeof(uint32_t)));
   B2_CHECK_CUDA(fmalloc(&n->d_rowcost, nb));
   const size_t state_bytes = size_t(nb) * kHist * kFrameBytes;
   B2_CHECK_CUDA(cudaMalloc(&n->d_pre, state_bytes + 256));
@@ -849,6 +932,12 @@ extern "C" int b200dqn_net_create(int device, const b200dqn_net_config* cfg, b20
   B2_LAUNCH_CHECK();
   n->pin_bytes = 2 * state_bytes + size_t(nb) * 16 + size_t(nb) * A * sizeof(float) + 256;
   B2_CHECK_CUDA(cudaMallocHost(&n->h_pin, n->pin_bytes));
+  {
+    void* m = nullptr;
+    B2_CHECK_CUDA(cudaHostAlloc(&m, 256, cudaHostAllocMapped));
+    memset(m, 0, 256);
+    n->h_res = static_cast<volatile uint32_t*>(m);
+  }
   {
     int prio_lo = 0, prio_hi = 0;   // numerically larger = lower priority
     B2_CHECK_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
@@ -882,9 +971,10 @@ extern "C" int b200dqn_net_destroy(b200dqn_net* n) {
     cudaFree(n->d_h1[z]); cudaFree(n->d_h2[z]); cudaFree(n->d_h3[z]); cudaFree(n->d_h4[z]); cudaFree(n->d_q[z]);
   }
   cudaFree(n->d_fc1part); cudaFree(n->d_delta); cudaFree(n->d_dz4); cudaFree(n->d_dz3); cudaFree(n->d_dz2);
-  cudaFree(n->d_dz1); cudaFree(n->d_cost); cudaFree(n->d_step); cudaFree(n->d_ticket); cudaFree(n->d_rowcost); cudaFree(n->d_pre); cudaFree(n->d_post);
+  cudaFree(n->d_dz1); cudaFree(n->d_cost); cudaFree(n->d_step); cudaFree(n->d_rowcost); cudaFree(n->d_pre); cudaFree(n->d_post);
   cudaFree(n->d_act); cudaFree(n->d_term); cudaFree(n->d_rew); cudaFree(n->d_iota1); cudaFree(n->d_iota4);
   cudaFreeHost(n->h_pin);
+  cudaFreeHost(const_cast<uint32_t*>(n->h_res));
   delete n;
   return B200DQN_OK;
 }
@@ -1095,19 +1185,24 @@ extern "C" int b200dqn_net_train_sampled(b200dqn_net* n, b200dqn_replay* r, void
   return B200DQN_OK;
 }
 
+// wait for train step number `want` (1-based count of steps run by this net) and fetch its cost from the mapped block
+static int wait_step_cost(b200dqn_net* n, cudaStream_t st, uint32_t want, float* cost) {
+  int rc = poll_mapped_seq(n->h_res, want, st, "train step result");
+  if (rc) return rc;
+  B2_REQUIRE(n->h_res[1] == 0, B200DQN_EINVAL,
+             "train: a sampled action is >= num_actions %d (IndexError at deepqnetwork.py:141 in the reference)", n->A);
+  if (cost) {
+    const uint32_t bits = n->h_res[4 + (want - 1) % kHostCosts];
+    memcpy(cost, &bits, sizeof(float));
+  }
+  return B200DQN_OK;
+}
+
 extern "C" int b200dqn_net_train_sampled_cost(b200dqn_net* n, b200dqn_replay* r, float* host_cost, void* stream) {
   B2_REQUIRE(host_cost, B200DQN_EINVAL, "net_train_sampled_cost: null argument");
   int rc = b200dqn_net_train_sampled(n, r, stream);
   if (rc) return rc;
-  DeviceGuard g(n->device);
-  cudaStream_t st = as_stream(stream);
-  float* pin = reinterpret_cast<float*>(n->h_pin);
-  B2_CHECK_CUDA(cudaMemcpyAsync(pin, n->d_cost + kCostRing, 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
-  B2_CHECK_CUDA(cudaStreamSynchronize(st));
-  *host_cost = pin[0];
-  B2_REQUIRE(reinterpret_cast<uint32_t*>(pin)[1] == 0, B200DQN_EINVAL,
-             "train: a sampled action is >= num_actions %d (IndexError at deepqnetwork.py:141 in the reference)", n->A);
-  return B200DQN_OK;
+  return wait_step_cost(n, as_stream(stream), uint32_t(n->train_iterations), host_cost);
 }
 
 extern "C" int b200dqn_net_train_fused(b200dqn_net* n, b200dqn_replay* r, int nsteps, void* stream) {
@@ -1156,6 +1251,50 @@ extern "C" int b200dqn_net_train_fused(b200dqn_net* n, b200dqn_replay* r, int ns
     }
   }
   n->train_iterations += nsteps;
+  r->samples_launched += uint32_t(nsteps);
+  return B200DQN_OK;
+}
+
+// agent.py:102-114 as ONE call (see include/b200dqn.h)
+extern "C" int b200dqn_net_step_host(b200dqn_net* n, b200dqn_replay* r, int nframes, const uint8_t* host_actions,
+                                     const int64_t* host_rewards, const uint8_t* host_frames,
+                                     const uint8_t* host_terminals, int train_repeat, const uint32_t* host_key624,
+                                     uint32_t host_pos, float* host_costs, uint32_t* host_words_consumed, void* stream) {
+  B2_REQUIRE(n && r && nframes >= 0 && train_repeat >= 0 && train_repeat <= kHostCosts, B200DQN_EINVAL,
+             "net_step_host: bad argument");
+  B2_REQUIRE(nframes == 0 || (host_actions && host_rewards && host_frames && host_terminals), B200DQN_EINVAL,
+             "net_step_host: null frame arrays");
+  for (int i = 0; i < nframes; ++i) {     // ReplayMemory.add x nframes (replay_memory.py:26-34): pinned bank, deferred
+    int rc = b200dqn_replay_add(r, host_actions[i], host_rewards[i], host_frames + size_t(i) * r->frame_bytes,
+                                host_terminals[i], stream);
+    if (rc) return rc;
+  }
+  if (train_repeat == 0) return B200DQN_OK;
+  DeviceGuard g(n->device);
+  cudaStream_t st = as_stream(stream);
+  int rc;
+  if (host_key624 && (rc = replay_set_rng_async(r, host_key624, host_pos, st))) return rc;   // the host stream moved
+  uint32_t words_before = 0;
+  if (host_words_consumed) {              // running totals: exact across several samplings, once earlier ones are in
+    if ((rc = replay_wait_words(r, st))) return rc;
+    words_before = r->h_words[2];
+  }
+  rc = b200dqn_net_train_fused(n, r, train_repeat, stream);
+  if (rc) return rc;
+  if (!host_costs && !host_words_consumed) return B200DQN_OK;      // asynchronous
+  float last = 0.f;
+  rc = wait_step_cost(n, st, uint32_t(n->train_iterations), &last);   // the last step's cost is published last
+  if (rc) return rc;
+  if (host_costs)
+    for (int i = 0; i < train_repeat; ++i) {
+      const uint32_t bits = n->h_res[4 + (uint32_t(n->train_iterations) - train_repeat + i) % kHostCosts];
+      memcpy(host_costs + i, &bits, sizeof(float));
+    }
+  if (host_words_consumed) {
+    rc = replay_wait_words(r, st);
+    if (rc) return rc;
+    *host_words_consumed = r->h_words[2] - words_before;   // running totals: exact across several samplings
+  }
   return B200DQN_OK;
 }
 

@@ -12,6 +12,7 @@ namespace b200 {
 constexpr int kLayers = 5;
 constexpr int kMaxActions = 32;
 constexpr int kCostRing = 1024;
+constexpr int kHostCosts = 60;            // per-step costs mirrored in host-mapped memory (a 256-byte block)
 constexpr int kFc1Splits = 14;            // 3136 / 14 = 224 = 14 * 16
 constexpr int kFc1Chunk = kFlat / kFc1Splits;
 
@@ -52,8 +53,10 @@ struct b200dqn_net {
   float* d_dz4 = nullptr, *d_dz3 = nullptr, *d_dz2 = nullptr, *d_dz1 = nullptr;
   float* d_cost = nullptr;     // cost ring [kCostRing]
   uint32_t* d_step = nullptr;  // device step counter (cost ring cursor)
-  uint32_t* d_ticket = nullptr;  // [nb + 1] tickets of the head kernel
   float* d_rowcost = nullptr;    // [nb] per-sample cost
+  // host-mapped result block written by k_cost_finish: [0] train steps completed (published last, after a system
+  // fence), [1] action-range flag, [4 + (step % kHostCosts)] cost of that step
+  volatile uint32_t* h_res = nullptr;
 
   // unfused-mode staging (host minibatch -> device)
   uint8_t* d_pre = nullptr, *d_post = nullptr, *d_act = nullptr, *d_term = nullptr;

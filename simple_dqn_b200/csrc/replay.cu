@@ -79,7 +79,7 @@ constexpr int kSampleThreads = 256;
 __global__ void __launch_bounds__(kSampleThreads, 1)
 k_sample(uint32_t* __restrict__ mt_state, const uint8_t* __restrict__ terminals,
          const int64_t* __restrict__ cursor, int hist, int batch, int32_t* __restrict__ idx_out,
-         uint32_t* __restrict__ words_out, const KTrace kt) {
+         uint32_t* __restrict__ words_out, volatile uint32_t* host_words, const KTrace kt) {
   __shared__ uint32_t mt[kMtN + 1];
   __shared__ int warp_cnt[kSampleThreads / 32];
   __shared__ int s_cut;
@@ -119,9 +119,10 @@ k_sample(uint32_t* __restrict__ mt_state, const uint8_t* __restrict__ terminals,
       if (r < n) {
         index = hist + static_cast<int>(r);
         ok = !(index >= current && index - hist < current);  // :61 wraps over the write pointer
-        if (ok) {
-          for (int j = 1; j <= hist; ++j) ok = ok && (terminals[index - j] == 0);  // :65 episode end
-        }
+        // :65 episode end — all `hist` bytes are requested at once (no short-circuit: one memory latency, not four)
+        unsigned any = 0;
+        for (int j = 1; j <= hist; ++j) any |= terminals[index - j];
+        ok = ok && any == 0;
       }
     }
     const unsigned ballot = __ballot_sync(0xffffffffu, ok);
@@ -158,7 +159,16 @@ k_sample(uint32_t* __restrict__ mt_state, const uint8_t* __restrict__ terminals,
   for (int i = tid; i < kMtN + 1; i += kSampleThreads) mt_state[i] = mt[i];
   if (tid == 0) {
     words_out[0] = words;
-    words_out[1] += words;
+    const uint32_t total = words_out[1] + words;
+    words_out[1] = total;
+    if (host_words) {             // host-mapped mirror: data, system fence, then the sequence number
+      const uint32_t seq = words_out[2] + 1;   // samplings completed (device-resident counter: no PCIe read)
+      words_out[2] = seq;
+      host_words[1] = words;
+      host_words[2] = total;
+      __threadfence_system();
+      host_words[0] = seq;
+    }
   }
   kt_end(kt);
 }
@@ -184,11 +194,31 @@ int replay_flush(b200dqn_replay* r, cudaStream_t st) {
   return B200DQN_OK;
 }
 
+// wait (polling host-mapped memory) until every sampler launched so far has published its word count
+int replay_wait_words(b200dqn_replay* r, cudaStream_t st) {
+  return poll_mapped_seq(r->h_words, r->samples_launched, st, "sampler result");
+}
+
+int replay_set_rng_async(b200dqn_replay* r, const uint32_t* key624, uint32_t pos, cudaStream_t st) {
+  B2_REQUIRE(pos <= 624, B200DQN_EINVAL, "MT19937 position %u > 624", pos);
+  const int slot = r->mt_slot;
+  r->mt_slot = (slot + 1) % b200dqn_replay::kMtSlots;
+  B2_CHECK_CUDA(cudaEventSynchronize(r->mt_done[slot]));   // the copy that last used this slot (long finished)
+  uint32_t* pin = r->h_mt + size_t(slot) * 640;
+  memcpy(pin, key624, 624 * sizeof(uint32_t));
+  pin[624] = pos;
+  B2_CHECK_CUDA(cudaMemcpyAsync(r->d_mt, pin, 625 * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+  B2_CHECK_CUDA(cudaEventRecord(r->mt_done[slot], st));
+  r->rng_set = true;
+  return B200DQN_OK;
+}
+
 int launch_sample(b200dqn_replay* r, cudaStream_t st) {
   int frc = replay_flush(r, st);
   if (frc) return frc;
   B2_CHECK_CUDA(launch_pdl(k_sample, dim3(1), dim3(kSampleThreads), 0, st, r->d_mt, (const uint8_t*)r->d_terminals,
-                           (const int64_t*)r->d_cursor, r->hist, r->batch, r->d_idx, r->d_words, ktrace_slot("sample")));
+                           (const int64_t*)r->d_cursor, r->hist, r->batch, r->d_idx, r->d_words, r->h_words,
+                           ktrace_slot("sample")));
   B2_PROF("sample", st);
   return B200DQN_OK;
 }
@@ -260,6 +290,9 @@ extern "C" int b200dqn_replay_create(int device, int64_t size, int screen_h, int
   B2_REQUIRE(out && size > 0 && screen_h > 0 && screen_w > 0 && history_length > 0 && batch_size > 0,
              B200DQN_EINVAL, "replay_create: bad argument");
   B2_REQUIRE(size < (int64_t(1) << 31), B200DQN_EINVAL, "replay_create: size must fit int32 indexes");
+  B2_REQUIRE(size >= b200dqn_replay::kPend, B200DQN_EINVAL,
+             "replay_create: size %lld is smaller than the %d-frame ingestion bank (a deferred flush may wrap at most once)",
+             (long long)size, b200dqn_replay::kPend);
   DeviceGuard g(device);
   auto* r = new (std::nothrow) b200dqn_replay();
   B2_REQUIRE(r, B200DQN_EINVAL, "out of host memory");
@@ -279,7 +312,7 @@ extern "C" int b200dqn_replay_create(int device, int64_t size, int screen_h, int
   B2_CHECK_CUDA(cudaMalloc(&r->d_cursor, 2 * sizeof(int64_t)));
   B2_CHECK_CUDA(cudaMalloc(&r->d_mt, 625 * sizeof(uint32_t)));
   B2_CHECK_CUDA(cudaMalloc(&r->d_idx, batch_size * sizeof(int32_t)));
-  B2_CHECK_CUDA(cudaMalloc(&r->d_words, 2 * sizeof(uint32_t)));
+  B2_CHECK_CUDA(cudaMalloc(&r->d_words, 4 * sizeof(uint32_t)));
   B2_CHECK_CUDA(cudaMalloc(&r->d_pre, state_bytes));
   B2_CHECK_CUDA(cudaMalloc(&r->d_post, state_bytes));
   B2_CHECK_CUDA(cudaMalloc(&r->d_mb_actions, batch_size));
@@ -293,8 +326,16 @@ extern "C" int b200dqn_replay_create(int device, int64_t size, int screen_h, int
   B2_CHECK_CUDA(cudaMemset(r->d_cursor, 0, 2 * sizeof(int64_t)));
   B2_CHECK_CUDA(cudaMemset(r->d_mt, 0, 625 * sizeof(uint32_t)));
   B2_CHECK_CUDA(cudaMemset(r->d_idx, 0, batch_size * sizeof(int32_t)));
-  B2_CHECK_CUDA(cudaMemset(r->d_words, 0, 2 * sizeof(uint32_t)));
+  B2_CHECK_CUDA(cudaMemset(r->d_words, 0, 4 * sizeof(uint32_t)));
   B2_CHECK_CUDA(cudaMallocHost(&r->h_stage, size_t(b200dqn_replay::kSlots) * r->frame_bytes));
+  B2_CHECK_CUDA(cudaMallocHost(&r->h_mt, size_t(b200dqn_replay::kMtSlots) * 640 * sizeof(uint32_t)));
+  for (auto& e : r->mt_done) B2_CHECK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  {
+    void* m = nullptr;
+    B2_CHECK_CUDA(cudaHostAlloc(&m, 64, cudaHostAllocMapped));
+    memset(m, 0, 64);
+    r->h_words = static_cast<volatile uint32_t*>(m);
+  }
   for (int b = 0; b < 2; ++b) {
     B2_CHECK_CUDA(cudaMallocHost(&r->h_bank[b], size_t(b200dqn_replay::kPend) * (r->frame_bytes + 16)));
     B2_CHECK_CUDA(cudaEventCreateWithFlags(&r->bank_done[b], cudaEventDisableTiming));
@@ -316,6 +357,9 @@ extern "C" int b200dqn_replay_destroy(b200dqn_replay* r) {
   cudaFree(r->d_pre); cudaFree(r->d_post); cudaFree(r->d_mb_actions); cudaFree(r->d_mb_rewards);
   cudaFree(r->d_mb_terminals);
   cudaFreeHost(r->h_stage);
+  cudaFreeHost(const_cast<uint32_t*>(r->h_words));
+  cudaFreeHost(r->h_mt);
+  for (auto& e : r->mt_done) if (e) cudaEventDestroy(e);
   for (int b = 0; b < 2; ++b) { cudaFreeHost(r->h_bank[b]); if (r->bank_done[b]) cudaEventDestroy(r->bank_done[b]); }
   for (auto& e : r->slot_done) if (e) cudaEventDestroy(e);
   delete r;
@@ -421,6 +465,13 @@ extern "C" int b200dqn_replay_set_rng(b200dqn_replay* r, const uint32_t host_mt6
   return B200DQN_OK;
 }
 
+extern "C" int b200dqn_replay_set_rng_parts(b200dqn_replay* r, const uint32_t* host_key624, uint32_t host_pos,
+                                            void* stream) {
+  B2_REQUIRE(r && host_key624, B200DQN_EINVAL, "replay_set_rng_parts: null argument");
+  DeviceGuard g(r->device);
+  return replay_set_rng_async(r, host_key624, host_pos, as_stream(stream));
+}
+
 extern "C" int b200dqn_replay_get_rng(b200dqn_replay* r, uint32_t host_mt625[625], void* stream) {
   B2_REQUIRE(r && host_mt625, B200DQN_EINVAL, "replay_get_rng: null argument");
   DeviceGuard g(r->device);
@@ -436,20 +487,18 @@ extern "C" int b200dqn_replay_sample(b200dqn_replay* r, void* stream) {
              (long long)r->count, r->hist);  // :52
   B2_REQUIRE(r->rng_set, B200DQN_ESTATE, "replay_sample: call b200dqn_replay_set_rng first");
   DeviceGuard g(r->device);
-  return launch_sample(r, as_stream(stream));
+  int rc = launch_sample(r, as_stream(stream));
+  if (!rc) r->samples_launched += 1;
+  return rc;
 }
 
 extern "C" int b200dqn_replay_sample_sync(b200dqn_replay* r, uint32_t* host_words_consumed, void* stream) {
   B2_REQUIRE(host_words_consumed, B200DQN_EINVAL, "replay_sample_sync: null argument");
   int rc = b200dqn_replay_sample(r, stream);
   if (rc) return rc;
-  DeviceGuard g(r->device);
-  cudaStream_t st = as_stream(stream);
-  uint32_t* pin = reinterpret_cast<uint32_t*>(r->h_stage);   // slot 0 of the pinned block doubles as a 4-byte landing pad
-  B2_CHECK_CUDA(cudaEventSynchronize(r->slot_done[0]));
-  B2_CHECK_CUDA(cudaMemcpyAsync(pin, r->d_words, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-  B2_CHECK_CUDA(cudaStreamSynchronize(st));
-  *host_words_consumed = pin[0];
+  rc = replay_wait_words(r, as_stream(stream));
+  if (rc) return rc;
+  *host_words_consumed = r->h_words[1];
   return B200DQN_OK;
 }
 

@@ -19,6 +19,15 @@ struct b200dqn_replay {
   uint32_t* d_mt = nullptr;        // 624 key words + position (CPython random.getstate()[1])
   int32_t* d_idx = nullptr;        // [batch] accepted indexes, acceptance order
   uint32_t* d_words = nullptr;     // [0] words consumed by the last sample() call, [1] running total
+  // host-mapped mirror written by the sampler: [0] samplings completed (published last), [1] words of the last
+  // one, [2] running total
+  volatile uint32_t* h_words = nullptr;
+  uint32_t samples_launched = 0;   // host count of sampler launches (= the sequence number the next wait expects)
+  // pinned staging for asynchronous MT19937 state uploads (the host stream moved since the last sampling)
+  static constexpr int kMtSlots = 4;
+  uint32_t* h_mt = nullptr;        // [kMtSlots][640]
+  cudaEvent_t mt_done[kMtSlots] = {};
+  int mt_slot = 0;
   uint8_t* d_pre = nullptr;        // [batch][hist][h][w]
   uint8_t* d_post = nullptr;       // [batch][hist][h][w]
   uint8_t* d_mb_actions = nullptr;
@@ -61,4 +70,7 @@ namespace b200 {
 int launch_sample(b200dqn_replay* r, cudaStream_t st);
 // push the pending add()s to HBM (no-op when there are none); call before anything reads the ring
 int replay_flush(b200dqn_replay* r, cudaStream_t st);
+int replay_wait_words(b200dqn_replay* r, cudaStream_t st);
+// adopt a host MT19937 state (624 key words + position) without synchronising the stream
+int replay_set_rng_async(b200dqn_replay* r, const uint32_t* key624, uint32_t pos, cudaStream_t st);
 }  // namespace b200

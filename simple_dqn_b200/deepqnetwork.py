@@ -188,13 +188,31 @@ class DeepQNetwork:
     def train(self, minibatch, epoch=0):
         """deepqnetwork.py:107-172.  A pristine DeviceMinibatch is trained in place from the ring."""
         if isinstance(minibatch, DeviceMinibatch) and not minibatch.materialised:
-            if self.callback:
-                cost = C.c_float()
-                L.call("b200dqn_net_train_sampled_cost", self._h, minibatch._mem._h, C.byref(cost), self._stream)
+            minibatch._check_current()
+            mem = minibatch._mem
+            cost = C.c_float()
+            if not minibatch.sampled:
+                # the index draw rides in this step's graph: one launch, results through host-mapped memory
+                words = C.c_uint32()
+                lockstep = mem.rng_mode == "python"
+                key, pos = mem._host_upload_args() if lockstep else (None, 0)
+                if not lockstep and not mem._rng_on_device:
+                    mem.seed_device_rng()
+                want = lockstep or self.callback is not None
+                L.call("b200dqn_net_step_host", self._h, mem._h, 0, None, None, None, None, 1, key, pos,
+                       C.byref(cost) if want else None, C.byref(words) if lockstep else None, self._stream)
+                minibatch.sampled = True
+                if lockstep:
+                    mem._host_advance(words.value)
                 self.train_iterations += 1
-                self.callback.on_train(np.float32(cost.value))          # :171-172 (cost[0,0] is a numpy float32)
+                if self.callback:
+                    self.callback.on_train(np.float32(cost.value))      # :171-172 (cost[0,0] is a numpy float32)
+            elif self.callback:
+                L.call("b200dqn_net_train_sampled_cost", self._h, mem._h, C.byref(cost), self._stream)
+                self.train_iterations += 1
+                self.callback.on_train(np.float32(cost.value))          # :171-172
             else:
-                L.call("b200dqn_net_train_sampled", self._h, minibatch._mem._h, self._stream)
+                L.call("b200dqn_net_train_sampled", self._h, mem._h, self._stream)
                 self.train_iterations += 1
             return
         prestates, actions, rewards, poststates, terminals = minibatch
@@ -226,6 +244,7 @@ class DeepQNetwork:
         L.call("b200dqn_net_train_fused", self._h, mem._h, int(nsteps), self._stream)
         self.train_iterations += nsteps
         mem._sample_ticket += nsteps
+        mem._host_state_in_sync = None        # the device stream ran ahead of the host's `random`
 
     def last_costs(self, count=1):
         out = np.empty(count, dtype=np.float32)

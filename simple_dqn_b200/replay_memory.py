@@ -11,6 +11,54 @@ from . import _lib as L
 logger = logging.getLogger(__name__)
 
 
+class _HostMT:
+    """Direct view of the MT19937 state inside CPython's process-global generator (``random._inst``), so that the
+    per-step lock-step with the host stream costs a few word reads instead of two ``random.getstate()`` calls
+    (8 us each: they build a 625-int tuple).  CPython's ``RandomObject`` is ``{PyObject_HEAD; int index;
+    uint32_t state[624]}``; the layout is VERIFIED against ``getstate()`` before it is trusted — on any mismatch
+    ``probe()`` returns None and the portable getstate()/setstate() path is used."""
+
+    def __init__(self, base, off):
+        self._words = (C.c_uint32 * 625).from_address(base + off)      # [0] = index, [1..624] = key
+        self.key_ptr = C.c_void_p(base + off + 4)
+
+    @staticmethod
+    def probe():
+        inst = getattr(random, "_inst", None)
+        if inst is None or type(inst).__basicsize__ < 16 + 625 * 4:
+            return None
+        st = inst.getstate()
+        if st[0] != 3 or len(st[1]) != 625:
+            return None
+        key = st[1]
+        raw = (C.c_uint32 * (type(inst).__basicsize__ // 4)).from_address(id(inst))
+        for off_words in range(2, len(raw) - 625):
+            if raw[off_words] == key[624] and raw[off_words + 1] == key[0] and \
+                    list(raw[off_words + 1:off_words + 625]) == list(key[:624]):
+                return _HostMT(id(inst), off_words * 4)
+        return None
+
+    def pos(self):
+        return self._words[0]
+
+    def fingerprint(self):
+        w = self._words
+        return (w[0], w[1], w[2], w[312], w[624])
+
+
+_host_mt = False      # False = not probed yet, None = unavailable
+
+
+def host_mt():
+    global _host_mt
+    if _host_mt is False:
+        try:
+            _host_mt = _HostMT.probe()
+        except Exception:
+            _host_mt = None
+    return _host_mt
+
+
 class DeviceMinibatch(tuple):
     """What ``getMinibatch()`` returns in device mode: a 5-tuple
     ``(prestates, actions, rewards, poststates, terminals)`` like the reference's
@@ -18,17 +66,24 @@ class DeviceMinibatch(tuple):
     them (statistics.py:85 does; agent.py:112-114 does not).  ``DeepQNetwork.train`` recognises
     an untouched instance and trains straight from the ring."""
 
-    def __new__(cls, mem):
+    def __new__(cls, mem, sampled=True):
         self = super().__new__(cls, ())
         self._mem = mem
         self._host = None
         self._ticket = mem._sample_ticket
+        self.sampled = sampled       # False: the index draw itself is still pending (it rides in train()'s graph)
         return self
+
+    def _check_current(self):
+        assert self._ticket == self._mem._sample_ticket, \
+            "this minibatch was overwritten by a later getMinibatch() / set_indexes() / train_fused() before it was used"
 
     def _materialise(self):
         if self._host is None:
-            assert self._ticket == self._mem._sample_ticket, \
-                "this minibatch was overwritten by a later getMinibatch() before it was read"
+            self._check_current()
+            if not self.sampled:
+                self._mem._sample_now()
+                self.sampled = True
             self._host = self._mem._gather_to_host()
         return self._host
 
@@ -77,7 +132,8 @@ class ReplayMemory:
         self.prestates = np.empty((self.batch_size, self.history_length) + self.dims, dtype=np.uint8)
         self.poststates = np.empty((self.batch_size, self.history_length) + self.dims, dtype=np.uint8)
         self._rng_on_device = False
-        self._host_state_in_sync = None       # host `random` state known to equal the device stream
+        self._host_state_in_sync = None       # host `random` state (or its fingerprint) known to equal the device stream
+        self._mt = host_mt() if rng == "python" else None
         self._sample_ticket = 0
         self.last_indexes = None
         self.last_words_consumed = None
@@ -137,9 +193,10 @@ class ReplayMemory:
     # ---- reference methods
     def add(self, action, reward, screen, terminal):
         assert screen.shape == self.dims                               # :27
-        screen = np.ascontiguousarray(screen, dtype=np.uint8)
-        reward = int(np.int64(reward))                                 # rewards is an int64 array (:11)
-        L.call("b200dqn_replay_add", self._h, int(action), reward, L.np_ptr(screen), int(bool(terminal)),
+        if screen.dtype != np.uint8 or not screen.flags["C_CONTIGUOUS"]:
+            screen = np.ascontiguousarray(screen, dtype=np.uint8)
+        # rewards is an int64 array (:11): a float reward is truncated toward zero on store, as numpy does
+        L.call("b200dqn_replay_add", self._h, int(action), int(reward), screen.ctypes.data, 1 if terminal else 0,
                self._stream)
 
     def add_batch(self, actions, rewards, screens, terminals):
@@ -171,31 +228,56 @@ class ReplayMemory:
         key = np.array(st[1], dtype=np.uint32)
         L.call("b200dqn_replay_set_rng", self._h, L.np_ptr(key), self._stream)
         self._rng_on_device = True
+        self._host_state_in_sync = None       # the device stream no longer (provably) equals the global one
 
     def read_device_rng(self):
         key = np.empty(625, dtype=np.uint32)
         L.call("b200dqn_replay_get_rng", self._h, L.np_ptr(key), self._stream)
         return key
 
-    def sample(self):
-        """Enqueue the index draw of getMinibatch (:55-69); nothing comes back to the host."""
-        assert self.count > self.history_length                        # :52
+    # ---- lock-step with the process-global `random` (rng="python")
+    def _host_upload_args(self):
+        """(key pointer or None, position): what the device must adopt before its next draw — None when the host
+        stream has not moved since the device last matched it."""
+        mt = self._mt
+        if mt is not None:
+            if mt.fingerprint() == self._host_state_in_sync:
+                return None, 0
+            return mt.key_ptr, mt.pos()
+        st = random.getstate()[1]
+        if st == self._host_state_in_sync:
+            return None, 0
+        self._key_keepalive = np.array(st, dtype=np.uint32)
+        return L.np_ptr(self._key_keepalive), int(st[624])
+
+    def _host_advance(self, words):
+        """The device consumed `words` 32-bit outputs (one per trial of replay_memory.py:59): so does the host."""
+        grb = random.getrandbits
+        for _ in range(words):
+            grb(32)
+        self._host_state_in_sync = self._mt.fingerprint() if self._mt is not None else random.getstate()[1]
+        self._rng_on_device = True
+        self.last_words_consumed = words
+
+    def _sample_now(self):
         if self.rng_mode == "python":
-            # Lock-step with the process-global stream: upload the 625-word state only if somebody else
-            # drew from `random` since our last sample, and advance the host by exactly the number of
-            # 32-bit words the device consumed (every trial of replay_memory.py:59 costs one word).
-            if random.getstate()[1] != self._host_state_in_sync:
-                self.seed_device_rng(random)
+            key, pos = self._host_upload_args()
+            if key is not None:
+                L.call("b200dqn_replay_set_rng_parts", self._h, key, pos, self._stream)
             words = C.c_uint32()
             L.call("b200dqn_replay_sample_sync", self._h, C.byref(words), self._stream)
-            for _ in range(words.value):
-                random.getrandbits(32)
-            self._host_state_in_sync = random.getstate()[1]
-            self.last_words_consumed = words.value
+            self._host_advance(words.value)
         else:
             if not self._rng_on_device:
                 self.seed_device_rng(random)
             L.call("b200dqn_replay_sample", self._h, self._stream)
+
+    def sample(self):
+        """The index draw of getMinibatch (:55-69) on the device.  rng="python": in lock-step with the process-global
+        stream — its state is uploaded only if somebody else drew from `random` since our last sample, and the host
+        is advanced by exactly the number of 32-bit words the device consumed."""
+        assert self.count > self.history_length                        # :52
+        self._sample_now()
         self._sample_ticket += 1
 
     def set_indexes(self, indexes):
@@ -220,7 +302,12 @@ class ReplayMemory:
 
     def getMinibatch(self):
         # replay_memory.py:50-79
-        self.sample()
         if self.device_minibatch:
-            return DeviceMinibatch(self)
+            # agent.py:112-114 is `mb = mem.getMinibatch(); net.train(mb, epoch)` with nothing in between: hand out
+            # a handle and let the draw ride in train()'s graph (one launch, one wait per step).  Anything else that
+            # looks at the handle (statistics.py:85) triggers the draw on the spot.
+            assert self.count > self.history_length                    # :52
+            self._sample_ticket += 1
+            return DeviceMinibatch(self, sampled=False)
+        self.sample()
         return self._gather_to_host()

@@ -352,12 +352,12 @@ class LockstepNet:
         return q
 
     def train(self, minibatch, epoch):
-        pre, act, rew, post, term = minibatch           # materialises a device handle: the checker needs host copies
-        host = (np.array(pre), np.array(act), np.array(rew), np.array(post), np.array(term))
         box = []
         self.subject.callback = types.SimpleNamespace(on_train=box.append)
-        self.subject.train(minibatch, epoch)
+        self.subject.train(minibatch, epoch)            # first: a pristine device handle is trained in place from the ring
         self.subject.callback = None
+        pre, act, rew, post, term = minibatch           # now materialise it: the checker needs host copies
+        host = (np.array(pre), np.array(act), np.array(rew), np.array(post), np.array(term))
         ref = float(self.checker.train(host, epoch))
         self.since_sync += 1
         self.cost_err.append((self.since_sync, abs(float(box[0]) - ref) / max(abs(ref), 1e-30)))

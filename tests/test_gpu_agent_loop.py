@@ -13,8 +13,6 @@ src/statistics.py by tests/test_agent_loop.py.  What is asserted:
     trace equality between two fp32 implementations is not meaningful for this chaotic system — see LockstepNet);
     greedy actions may differ from the oracle's only inside the measured Q error band;
   * the Statistics pattern (statistics.py:83-90): validation prestates kept by reference and predicted later."""
-import random
-
 import numpy as np
 import pytest
 
@@ -58,10 +56,6 @@ def test_reference_loop_on_product_classes(name, mode):
     assert (tr["rewards"] == ref["rewards"]).all() and (tr["terminals"] == ref["terminals"]).all()
     assert tr["costs"].shape == ref["costs"].shape and tr["q_rows"].shape == ref["q_rows"].shape
     # random.random() is consumed identically, so the SAME steps are random / greedy; random ones match exactly
-    greedy_steps = []
-    rnd = random.Random(cfg.random_seed)
-    # (replaying the stream exactly would re-implement the loop; the stream-position CRCs above already pin it —
-    #  here: wherever the golden and the product agree on "this step drew randrange", the action is the same)
     same = tr["actions"] == ref["actions"]
     assert same[:cfg.random_steps].all()                                      # ε = 1: every action is random
     # ---- numbers: against the lock-step oracle

@@ -22,28 +22,49 @@ def _gpus():
         return 0
 
 
-def _run(env_extra, port):
+WORLDS = [w for w in (2, 4, 8) if w <= _gpus()] or [2]
+
+
+def _run(env_extra, port, world=2):
     env = dict(os.environ, **env_extra)
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
            "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tools", "mgpu_check.py")]
-    p = subprocess.run(cmd, env=env, cwd=ROOT, capture_output=True, text=True, timeout=240)
+    p = subprocess.run(cmd, env=env, cwd=ROOT, capture_output=True, text=True, timeout=420)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
     return p.stdout
 
 
 @pytest.mark.gpu
 @pytest.mark.skipif(_gpus() < 2, reason="needs two GPUs")
+@pytest.mark.parametrize("world", WORLDS)
 @pytest.mark.parametrize("env", [{}, {"B200DQN_FUSED_XLL": "1"}, {"B200DQN_P2P_SCHED": "layer"}, {"B200DQN_COMM": "nccl"}],
                          ids=["p2p-gather", "p2p-gather-fused-conv-exchange", "p2p-two-shot", "nccl"])
-def test_ranks_stay_identical(env):
-    out = _run(env, 29610)
+def test_ranks_stay_identical(env, world):
+    out = _run(env, 29610 + world, world)
     assert "ranks diverged" not in out
     crcs = re.findall(r"weights crc32 ([0-9a-f]{8})", out)
-    assert len(crcs) == 2 and crcs[0] == crcs[1], crcs
+    assert len(crcs) == world and len(set(crcs)) == 1, crcs
     status = re.findall(r"comm status after run: \('(\w+)', (True|False)\)", out)
     assert status and all(ok == "True" for _, ok in status), status
     want = "nccl" if env.get("B200DQN_COMM") == "nccl" else "p2p"
     assert all(mode == want for mode, _ in status), status
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(_gpus() < 2, reason="needs two GPUs")
+@pytest.mark.parametrize("world", WORLDS)
+@pytest.mark.parametrize("env", [{}, {"B200DQN_FUSED_XLL": "1"}, {"B200DQN_P2P_SCHED": "layer"}, {"B200DQN_COMM": "nccl"}],
+                         ids=["p2p-gather", "p2p-gather-fused-conv-exchange", "p2p-two-shot", "nccl"])
+def test_n_ranks_equal_the_oracle_at_the_global_batch(env, world):
+    """W ranks x 32 samples are ONE step of the single-process reference at batch_size = W * 32 —
+    the global minibatch indexes bit for bit (same MT19937 stream), the weights after 3 steps within the
+    single-GPU bar (rel-L2 of the update <= 2e-2), the mean of the ranks' costs equal to the oracle's cost."""
+    out = _run(dict(env, ORACLE="3"), 29630 + world, world)
+    assert "indexes of the global minibatch bit-exact" in out, out[-2000:]
+    assert "match (update rel-L2 <= 2e-2)" in out, out[-2000:]
+    assert "ranks diverged" not in out
+    crcs = re.findall(r"weights crc32 ([0-9a-f]{8})", out)
+    assert len(crcs) == world and len(set(crcs)) == 1, crcs
 
 
 @pytest.mark.gpu
