@@ -150,7 +150,8 @@ k_head(const float* __restrict__ part, int splits, int rows, int nets, float* h4
 // chain (the stream of the fc2 optimizer): nothing on the device waits for the scalar.
 __global__ void __launch_bounds__(256)
 k_cost_finish(const float* __restrict__ row_cost, int rows, float* cost_ring, uint32_t* step,
-              volatile uint32_t* host_res, const KTrace kt) {
+              volatile uint32_t* host_res, const uint32_t* __restrict__ sampler_words, volatile uint32_t* host_words,
+              const KTrace kt) {
   __shared__ float s_c[1024];
   kt_begin(kt);
   float tot = 0.f;
@@ -171,7 +172,12 @@ k_cost_finish(const float* __restrict__ row_cost, int rows, float* cost_ring, ui
     if (host_res) {                // the host polls [0]: data first, system fence, then the sequence number
       host_res[4 + sidx % kHostCosts] = __float_as_uint(cost);
       host_res[1] = __float_as_uint(cost_ring[kCostRing + 1]);   // action-range flag word
+      if (sampler_words) {         // this step's index draw: words consumed, for the host's lock-step `random`
+        host_words[1] = sampler_words[0];
+        host_words[2] = sampler_words[1];
+      }
       __threadfence_system();
+      if (sampler_words) host_words[0] = sampler_words[2];
       host_res[0] = sidx + 1;
     }
   }
@@ -302,6 +308,7 @@ struct FrameSource {
   const uint8_t* src[2];
   const int32_t* idx[2];
   int shift[2];
+  int64_t nframes[2];   // frames in each source array
 };
 
 // Model.fprop for `nets` networks (z = 0 online, z = 1 target) on `rows` samples.
@@ -311,7 +318,7 @@ static int forward(b200dqn_net* n, const FrameSource& fs, int nets, int rows, cu
   const float* w[2] = {n->d_w, n->d_tw};
   int rc;
   if (n->cfg.math_mode == B200DQN_MATH_TCGEN05) {
-    rc = umma_forward(n, fs.src, fs.idx, fs.shift, nets, rows, st);
+    rc = umma_forward(n, fs.src, fs.idx, fs.shift, fs.nframes, nets, rows, st);
     if (rc) return rc;
   } else {
     {
@@ -344,7 +351,7 @@ static int forward(b200dqn_net* n, const FrameSource& fs, int nets, int rows, cu
       if ((rc = launch_gemm<Fc1Fwd, 32, 64, 16, 2, 4>("fc1_fwd", p, rows, kHidden, nets * kFc1Splits, st))) return rc;
     }
   }
-  const int fc1_splits = n->cfg.math_mode == B200DQN_MATH_TCGEN05 ? umma_fc1_splits() : kFc1Splits;
+  const int fc1_splits = n->cfg.math_mode == B200DQN_MATH_TCGEN05 ? umma_fc1_splits(rows) : kFc1Splits;
   B2_CHECK_CUDA(launch_pdl(k_head, dim3(rows), dim3(kHidden), 0, st, (const float*)n->d_fc1part, fc1_splits, rows, nets,
                            n->d_h4[0], n->d_h4[1], w[0] + lt.off[4], w[1] + lt.off[4], n->d_q[0], n->d_q[1], n->A,
                            td, ktrace_slot("head")));
@@ -436,8 +443,10 @@ static int optimizer_range(b200dqn_net* n, int l0, int l1, int mode, int rows, c
 // batch-mean cost -> cost ring, step counter + 1 (once per train step, after the head, on any stream behind it)
 static int cost_finish_on(b200dqn_net* n, int rows, cudaStream_t s) {
   NoPdlScope plain;
+  b200dqn_replay* r = n->step_replay;     // the ring this step samples from (nullptr: host-supplied minibatch)
   B2_CHECK_CUDA(launch_pdl(k_cost_finish, dim3(1), dim3(256), 0, s, (const float*)n->d_rowcost, rows, n->d_cost, n->d_step,
-                           n->h_res, ktrace_slot("cost")));
+                           n->h_res, (const uint32_t*)(r ? r->d_words : nullptr),
+                           (volatile uint32_t*)(r ? r->h_words : nullptr), ktrace_slot("cost")));
   B2_PROF("cost", s);
   return B200DQN_OK;
 }
@@ -1065,7 +1074,8 @@ extern "C" int b200dqn_net_predict_device(b200dqn_net* n, const uint8_t* dev_sta
              "net_predict_device: bad argument");
   DeviceGuard g(n->device);
   cudaStream_t st = as_stream(stream);
-  FrameSource fs{{dev_states, dev_states}, {n->d_iota4, n->d_iota4}, {0, 0}};
+  const int64_t state_frames = int64_t(n->nb) * kHist;
+  FrameSource fs{{dev_states, dev_states}, {n->d_iota4, n->d_iota4}, {0, 0}, {state_frames, state_frames}};
   HeadTrainArgs no_td{};
   int rc = forward(n, fs, 1, live_rows, st, no_td);
   if (rc) return rc;
@@ -1101,7 +1111,8 @@ extern "C" int b200dqn_net_train_device(b200dqn_net* n, const uint8_t* dev_pre, 
   B2_REQUIRE(n && dev_pre && dev_actions && dev_rewards && dev_post && dev_terminals, B200DQN_EINVAL,
              "net_train_device: null argument");
   DeviceGuard g(n->device);
-  FrameSource fs{{dev_pre, dev_post}, {n->d_iota4, n->d_iota4}, {0, 0}};
+  const int64_t state_frames = int64_t(n->nb) * kHist;
+  FrameSource fs{{dev_pre, dev_post}, {n->d_iota4, n->d_iota4}, {0, 0}, {state_frames, state_frames}};
   B2_TRY(train_step(n, fs, dev_actions, dev_rewards, dev_terminals, n->d_iota1, as_stream(stream)));
   n->train_iterations += 1;
   return B200DQN_OK;
@@ -1148,8 +1159,11 @@ static int check_fusable(b200dqn_net* n, b200dqn_replay* r) {
 static int train_on_ring(b200dqn_net* n, b200dqn_replay* r, cudaStream_t st) {
   const int32_t* my_idx = r->d_idx + n->rank * n->nb;  // this rank's slice of the global minibatch
   // prestates = frames index-4 .. index-1, poststates = index-3 .. index (src/replay_memory.py:71-72)
-  FrameSource fs{{r->d_screens, r->d_screens}, {my_idx, my_idx}, {-kHist, -kHist + 1}};
-  return train_step(n, fs, r->d_actions, r->d_rewards, r->d_terminals, my_idx, st);
+  FrameSource fs{{r->d_screens, r->d_screens}, {my_idx, my_idx}, {-kHist, -kHist + 1}, {r->size, r->size}};
+  n->step_replay = r;
+  const int rc = train_step(n, fs, r->d_actions, r->d_rewards, r->d_terminals, my_idx, st);
+  n->step_replay = nullptr;
+  return rc;
 }
 
 // train_on_ring through a cached CUDA graph (the sampler is NOT part of it: the indexes are already in r)

@@ -57,6 +57,7 @@ struct b200dqn_net {
   // host-mapped result block written by k_cost_finish: [0] train steps completed (published last, after a system
   // fence), [1] action-range flag, [4 + (step % kHostCosts)] cost of that step
   volatile uint32_t* h_res = nullptr;
+  b200dqn_replay* step_replay = nullptr;   // set while a step that samples from a ring is being enqueued / captured
 
   // unfused-mode staging (host minibatch -> device)
   uint8_t* d_pre = nullptr, *d_post = nullptr, *d_act = nullptr, *d_term = nullptr;

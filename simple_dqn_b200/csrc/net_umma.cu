@@ -8,6 +8,7 @@
 #include "umma.cuh"
 #include "umma2.cuh"
 #include "umma_mn.cuh"
+#include "conv1_tma.cuh"
 
 namespace b200 {
 
@@ -305,14 +306,23 @@ struct WConv1Wgrad {
   PlanePair dz16;          // dZ1 [rows][20][20][32]
   float* part;             // [splits][256][32]
   int rows, kb_per_split;
+  int tile_rows;           // live rows per 128-row im2col tile: 128 (dense tiling) or 100 (conv1_tma.cuh: 4 tiles/sample)
   __device__ int M(int) const { return kK1; }
   __device__ int N(int) const { return kC1; }
+  __device__ int total_kb() const {
+    return tile_rows == 128 ? (rows * kP1 * kP1 + 63) / 64 : rows * conv1tma::kTilesPerSample * 2;
+  }
   __device__ void krange(int z, int& kb, int& ke) const {
-    const int total = (rows * kP1 * kP1 + 63) / 64;
+    const int total = total_kb();
     kb = min(z * kb_per_split, total);
     ke = min(kb + kb_per_split, total);
   }
-  __device__ umma_mn::PixCtx pix(int, int kpix) const { return {kpix, 0, 0, kpix < rows * kP1 * kP1}; }
+  // kpix indexes the padded im2col rows; n = the real pixel (row of dZ1)
+  __device__ umma_mn::PixCtx pix(int, int kpix) const {
+    if (tile_rows == 128) return {kpix, 0, 0, kpix < rows * kP1 * kP1};
+    const int tile = kpix >> 7, local = kpix & 127;
+    return {tile * tile_rows + local, 0, 0, local < tile_rows && tile < rows * conv1tma::kTilesPerSample};
+  }
   __device__ const uint8_t* a_sub(int, int c, int kb) const {   // kb = global 64-pixel block
     return im2col + (int64_t(kb >> 1) * (kK1 / 64) + c) * (128 * 128) + (kb & 1) * (64 * 128);
   }
@@ -715,20 +725,32 @@ int umma_pack_layers(b200dqn_net* n, int which, int l0, int l1, cudaStream_t st)
   return rc;
 }
 
-constexpr int kUFc1Splits = 7;    // 49 k-blocks of 64 -> 7 per CTA; 4 M-tiles x 7 x 2 nets = 56 CTAs
+// fc1 forward split-K over blockIdx.z (the head kernel sums the partials): 49 k-blocks of 64.  Batch <= 64: 13 splits
+// (4 k-blocks per CTA, 4 M-tiles x 13 x 2 nets = 104 CTAs); larger minibatches bring their own tiles, so fewer
+// splits keep the partial-sum traffic down.
+static inline int fc1_splits_for(int rows) { return rows <= 64 ? 13 : rows <= 256 ? 7 : 4; }
+// Cluster split-K (umma2.cuh) for the kernels whose tile count leaves most of the 148 SMs idle at batch 32:
+//   conv2_fwd 42 tiles x 3 partners (8 k-blocks -> 3/3/2),  conv3_fwd 26 x 4 (9 -> 3/2/2/2),
+//   conv3_dgrad 21 x 4,  fc1_dgrad 25 x 4 (8 -> 2 each).  B200DQN_SPLITK=0 launches the single-CTA tiles.
+static const bool g_splitk = !(getenv("B200DQN_SPLITK") && atoi(getenv("B200DQN_SPLITK")) == 0);
+// Larger minibatches already fill the chip with tiles: split only while the tile count is below the SM count.
+static inline bool use_splitk(int tiles, int ks) { return g_splitk && tiles * ks <= 160; }
 constexpr int kUWgradKb = 4;      // minimum k-blocks (of 64 pixels) per wgrad split
 
 // k-blocks (of 64 pixels) per wgrad split: at least kUWgradKb, and few enough splits (<= 48) for the
 // one-pass reduction of k_opt_conv
+// conv1 through tensor-map TMA (conv1_tma.cuh) unless B200DQN_CONV1=ldg selects the register-path gather of umma2.cuh
+static const bool g_conv1_tma = !(getenv("B200DQN_CONV1") && strcmp(getenv("B200DQN_CONV1"), "ldg") == 0);
+static inline int conv1_pixels_padded(int rows) { return g_conv1_tma ? rows * conv1tma::kTilesPerSample * 128 : rows * kP1 * kP1; }
+
 int umma_wgrad_kb(int layer, int rows) {
-  const int kred = layer == 0 ? rows * kP1 * kP1 : layer == 1 ? rows * kP2 * kP2 : rows * kP3 * kP3;
+  const int kred = layer == 0 ? conv1_pixels_padded(rows) : layer == 1 ? rows * kP2 * kP2 : rows * kP3 * kP3;
   const int kbs = (kred + 63) / 64;
   int per = (kbs + 47) / 48;
-  if (layer == 0 && per < 8) per = 8;   // conv1: A tiles arrive by TMA, 8 k-blocks per CTA keep the grid at 50 CTAs
   return per > kUWgradKb ? per : kUWgradKb;
 }
 int umma_wgrad_splits(int layer, int rows) {
-  const int kred = layer == 0 ? rows * kP1 * kP1 : layer == 1 ? rows * kP2 * kP2 : rows * kP3 * kP3;
+  const int kred = layer == 0 ? conv1_pixels_padded(rows) : layer == 1 ? rows * kP2 * kP2 : rows * kP3 * kP3;
   const int kbs = (kred + 63) / 64, per = umma_wgrad_kb(layer, rows);
   return (kbs + per - 1) / per;
 }
@@ -763,7 +785,7 @@ int umma_net_init(b200dqn_net* n) {
       B2_CHECK_CUDA(cudaMemset(u->img_fwd[z][l], 0, u->img_fwd_bytes[l]));
     }
   }
-  B2_CHECK_CUDA(cudaMalloc(&u->im2col1, int64_t((nb * kP1 * kP1 + 127) / 128) * (kK1 / 64) * 128 * 128));
+  B2_CHECK_CUDA(cudaMalloc(&u->im2col1, int64_t(nb) * conv1tma::kTilesPerSample * (kK1 / 64) * 128 * 128));
   const int64_t dgr_bytes[3] = {int64_t((kFlat + 127) / 128) * (kHidden / 64) * 128 * 256,
                                 int64_t(kK3 / 64) * kC2 * 256, int64_t(4) * (256 / 64) * kC1 * 256};
   for (int i = 0; i < 3; ++i) {
@@ -812,11 +834,37 @@ void umma_dz4_planes(b200dqn_net* n, __half** hi, int64_t* lo_off) {
 }
 
 int umma_forward(b200dqn_net* n, const uint8_t* const src[2], const int32_t* const idx[2], const int shift[2],
-                 int nets, int rows, cudaStream_t st) {
+                 const int64_t nframes[2], int nets, int rows, cudaStream_t st) {
   UmmaState* u = ust(n);
   int rc;
   auto planes = [&](int i, int z) { return PlanePair{u->h16[i][z], u->h_elems[i]}; };
-  {
+  if (g_conv1_tma) {
+    // frames by tensor-map TMA.  Ring case (both states out of one frame array, poststates one frame later): ONE
+    // 5-frame window per CTA serves both networks.
+    conv1tma::Params p{};
+    const bool shared5 = nets == 2 && src[0] == src[1] && idx[0] == idx[1] && shift[1] == shift[0] + 1;
+    for (int z = 0; z < 2; ++z) {
+      p.idx[z] = idx[z]; p.shift[z] = shift[z];
+      p.wimg[z] = u->img_fwd[z][0]; p.out16[z] = u->h16[0][z];
+    }
+    p.out[0] = n->d_h1[0];
+    p.out[1] = nullptr;                       // nothing reads the target network's fp32 H1
+    p.shared5 = shared5 ? 1 : 0; p.nets = nets; p.rows = rows; p.lo_off = u->h_elems[0];
+    p.im2col = (nets == 2 && rows == n->nb) ? u->im2col1 : nullptr;
+    CUtensorMap m0, m1;
+    const int64_t nframes0 = nframes[0], nframes1 = nframes[1];
+    if ((rc = conv1tma::make_frame_map(&m0, src[0], nframes0, shared5 ? kHist + 1 : kHist))) return rc;
+    if ((rc = conv1tma::make_frame_map(&m1, src[nets == 2 ? 1 : 0], nets == 2 ? nframes1 : nframes0, kHist))) return rc;
+    static bool configured = false;
+    if (!configured) {
+      B2_CHECK_CUDA(cudaFuncSetAttribute(conv1tma::k_conv1_tma, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         conv1tma::kSmemBytes));
+      configured = true;
+    }
+    B2_CHECK_CUDA(launch_pdl(conv1tma::k_conv1_tma, dim3(rows * conv1tma::kTilesPerSample), dim3(umma2::kThreads2),
+                             conv1tma::kSmemBytes, st, m0, m1, p, ktrace_slot("conv1_fwd")));
+    B2_PROF("conv1_fwd", st);
+  } else {
     V2Conv1Fwd p;
     for (int z = 0; z < 2; ++z) {
       p.src[z] = src[z]; p.idx[z] = idx[z]; p.shift[z] = shift[z];
@@ -833,7 +881,10 @@ int umma_forward(b200dqn_net* n, const uint8_t* const src[2], const int32_t* con
       p.in16[z] = planes(0, z); p.wimg[z] = u->img_fwd[z][1]; p.out[z] = n->d_h2[z]; p.out16[z] = planes(1, z);
     }
     p.rows = rows;
-    if ((rc = umma2::launch_umma2("conv2_fwd", p, rows * kP2 * kP2, kC2, nets, st))) return rc;
+    const int tiles = (rows * kP2 * kP2 + 127) / 128 * nets;
+    if (use_splitk(tiles, 3)) rc = umma2::launch_umma2<P, 3>("conv2_fwd", p, rows * kP2 * kP2, kC2, nets, st);
+    else rc = umma2::launch_umma2("conv2_fwd", p, rows * kP2 * kP2, kC2, nets, st);
+    if (rc) return rc;
   }
   {
     using P = V2ConvFwd<kP2, kC2, 3, 1, kC3>;
@@ -842,15 +893,18 @@ int umma_forward(b200dqn_net* n, const uint8_t* const src[2], const int32_t* con
       p.in16[z] = planes(1, z); p.wimg[z] = u->img_fwd[z][2]; p.out[z] = n->d_h3[z]; p.out16[z] = planes(2, z);
     }
     p.rows = rows;
-    if ((rc = umma2::launch_umma2("conv3_fwd", p, rows * kP3 * kP3, kC3, nets, st))) return rc;
+    const int tiles = (rows * kP3 * kP3 + 127) / 128 * nets;
+    if (use_splitk(tiles, 4)) rc = umma2::launch_umma2<P, 4>("conv3_fwd", p, rows * kP3 * kP3, kC3, nets, st);
+    else rc = umma2::launch_umma2("conv3_fwd", p, rows * kP3 * kP3, kC3, nets, st);
+    if (rc) return rc;
     // data-parallel learners: this rank's H3 rows start travelling to every rank's fc1_wgrad now
     if (nets == 2 && rows == n->nb && comm_gather_active(n, st) && (rc = umma_push_h3(n, st))) return rc;
   }
   {
     V2Fc1Fwd p;
     for (int z = 0; z < 2; ++z) { p.in16[z] = planes(2, z); p.wimg[z] = u->img_fwd[z][3]; }
-    p.part = n->d_fc1part; p.rows = rows; p.splits = kUFc1Splits;
-    if ((rc = umma2::launch_umma2("fc1_fwd", p, kHidden, rows, nets * kUFc1Splits, st))) return rc;
+    p.part = n->d_fc1part; p.rows = rows; p.splits = fc1_splits_for(rows);
+    if ((rc = umma2::launch_umma2("fc1_fwd", p, kHidden, rows, nets * p.splits, st))) return rc;
   }
   return B200DQN_OK;
 }
@@ -870,6 +924,7 @@ int umma_backward_op(b200dqn_net* n, int op, const uint8_t* src, const int32_t* 
       UmmaState* u = ust(n);
       V2Fc1Dgrad p{u->img_dgr[0], PlanePair{u->dz16[0], u->dz_elems[0]}, n->d_h3[0], n->d_dz3,
                    PlanePair{u->dz16[1], u->dz_elems[1]}, rows};
+      if (use_splitk(25 * ((rows + 31) / 32), 4)) return umma2::launch_umma2<V2Fc1Dgrad, 4>("fc1_dgrad", p, kFlat, rows, 1, st);
       return umma2::launch_umma2("fc1_dgrad", p, kFlat, rows, 1, st);
     }
     case 2: {
@@ -884,6 +939,8 @@ int umma_backward_op(b200dqn_net* n, int op, const uint8_t* src, const int32_t* 
       using P = V2ConvDgrad<kP2, kC2, 3, 1, kC3>;
       P p{PlanePair{u->dz16[1], u->dz_elems[1]}, u->img_dgr[1], n->d_h2[0], n->d_dz2,
           PlanePair{u->dz16[2], u->dz_elems[2]}, rows};
+      if (use_splitk((rows * P::HC * P::HC + 127) / 128, 4))
+        return umma2::launch_umma2<P, 4>("conv3_dgrad", p, rows * P::HC * P::HC, kC2, 1, st);
       return umma2::launch_umma2("conv3_dgrad", p, rows * P::HC * P::HC, kC2, 1, st);
     }
     case 4: {
@@ -904,7 +961,7 @@ int umma_backward_op(b200dqn_net* n, int op, const uint8_t* src, const int32_t* 
       UmmaState* u = ust(n);
       (void)src; (void)idx; (void)shift;   // the frames were already gathered by conv1_fwd (im2col image)
       WConv1Wgrad p{u->im2col1, PlanePair{u->dz16[3], u->dz_elems[3]}, n->d_part + lt.part_off[0], rows,
-                    umma_wgrad_kb(0, rows)};
+                    umma_wgrad_kb(0, rows), g_conv1_tma ? conv1tma::kTileRows : 128};
       return umma_mn::launch_umma_mn("conv1_wgrad", p, kK1, kC1, lt.splits[0], st);
     }
   }
@@ -920,7 +977,7 @@ int umma_fc1_wgrad_fused(b200dqn_net* n, int rows, cudaStream_t st, bool keep_gr
   return umma_mn::launch_umma_mn("fc1_wgrad+opt", p, kFlat, kHidden, 1, st);
 }
 
-int umma_fc1_splits() { return kUFc1Splits; }
+int umma_fc1_splits(int rows) { return fc1_splits_for(rows); }
 bool umma_has_backward() { return true; }
 // ---- gather schedule hooks (data-parallel learners, comm_p2p.cuh) ---------------------------------------
 int umma_push_h3(b200dqn_net* n, cudaStream_t st) {

@@ -18,9 +18,10 @@ int umma_net_init(b200dqn_net* n);                      // allocate operand imag
 void umma_net_destroy(b200dqn_net* n);
 int umma_weights_changed(b200dqn_net* n, cudaStream_t st);  // fp32 master weights were overwritten by the host
 int umma_target_synced(b200dqn_net* n, cudaStream_t st);    // target <- online
+// nframes[z]: frames in the array src[z] points to (the tensor-map TMA gather of conv1 needs the extent)
 int umma_forward(b200dqn_net* n, const uint8_t* const src[2], const int32_t* const idx[2], const int shift[2],
-                 int nets, int rows, cudaStream_t st);
-int umma_fc1_splits();
+                 const int64_t nframes[2], int nets, int rows, cudaStream_t st);
+int umma_fc1_splits(int rows);
 // RMSProp of the fc1 layer + refresh of both of its tile images in one smem-free kernel
 int umma_opt_fc1(b200dqn_net* n, int rows, cudaStream_t st, bool from_g = false);
 int umma_fc1_wgrad_fused(b200dqn_net* n, int rows, cudaStream_t st, bool keep_grads);

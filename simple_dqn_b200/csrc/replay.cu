@@ -79,7 +79,7 @@ constexpr int kSampleThreads = 256;
 __global__ void __launch_bounds__(kSampleThreads, 1)
 k_sample(uint32_t* __restrict__ mt_state, const uint8_t* __restrict__ terminals,
          const int64_t* __restrict__ cursor, int hist, int batch, int32_t* __restrict__ idx_out,
-         uint32_t* __restrict__ words_out, volatile uint32_t* host_words, const KTrace kt) {
+         uint32_t* __restrict__ words_out, const KTrace kt) {
   __shared__ uint32_t mt[kMtN + 1];
   __shared__ int warp_cnt[kSampleThreads / 32];
   __shared__ int s_cut;
@@ -159,18 +159,23 @@ k_sample(uint32_t* __restrict__ mt_state, const uint8_t* __restrict__ terminals,
   for (int i = tid; i < kMtN + 1; i += kSampleThreads) mt_state[i] = mt[i];
   if (tid == 0) {
     words_out[0] = words;
-    const uint32_t total = words_out[1] + words;
-    words_out[1] = total;
-    if (host_words) {             // host-mapped mirror: data, system fence, then the sequence number
-      const uint32_t seq = words_out[2] + 1;   // samplings completed (device-resident counter: no PCIe read)
-      words_out[2] = seq;
-      host_words[1] = words;
-      host_words[2] = total;
-      __threadfence_system();
-      host_words[0] = seq;
-    }
+    words_out[1] += words;
+    words_out[2] += 1;            // samplings completed
   }
   kt_end(kt);
+}
+
+// Host-mapped mirror of the sampler's counters: data, system fence, then the sequence number the host polls.  Kept
+// OUT of k_sample (a system-scope fence on the critical chain costs ~2 us): the fused step publishes from its
+// off-chain cost kernel, a stand-alone sampling from this one-thread kernel.
+__global__ void k_publish_words(const uint32_t* __restrict__ words, volatile uint32_t* host_words) {
+  publish_words(words, host_words);
+}
+
+int replay_publish_words(b200dqn_replay* r, cudaStream_t st) {
+  k_publish_words<<<1, 1, 0, st>>>(r->d_words, r->h_words);
+  B2_LAUNCH_CHECK();
+  return B200DQN_OK;
 }
 
 int replay_flush(b200dqn_replay* r, cudaStream_t st) {
@@ -217,8 +222,7 @@ int launch_sample(b200dqn_replay* r, cudaStream_t st) {
   int frc = replay_flush(r, st);
   if (frc) return frc;
   B2_CHECK_CUDA(launch_pdl(k_sample, dim3(1), dim3(kSampleThreads), 0, st, r->d_mt, (const uint8_t*)r->d_terminals,
-                           (const int64_t*)r->d_cursor, r->hist, r->batch, r->d_idx, r->d_words, r->h_words,
-                           ktrace_slot("sample")));
+                           (const int64_t*)r->d_cursor, r->hist, r->batch, r->d_idx, r->d_words, ktrace_slot("sample")));
   B2_PROF("sample", st);
   return B200DQN_OK;
 }
@@ -496,6 +500,7 @@ extern "C" int b200dqn_replay_sample_sync(b200dqn_replay* r, uint32_t* host_word
   B2_REQUIRE(host_words_consumed, B200DQN_EINVAL, "replay_sample_sync: null argument");
   int rc = b200dqn_replay_sample(r, stream);
   if (rc) return rc;
+  if ((rc = replay_publish_words(r, as_stream(stream)))) return rc;
   rc = replay_wait_words(r, as_stream(stream));
   if (rc) return rc;
   *host_words_consumed = r->h_words[1];

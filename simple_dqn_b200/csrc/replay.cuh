@@ -71,6 +71,16 @@ int launch_sample(b200dqn_replay* r, cudaStream_t st);
 // push the pending add()s to HBM (no-op when there are none); call before anything reads the ring
 int replay_flush(b200dqn_replay* r, cudaStream_t st);
 int replay_wait_words(b200dqn_replay* r, cudaStream_t st);
+int replay_publish_words(b200dqn_replay* r, cudaStream_t st);   // device counters -> host-mapped mirror (tiny kernel)
+#ifdef __CUDACC__
+// [0] samplings completed (published last), [1] words of the last one, [2] running total
+__device__ __forceinline__ void publish_words(const uint32_t* __restrict__ words, volatile uint32_t* host_words) {
+  host_words[1] = words[0];
+  host_words[2] = words[1];
+  __threadfence_system();
+  host_words[0] = words[2];
+}
+#endif
 // adopt a host MT19937 state (624 key words + position) without synchronising the stream
 int replay_set_rng_async(b200dqn_replay* r, const uint32_t* key624, uint32_t pos, cudaStream_t st);
 }  // namespace b200

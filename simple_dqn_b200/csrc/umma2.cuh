@@ -123,9 +123,14 @@ constexpr int kThreads2 = kLoadThreads + 32; // warp 8: MMA issuer
 //             2 MMAs per k-step:  [acc0 | acc1] += A_hi x [B_hi ; B_lo]   (one N = 2*BN instruction:
 //             the hi and lo weight tiles are adjacent in shared memory)  and  acc1 += A_lo x B_hi;
 //             tcgen05.commit -> empty[s]
-template <class P>
+// KS > 1: split-K across a thread-block cluster of KS CTAs along grid x.  Rank r of a cluster walks k-blocks
+// [r*per, (r+1)*per) of its tile into its own TMEM; ranks > 0 park their combined fp32 accumulators in their own
+// shared memory, rank 0 adds them in rank order through DSMEM loads (deterministic) and runs the epilogue.  Gives the
+// 21-56-CTA kernels of the batch-32 step the whole chip: 2-3 k-blocks per CTA instead of 8-9.
+template <class P, int KS = 1>
 __global__ void __launch_bounds__(kThreads2, 1) k_umma2(const P p, const int trace_in, const KTrace kt) {
   using C = Cfg2<P>;
+  static_assert(KS >= 1 && KS <= 8 && !(KS > 1 && P::kDumpA), "cluster split-K: 1..8 partners, not with the A dump");
   constexpr int BN = C::BN;
   constexpr int S = C::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -141,10 +146,17 @@ __global__ void __launch_bounds__(kThreads2, 1) k_umma2(const P p, const int tra
   kt_begin(kt);
   B2_TRACE(tid == 0, 0);
   const int M = p.M(z), N = p.N(z);
-  const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * BN;
-  if (m0 >= M || n0 >= N) return;
+  const int crank = KS > 1 ? int(cluster_ctarank()) : 0;
+  const int mtile = KS > 1 ? int(blockIdx.x) / KS : int(blockIdx.x);
+  const int m0 = mtile * kBM, n0 = blockIdx.y * BN;
+  if (m0 >= M || n0 >= N) return;      // the same for every partner of a cluster
   int kb0, kb1;
   p.krange(z, kb0, kb1);
+  if constexpr (KS > 1) {
+    const int per = (kb1 - kb0 + KS - 1) / KS;
+    kb0 = min(kb0 + crank * per, kb1);
+    kb1 = min(kb0 + per, kb1);
+  }
   const int nkb = kb1 - kb0;
 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -189,7 +201,7 @@ __global__ void __launch_bounds__(kThreads2, 1) k_umma2(const P p, const int tra
         if constexpr (P::kDumpA) {
           // The staged [128 x 64] A_hi tile IS the MN-major operand the wgrad of this layer needs
           // (row = pixel, 64 contiguous taps): ship it out with one TMA bulk store per k-block.
-          uint8_t* dump = p.a_dump(z, blockIdx.x, kb0 + it);
+          uint8_t* dump = p.a_dump(z, mtile, kb0 + it);
           if (dump) tma_bulk_s2g(dump, smem_gen + s * C::kStageBytes, C::kABytes);
         }
 #pragma unroll
@@ -209,6 +221,11 @@ __global__ void __launch_bounds__(kThreads2, 1) k_umma2(const P p, const int tra
       }
       __syncwarp();
       B2_TRACE(lane == 0, 8 + it * 4 + 1);
+    }
+    if (nkb == 0 && lane == 0) mbar_arrive(&s_done);   // a partner without k-blocks: nothing to wait for
+    if constexpr (KS > 1) {   // take part in the two cluster barriers of the epilogue's reduction
+      cluster_arrive_release(); cluster_wait_acquire();
+      cluster_arrive_release(); cluster_wait_acquire();
     }
   } else {
     // ================================================================ loaders
@@ -269,7 +286,7 @@ __global__ void __launch_bounds__(kThreads2, 1) k_umma2(const P p, const int tra
       if (kAnyBulk && tid == 0) {
         mbar_arrive_expect_tx(&s_full[s], kBulkBytes);
         if constexpr (P::kAMode == kBulk)
-          tma_bulk_g2s(st_gen, p.a_tile(z, blockIdx.x, kb), 2 * C::kABytes, &s_full[s]);
+          tma_bulk_g2s(st_gen, p.a_tile(z, mtile, kb), 2 * C::kABytes, &s_full[s]);
         if constexpr (P::kBMode == kBulk)
           tma_bulk_g2s(st_gen + C::kAStage, p.b_tile(z, blockIdx.y, kb), 2 * C::kBBytes, &s_full[s]);
       }
@@ -352,7 +369,9 @@ __global__ void __launch_bounds__(kThreads2, 1) k_umma2(const P p, const int tra
     constexpr int kDirIt = BN / 16;                              // direct path: 8-column chunks per thread
     float pf[P::kPrefetch ? (P::kStagedEpilogue ? kStIt : kDirIt) : 1][8];
     if constexpr (P::kPrefetch) {
-      if constexpr (P::kStagedEpilogue) {
+      if (crank != 0) {
+        // partners only contribute accumulators
+      } else if constexpr (P::kStagedEpilogue) {
 #pragma unroll
         for (int i = 0; i < kStIt; ++i) {
           const int id = tid + i * kLoadThreads;
@@ -389,8 +408,44 @@ __global__ void __launch_bounds__(kThreads2, 1) k_umma2(const P p, const int tra
 #pragma unroll
       for (int c = 0; c < kChunks; ++c)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) a0[c][j] = fmaf(a1[c][j], umma::kLoInv, a0[c][j]);
-      if constexpr (P::kStagedEpilogue) {
+        for (int j = 0; j < 8; ++j) a0[c][j] = nkb > 0 ? fmaf(a1[c][j], umma::kLoInv, a0[c][j]) : 0.f;
+      bool emit = true;
+      if constexpr (KS > 1) {
+        // ---- split-K reduction through distributed shared memory.  A thread owns accumulator row `row`, columns
+        // [half * BN/2, +BN/2): partners park exactly that slice at the same offset of their own (now idle) stage
+        // memory, the leader adds the slices in rank order.
+        constexpr int kRedPitch = BN * 4 + 16;
+        static_assert(kBM * kRedPitch <= C::kStages * C::kStageBytes, "reduction tile must fit the stage ring");
+        uint8_t* mine = smem_gen + row * kRedPitch + half * kColsPerHalf * 4;
+        if (crank != 0) {
+#pragma unroll
+          for (int c = 0; c < kChunks; ++c) {
+            *reinterpret_cast<float4*>(mine + c * 32) = make_float4(a0[c][0], a0[c][1], a0[c][2], a0[c][3]);
+            *reinterpret_cast<float4*>(mine + c * 32 + 16) = make_float4(a0[c][4], a0[c][5], a0[c][6], a0[c][7]);
+          }
+        }
+        cluster_arrive_release();
+        cluster_wait_acquire();
+        if (crank == 0) {
+          const uint32_t local = smem_u32(mine);
+#pragma unroll
+          for (int r = 1; r < KS; ++r) {
+            const uint32_t remote = dsmem_addr(local, uint32_t(r));
+#pragma unroll
+            for (int c = 0; c < kChunks; ++c) {
+              const float4 v0 = ld_dsmem_f4(remote + c * 32), v1 = ld_dsmem_f4(remote + c * 32 + 16);
+              a0[c][0] += v0.x; a0[c][1] += v0.y; a0[c][2] += v0.z; a0[c][3] += v0.w;
+              a0[c][4] += v1.x; a0[c][5] += v1.y; a0[c][6] += v1.z; a0[c][7] += v1.w;
+            }
+          }
+        }
+        cluster_arrive_release();   // partners keep their shared memory alive until the leader has read it
+        cluster_wait_acquire();
+        emit = crank == 0;
+      }
+      if (!emit) {
+        // partner: done
+      } else if constexpr (P::kStagedEpilogue) {
         // A thread owns one accumulator ROW; written straight to HBM every store instruction would
         // touch 32 different lines.  Transpose through (now idle) pipeline smem so each warp store
         // covers whole lines: row pitch BN*4 + 16 B keeps both phases bank-conflict free.
@@ -444,18 +499,19 @@ static inline int read_trace(unsigned long long* out, int n) {
   return cudaMemcpyFromSymbol(out, g_trace, n * sizeof(unsigned long long)) == cudaSuccess ? n : -1;
 }
 
-template <class P>
+template <class P, int KS = 1>
 static int launch_umma2(const char* label, const P& p, int M, int N, int Z, cudaStream_t st) {
   using C = Cfg2<P>;
   static bool configured = false;
   if (!configured) {
-    B2_CHECK_CUDA(cudaFuncSetAttribute(k_umma2<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    B2_CHECK_CUDA(cudaFuncSetAttribute(k_umma2<P, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
     configured = true;
   }
-  dim3 grid((M + kBM - 1) / kBM, (N + C::BN - 1) / C::BN, Z);
+  dim3 grid(((M + kBM - 1) / kBM) * KS, (N + C::BN - 1) / C::BN, Z);
   static const char* trace_label = getenv("B200DQN_TRACE_LABEL");
   const int trace = (trace_label && strcmp(trace_label, label) == 0) ? 1 : 0;
-  B2_CHECK_CUDA(launch_pdl(k_umma2<P>, grid, dim3(kThreads2), C::kSmemBytes, st, p, trace, ktrace_slot(label)));
+  B2_CHECK_CUDA(launch_pdl_cluster(k_umma2<P, KS>, grid, dim3(kThreads2), C::kSmemBytes, st, KS, p, trace,
+                                   ktrace_slot(label)));
   B2_PROF(label, st);
   return B200DQN_OK;
 }

@@ -54,6 +54,7 @@ class Trace:
         self.actions, self.rewards, self.terminals, self.rates = [], [], [], []
         self.costs = []                 # cost[0,0] of every DeepQNetwork.train (callback.on_train)
         self.q_rows = []                # row 0 of every DeepQNetwork.predict, in call order
+        self.stats_q = []               # positions in q_rows of the Statistics.write predicts (validation states)
         self.rng_crc = []               # crc32 of random.getstate() at every phase boundary
         self.phase_rows = []            # (epoch, phase, steps, nr_games, avg_reward, min, max, meanq, meancost, updates)
         self.mem_cursor = []            # (count, current) at every phase boundary
@@ -223,6 +224,8 @@ def run_restated_loop(env, mem, net, buf, cfg, fused_train=None):
             S.games, S.avg_reward = 1, S.game_reward
         if S.validation is None and mem.count > mem.batch_size:
             S.validation = mem.getMinibatch()[0]           # the persistent prestates buffer, aliased
+        if S.validation is not None:
+            trace.stats_q.append(len(trace.q_rows))
         meanq = float(np.mean(np.max(rnet.predict(S.validation), axis=1))) if S.validation is not None else 0
         import sys
         lo = sys.maxsize if S.lo is None else S.lo

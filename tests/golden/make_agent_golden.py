@@ -23,12 +23,7 @@ import agent_loop as AL  # noqa: E402
 import ref_convert as RC  # noqa: E402
 from synthetic_env import SyntheticEnvironment  # noqa: E402
 
-CASES = {
-    "breakout10k": dict(num_actions=4, env_seed=3, cfg=dict()),
-    "pong_repeat2": dict(num_actions=6, env_seed=5,
-                         cfg=dict(train_repeat=2, target_steps=120, random_steps=150, train_steps=240, test_steps=60,
-                                  epochs=2, exploration_decay_steps=200, random_seed=4242, replay_size=400)),
-}
+from test_agent_loop import CASES  # noqa: E402  (one definition of the cases: the tests own it)
 
 
 def run_case(name, spec, tmp):

@@ -21,10 +21,14 @@ from conftest import GOLDEN, needs_reference
 from synthetic_env import SyntheticEnvironment
 
 CASES = {
-    "breakout10k": dict(num_actions=4, env_seed=3, cfg=dict()),
+    # BASELINE configs[0]: replay 10k, batch 32, history 4, A = 4 (Breakout); 920 env steps, 150 updates, 3 target syncs/epoch
+    "breakout10k": dict(num_actions=4, env_seed=3,
+                        cfg=dict(random_steps=200, train_steps=300, test_steps=60, target_steps=120,
+                                 exploration_decay_steps=250)),
+    # A = 6 (Pong), --train_repeat 2, a ring small enough to wrap (replay 400 < 500 env steps), periodic target syncs
     "pong_repeat2": dict(num_actions=6, env_seed=5,
-                         cfg=dict(train_repeat=2, target_steps=120, random_steps=150, train_steps=240, test_steps=60,
-                                  epochs=2, exploration_decay_steps=200, random_seed=4242, replay_size=400)),
+                         cfg=dict(train_repeat=2, target_steps=80, random_steps=100, train_steps=160, test_steps=40,
+                                  epochs=2, exploration_decay_steps=150, random_seed=4242, replay_size=400)),
 }
 
 

@@ -83,10 +83,17 @@ def test_host_minibatch_and_device_handle_paths_agree(mode):
     for device_minibatch in (False, True):
         env = SyntheticEnvironment(spec["num_actions"], seed=spec["env_seed"])
         mem, net, buf = _product(cfg, env.numActions(), mode, device_minibatch)
-        tr = AL.run_restated_loop(env, mem, net, buf, cfg).arrays()
-        out.append((tr, net.get_weights(with_states=False)))
-    (ta, wa), (tb, wb) = out
+        trace = AL.run_restated_loop(env, mem, net, buf, cfg)
+        out.append((trace.arrays(), trace.stats_q, net.get_weights(with_states=False)))
+    (ta, sa, wa), (tb, sb, wb) = out
     for k in ("actions", "rng_crc", "mem_cursor"):
         assert (ta[k] == tb[k]).all(), k
-    assert (ta["costs"] == tb["costs"]).all() and (ta["q_rows"] == tb["q_rows"]).all()
+    assert (ta["costs"] == tb["costs"]).all()
+    # Q rows of the agent's own predicts: identical.  The Statistics predicts run on `validation_states`, which in the
+    # reference ALIASES the replay's persistent prestates buffer and silently changes with every later
+    # getMinibatch; the host-array path reproduces that, a device handle that nobody looks at does not touch the
+    # host buffer — the one documented difference of device_minibatch=True.
+    assert sa == sb
+    agent_rows = np.setdiff1d(np.arange(len(ta["q_rows"])), np.array(sa, dtype=np.int64))
+    assert (ta["q_rows"][agent_rows] == tb["q_rows"][agent_rows]).all()
     assert all((a == b).all() for a, b in zip(wa, wb))
