@@ -24,3 +24,49 @@ def broadcast_unique_id(dist, make_id, rank, src=0):
     dist.broadcast_object_list(box, src=src)
     assert isinstance(box[0], (bytes, bytearray)) and len(box[0]) == 128
     return bytes(box[0])
+
+
+class ReplicatedReplay:
+    """ReplayMemory.add for data-parallel learners whose replicas must all see the frames of ONE environment
+    (SURVEY §8e "add is applied to all replicas"; §8 f3): the rank that owns the environment (`src`) calls
+    :meth:`add` exactly like ``ReplayMemory.add`` (/root/reference/src/replay_memory.py:26-34); every `block`
+    env steps — and at the latest before anybody samples (:meth:`flush`) — the buffered frames and their
+    (action, reward, terminal) travel ONCE through ``dist.broadcast`` and every rank appends them to its own ring
+    with one ``add_batch`` (one H2D per rank per block instead of one upload per env step per rank; the other
+    ranks never need the environment).  Ranks other than `src` call :meth:`add` with ``None`` arguments (or simply
+    :meth:`flush`) at the same points of the loop: the broadcasts are collective.
+
+    Works with anything that has ``add_batch(actions, rewards, screens, terminals)`` — the device ring or, in
+    the CPU tests, the oracle ring."""
+
+    def __init__(self, mem, dist, rank, src=0, block=4, dims=(84, 84)):
+        import numpy as np
+        self.mem, self.dist, self.rank, self.src, self.block = mem, dist, rank, src, int(block)
+        self._np = np
+        self._frames = np.zeros((self.block,) + tuple(dims), dtype=np.uint8)
+        self._meta = np.zeros((self.block, 3), dtype=np.int64)        # action, reward, terminal
+        self._n = 0
+
+    def add(self, action=None, reward=None, screen=None, terminal=None):
+        if self.rank == self.src:
+            assert screen.shape == self._frames.shape[1:]
+            self._frames[self._n] = screen
+            self._meta[self._n] = (int(action), int(reward), 1 if terminal else 0)
+        self._n += 1
+        if self._n == self.block:
+            self.flush()
+
+    def flush(self):
+        """Collective: broadcast what `src` has buffered and append it on every rank."""
+        import torch
+        n = self._n
+        if n == 0:
+            return
+        frames = torch.from_numpy(self._frames[:n])
+        meta = torch.from_numpy(self._meta[:n])
+        self.dist.broadcast(frames, src=self.src)
+        self.dist.broadcast(meta, src=self.src)
+        np = self._np
+        self.mem.add_batch(np.ascontiguousarray(self._meta[:n, 0], dtype=np.uint8), self._meta[:n, 1].copy(),
+                           self._frames[:n], np.ascontiguousarray(self._meta[:n, 2], dtype=np.uint8))
+        self._n = 0

@@ -125,3 +125,45 @@ def test_rank_slice_partition():
         assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
     with pytest.raises(AssertionError):
         rank_slice(2, 2, 32)
+
+
+def _bcast_worker(rank, port, out_dir):
+    from simple_dqn_b200.parallel import ReplicatedReplay
+    from simple_dqn_b200.synthetic_env import SyntheticEnvironment
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=WORLD)
+    ring = ReplayOracle(64, batch_size=4)
+
+    class Ring:      # add_batch on the oracle ring = n consecutive add()s
+        def add_batch(self, actions, rewards, screens, terminals):
+            for a, r, s, t in zip(actions, rewards, screens, terminals):
+                ring.add(int(a), int(r), s, bool(t))
+    rep = ReplicatedReplay(Ring(), dist, rank, src=0, block=4)
+    env = SyntheticEnvironment(4, seed=1) if rank == 0 else None      # only rank 0 owns an environment
+    for t in range(150):                                               # wraps the 64-frame ring; 150 % 4 != 0
+        if rank == 0:
+            r = env.act(t % 4)
+            rep.add(t % 4, r, env.getScreen(), env.isTerminal())
+        else:
+            rep.add()
+    rep.flush()                                                        # the tail that did not fill a block
+    np.savez(os.path.join(out_dir, "ring%d.npz" % rank), screens=ring.screens, actions=ring.actions,
+             rewards=ring.rewards, terminals=ring.terminals, cursor=np.array([ring.count, ring.current]))
+    dist.destroy_process_group()
+
+
+def test_replica_broadcast_keeps_rings_identical(tmp_path):
+    """§8 f3: one environment, W replicas — every rank's ring ends up byte-identical to the single-process ring."""
+    from simple_dqn_b200.synthetic_env import SyntheticEnvironment
+    port = _free_port()
+    mp.spawn(_bcast_worker, args=(port, str(tmp_path)), nprocs=WORLD, join=True)
+    ref = ReplayOracle(64, batch_size=4)
+    env = SyntheticEnvironment(4, seed=1)
+    for t in range(150):
+        r = env.act(t % 4)
+        ref.add(t % 4, r, env.getScreen(), env.isTerminal())
+    for rank in range(WORLD):
+        g = np.load(os.path.join(str(tmp_path), "ring%d.npz" % rank))
+        assert (g["screens"] == ref.screens).all() and (g["actions"] == ref.actions).all()
+        assert (g["rewards"] == ref.rewards).all() and (g["terminals"] == ref.terminals).all()
+        assert tuple(g["cursor"]) == (ref.count, ref.current)
