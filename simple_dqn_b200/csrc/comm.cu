@@ -86,7 +86,27 @@ int comm_xchg_range(b200dqn_net* n, int l0, int l1, int chan, cudaStream_t st, c
   return B200DQN_OK;
 }
 
-constexpr int kXCounterWords = kXChannels * kXMaxBlocks + 1 + 2 * kXChannels + 2 * kXPushChannels;
+constexpr int kXCounterWords = kXChannels * kXMaxBlocks + 1 + 2 * kXChannels + 2 * kXPushChannels + 1;
+
+// the head kernel pushes its dZ4 rows itself in the gather schedule unless B200DQN_HEAD_PUSH=0
+bool comm_head_push(const b200dqn_net* n, cudaStream_t st, HeadPush* out) {
+  static const bool enabled = !(getenv("B200DQN_HEAD_PUSH") && atoi(getenv("B200DQN_HEAD_PUSH")) == 0);
+  if (!enabled || !comm_gather_active(n, st)) return false;
+  if (out) {
+    HeadPush h{};
+    h.world = n->world; h.rank = n->rank; h.rows = n->nb;
+    const int64_t mine = int64_t(n->nb) * kHidden * 2;     // bytes of this rank's rows in one plane
+    for (int p = 0; p < n->world; ++p) {
+      h.gat[p] = reinterpret_cast<uint4*>(n->xbuf[p] + n->x_dz_off);
+      h.cnt[p] = reinterpret_cast<uint32_t*>(n->xbuf[p]) + kXCountWord;
+    }
+    h.parity16 = n->x_dz_parity / 16;
+    h.lo16 = mine * n->world / 16;
+    h.epoch = n->d_xpush_epoch + 1;
+    *out = h;
+  }
+  return true;
+}
 
 // true when this train step uses the gather schedule (net.cu::backward_and_update_gather)
 bool comm_gather_active(const b200dqn_net* n, cudaStream_t st) {
@@ -153,11 +173,12 @@ int comm_push_planes(b200dqn_net* n, int chan, const void* hi, int64_t lo_off_el
 }
 
 // Block the stream until every rank's H3 and dZ4 rows of this step have landed in the local gather area.
-int comm_wait_pushes(b200dqn_net* n, cudaStream_t st) {
+int comm_wait_pushes(b200dqn_net* n, cudaStream_t st, int dz_rows) {
   B2_REQUIRE(n->xchg_ok && n->d_xbuf, B200DQN_ESTATE, "plane push not initialised");
   NoPdlScope plain;
-  B2_CHECK_CUDA(launch_pdl(k_xwait, dim3(1), dim3(32), 0, st, (const uint32_t*)n->d_xbuf, (const uint32_t*)n->d_xpush_epoch,
-                           n->world, n->d_xerr, ktrace_slot("wait_push")));
+  B2_CHECK_CUDA(launch_pdl(k_xwait, dim3(1), dim3(32), 0, st, reinterpret_cast<uint32_t*>(n->d_xbuf), n->d_xpush_epoch,
+                           n->world, n->d_xerr, dz_rows, n->d_xpush_epoch + 2 * kXPushChannels,
+                           ktrace_slot("wait_push")));
   B2_PROF("wait_push", st);
   return B200DQN_OK;
 }

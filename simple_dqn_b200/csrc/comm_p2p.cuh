@@ -64,6 +64,19 @@ struct XPushArgs {
   uint32_t* ticket;          // [kXPushChannels]
 };
 
+// dZ4 rows pushed by the head kernel itself (one CTA per sample): no separate push kernel between the head and the
+// peers' fc1_wgrad.  Arrival is counted: every CTA adds 1 (red.release.sys) to counter [source rank] in each peer's
+// exchange buffer after its stores; the consumer waits for rows x (pushes so far + 1).
+constexpr int kXCountWord = 32;    // arrival counters [kXMaxWorld] start at this word of the exchange buffer
+struct HeadPush {
+  int world;                       // 0 = off
+  int rank, rows;                  // rows per rank
+  uint4* gat[kXMaxWorld];          // rank p's dZ4 gather area (parity 0) as mapped here
+  uint32_t* cnt[kXMaxWorld];       // rank p's arrival counters as mapped here
+  int64_t parity16, lo16;          // 16-byte units: one parity's area, offset of the lo plane inside it
+  const uint32_t* epoch;           // completed dZ4 pushes (the next one uses parity (epoch + 1) & 1)
+};
+
 struct XPeers {
   float4* g[kXMaxWorld];        // rank p's gradient buffer as mapped here ([rank] = the local one)
   uint32_t* flags[kXMaxWorld];  // rank p's flag words
@@ -316,15 +329,27 @@ __global__ void __launch_bounds__(kXThreads) k_xpush(XPushArgs a, KTrace kt) {
   kt_end(kt);
 }
 
-// wait until every rank's push of the current epoch has landed here (one block; runs ahead of the consumer)
-__global__ void k_xwait(const uint32_t* pflags, const uint32_t* epoch, int world, uint32_t* err, KTrace kt) {
+// wait until every rank's push of the current epoch has landed here (one block; runs ahead of the consumer).
+// dz_rows > 0: the dZ4 rows come from the peers' head kernels and are COUNTED (HeadPush): wait for
+// dz_rows x (count_epoch + 1) arrivals per source, then advance count_epoch and the dZ4 epoch (the parity selector).
+__global__ void k_xwait(uint32_t* pflags, uint32_t* epoch, int world, uint32_t* err, int dz_rows, uint32_t* count_epoch,
+                        KTrace kt) {
   kt_begin(kt);
   const int t = threadIdx.x;
-  if (t < kXPushChannels * world) {
-    const int chan = t / world, p = t % world;
-    xwait(pflags + chan * kXMaxWorld + p, *reinterpret_cast<const volatile uint32_t*>(epoch + chan), err);
+  if (t < world) {
+    xwait(pflags + t, *reinterpret_cast<const volatile uint32_t*>(epoch), err);            // channel 0: H3 planes
+  } else if (t < 2 * world) {
+    const int p = t - world;
+    if (dz_rows == 0)
+      xwait(pflags + kXMaxWorld + p, *reinterpret_cast<const volatile uint32_t*>(epoch + 1), err);
+    else
+      xwait(pflags + kXCountWord + p, uint32_t(dz_rows) * (*reinterpret_cast<const volatile uint32_t*>(count_epoch) + 1u), err);
   }
   __syncthreads();
+  if (dz_rows && t == 0) {
+    count_epoch[0] += 1;
+    epoch[1] += 1;
+  }
   kt_end(kt);
 }
 #endif  // B200_COMM_P2P_KERNELS

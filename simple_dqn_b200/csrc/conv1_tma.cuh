@@ -15,8 +15,8 @@
 //   * the online network's tiles are also shipped to the im2col image conv1_wgrad reads (TMA bulk store).
 //
 // Tiling: one CTA = 5 output rows x 20 columns = 100 pixels of one sample (a 128-row UMMA tile, 100 live rows);
-// grid = 4 x samples.  All operands of a CTA fit in shared memory at once (no ring): <= 8 A tiles (128 KB),
-// 8 weight tiles (64 KB), two windows (23 KB).
+// grid = 4 x samples.  Shared memory: the window(s) (12 KB each) + a 3-stage ring of [A tile 16 KB | weight tiles
+// 2 x 8 KB] = 109 KB, so two CTAs share an SM and the next kernels of the PDL chain can still pre-launch.
 #pragma once
 #include <cuda.h>
 
@@ -32,10 +32,13 @@ constexpr int kGroupBytes = 4 * kFrameW;        // 336
 constexpr int kFrameBoxBytes = kBoxGroups * kGroupBytes;   // 2352 per frame
 constexpr uint32_t kATile = 128 * 128;          // [128 rows x 64 fp16]
 constexpr uint32_t kWTile = 64 * 128;           // [32 hi rows ; 32 lo rows] x 64 fp16
-constexpr int kMaxSlots = 8;
+constexpr int kRing = 3;                        // stages: one frame's A tile + the (<= 2) weight tiles that multiply it
+constexpr uint32_t kStage = kATile + 2 * kWTile;   // 32 KB
 constexpr uint32_t kBoxStride = 12288;          // one window (<= 5 frames x 2352 B), 128-byte aligned
-constexpr uint32_t kSmemBytes = kMaxSlots * kATile + 8 * kWTile + 2 * kBoxStride + 1024;
 constexpr uint32_t kTmemCols = 128;             // 2 networks x [acc_hi | acc_lo] x 32 channels
+// 109 KB with one window (ring train / predict): two CTAs per SM, and successor kernels of the PDL chain still find
+// room to pre-launch; 121 KB with two windows (staged states)
+static inline uint32_t smem_bytes(int windows) { return kRing * kStage + uint32_t(windows) * kBoxStride + 1024; }
 
 struct Params {
   // frame sources: src 0 feeds the online network, src 1 the target network.  shared5: both read ONE 5-frame
@@ -63,24 +66,32 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
 
-__global__ void __launch_bounds__(umma2::kThreads2, 1)
+// which k-block of network z multiplies the tile of slot j (frame f of window b); -1: none
+__device__ __forceinline__ int kb_for(const Params& p, int nets, int b, int f, int z) {
+  int kb;
+  if (p.shared5) kb = f - z;                     // online: frame f is k-block f; target: k-block f - 1
+  else if (nets == 2 && b != z) return -1;       // staged: window b belongs to network b
+  else kb = f;
+  return (kb >= 0 && kb < kHist) ? kb : -1;
+}
+
+__global__ void __launch_bounds__(umma2::kThreads2, 2)
 k_conv1_tma(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1, const Params p,
             const KTrace kt) {
   using umma2::kLoadThreads;
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint32_t s_tmem;
-  __shared__ __align__(8) uint64_t s_box[2];      // windows have landed
-  __shared__ __align__(8) uint64_t s_w;           // weight tiles have landed
-  __shared__ __align__(8) uint64_t s_slot[kMaxSlots];   // A tile converted
-  __shared__ __align__(8) uint64_t s_done;        // all MMAs complete
-  __shared__ __align__(8) uint64_t s_dumped;      // im2col bulk stores have read their tiles
+  __shared__ __align__(8) uint64_t s_box[2];          // windows have landed
+  __shared__ __align__(8) uint64_t s_full[kRing];     // A tile converted + weight tiles landed
+  __shared__ __align__(8) uint64_t s_empty[kRing];    // the MMAs (and the im2col store) that read the stage are done
+  __shared__ __align__(8) uint64_t s_done;            // all MMAs complete
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n = blockIdx.x / kTilesPerSample, t = blockIdx.x % kTilesPerSample;
   kt_begin(kt);
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t a_base = smem_base, w_base = smem_base + kMaxSlots * kATile, box_base = w_base + 8 * kWTile;
+  const uint32_t box_base = smem_base + kRing * kStage;
   const int nets = p.nets;
   const int nboxes = (nets == 2 && !p.shared5) ? 2 : 1;
   const int box_frames = (nets == 2 && p.shared5) ? kHist + 1 : kHist;
@@ -90,11 +101,12 @@ k_conv1_tma(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CU
   if (tid == 32) {
     mbar_init(&s_box[0], 1);
     mbar_init(&s_box[1], 1);
-    mbar_init(&s_w, 1);
 #pragma unroll
-    for (int j = 0; j < kMaxSlots; ++j) mbar_init(&s_slot[j], kLoadThreads);
+    for (int s = 0; s < kRing; ++s) {
+      mbar_init(&s_full[s], kLoadThreads + 1);
+      mbar_init(&s_empty[s], 1);
+    }
     mbar_init(&s_done, 1);
-    mbar_init(&s_dumped, 1);
     mbar_fence_init();
   }
   umma::fence_before_sync();
@@ -102,14 +114,21 @@ k_conv1_tma(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CU
   umma::fence_after_sync();
   const uint32_t tmem = s_tmem;
 
+  // weight tiles of slot j into its stage (thread 0): they do not depend on the predecessor kernel
+  auto fetch_weights = [&](int j) {
+    const int s = j % kRing, b = j / box_frames, f = j % box_frames;
+    uint32_t bytes = 0;
+    for (int z = 0; z < nets; ++z) bytes += kb_for(p, nets, b, f, z) >= 0 ? kWTile : 0u;
+    mbar_arrive_expect_tx(&s_full[s], bytes);
+    for (int z = 0; z < nets; ++z) {
+      const int kb = kb_for(p, nets, b, f, z);
+      if (kb >= 0) tma_bulk_g2s(smem_gen + s * kStage + kATile + z * kWTile, p.wimg[z] + kb * kWTile, kWTile, &s_full[s]);
+    }
+  };
   if (tid == 0) {
-    // weights do not depend on the predecessor kernel (the previous step's optimizer finished long ago)
     tma_prefetch_desc(&map0);
     if (nboxes == 2) tma_prefetch_desc(&map1);
-    mbar_arrive_expect_tx(&s_w, uint32_t(nets) * 4 * kWTile);
-    for (int z = 0; z < nets; ++z)
-      for (int kb = 0; kb < 4; ++kb)
-        tma_bulk_g2s(smem_gen + (w_base - smem_base) + (z * 4 + kb) * kWTile, p.wimg[z] + kb * kWTile, kWTile, &s_w);
+    for (int j = 0; j < kRing && j < nslots; ++j) fetch_weights(j);
   }
   pdl_wait();   // the sampled indexes come from the predecessor
   if (tid == 0) {
@@ -123,34 +142,32 @@ k_conv1_tma(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CU
   if (warp == 8) {
     // ================================================================ MMA issuer
     constexpr uint32_t idesc = umma::make_idesc_f16(128, 64);
-    mbar_wait(&s_w, 0);
     for (int j = 0; j < nslots; ++j) {
-      mbar_wait(&s_slot[j], 0);
+      const int s = j % kRing, b = j / box_frames, f = j % box_frames;
+      mbar_wait(&s_full[s], (j / kRing) & 1);
       fence_proxy_async_smem();
       umma::fence_after_sync();
-      const int b = j / box_frames, f = j % box_frames;
-      const uint64_t da = umma::make_desc_sw128(a_base + j * kATile);
+      const uint32_t stage = smem_base + s * kStage;
+      const uint64_t da = umma::make_desc_sw128(stage);
       if (umma2::elect_one()) {
-        // which (network, k-block) pairs consume this frame's tile
+        bool dumped = false;
         for (int z = 0; z < nets; ++z) {
-          int kb;
-          if (p.shared5) kb = f - z;                 // online: frame f is k-block f; target: k-block f - 1
-          else if (nets == 2 && b != z) continue;    // staged: window b belongs to network b
-          else kb = f;
-          if (kb < 0 || kb >= kHist) continue;
-          const uint64_t db = umma::make_desc_sw128(w_base + (z * 4 + kb) * kWTile);
+          const int kb = kb_for(p, nets, b, f, z);
+          if (kb < 0) continue;
+          const uint64_t db = umma::make_desc_sw128(stage + kATile + z * kWTile);
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma::mma_f16(tmem + z * 64, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          if (z == 0 && p.im2col)   // the online network's tile IS conv1_wgrad's MN-major A operand
-            tma_bulk_s2g(p.im2col + (int64_t(blockIdx.x) * 4 + kb) * kATile, smem_gen + j * kATile, kATile);
+          if (z == 0 && p.im2col) {   // the online network's tile IS conv1_wgrad's MN-major A operand
+            tma_bulk_s2g(p.im2col + (int64_t(blockIdx.x) * 4 + kb) * kATile, smem_gen + s * kStage, kATile);
+            tma_bulk_commit();
+            dumped = true;
+          }
         }
+        if (j + kRing < nslots && dumped) tma_bulk_wait_read_all();   // the stage is about to be overwritten
+        umma::mma_commit(&s_empty[s]);
         if (j == nslots - 1) {
           umma::mma_commit(&s_done);
-          if (p.im2col) {
-            tma_bulk_commit();
-            tma_bulk_wait_read_all();
-          }
-          mbar_arrive(&s_dumped);
+          if (p.im2col) tma_bulk_wait_read_all();
         }
       }
       __syncwarp();
@@ -171,10 +188,14 @@ k_conv1_tma(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CU
       dst_off[i] = umma::sw128_off(row, r);
     }
     for (int j = 0; j < nslots; ++j) {
-      const int b = j / box_frames, f = j % box_frames;
+      const int s = j % kRing, b = j / box_frames, f = j % box_frames;
       if (f == 0) mbar_wait(&s_box[b], 0);
+      if (j >= kRing) {
+        mbar_wait(&s_empty[s], ((j / kRing) - 1) & 1);
+        if (tid == 0) fetch_weights(j);
+      }
       const uint8_t* win = smem_gen + (box_base - smem_base) + b * kBoxStride + f * kFrameBoxBytes;
-      uint8_t* tile = smem_gen + j * kATile;
+      uint8_t* tile = smem_gen + s * kStage;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         uint4 hi = make_uint4(0u, 0u, 0u, 0u);
@@ -197,13 +218,12 @@ k_conv1_tma(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CU
         *reinterpret_cast<uint4*>(tile + dst_off[i]) = hi;
       }
       fence_proxy_async_smem();   // st.shared (generic proxy) -> async proxy, writer side
-      mbar_arrive(&s_slot[j]);
+      mbar_arrive(&s_full[s]);
     }
     pdl_launch_dependents();
 
     // ---- epilogue: thread <-> (pixel row, 16 channels); x 1/255, Rectlin, fp32 + hi/lo planes
     mbar_wait(&s_done, 0);
-    mbar_wait(&s_dumped, 0);
     umma::fence_after_sync();
     const int q4 = warp & 3, half = warp >> 2;
     const int row = q4 * 32 + lane;

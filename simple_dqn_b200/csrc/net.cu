@@ -42,6 +42,7 @@ struct HeadTrainArgs {
   float adam_lr;
   int num_actions;    // actions[] >= num_actions would index q / W5 out of bounds: flagged in err, clamped
   uint32_t* err;
+  HeadPush push;      // data-parallel gather schedule: this CTA's dZ4 row goes straight to every rank (world = 0: off)
 };
 
 __global__ void __launch_bounds__(kHidden)
@@ -52,6 +53,7 @@ k_head(const float* __restrict__ part, int splits, int rows, int nets, float* h4
   __shared__ float s_q[2][kMaxActions];
   __shared__ float s_d;
   __shared__ int s_a;
+  __shared__ __align__(16) __half s_row[2][kHidden];   // hi / lo of this sample's dZ4 row (peer push)
   const int b = blockIdx.x, t = threadIdx.x;
   kt_begin(kt);
   // The TD scalars of this sample depend only on the sampler (several kernels upstream, complete by now):
@@ -136,11 +138,34 @@ k_head(const float* __restrict__ part, int splits, int rows, int nets, float* h4
     td.dz4[b * kHidden + t] = o;
     if (td.dz4_hi) {
       const __half hh = __float2half_rn(o);
+      const __half ll = __float2half_rn((o - __half2float(hh)) * 2048.0f);
       td.dz4_hi[b * kHidden + t] = hh;
-      td.dz4_hi[td.dz4_lo_off + b * kHidden + t] = __float2half_rn((o - __half2float(hh)) * 2048.0f);
+      td.dz4_hi[td.dz4_lo_off + b * kHidden + t] = ll;
+      s_row[0][t] = hh;
+      s_row[1][t] = ll;
     }
     float* dw = td.dw5_rows + (int64_t(b) * kHidden + t) * A;        // per-row partial, summed by the optimizer
     for (int j = 0; j < A; ++j) dw[j] = (j == a) ? hv * d : 0.f;
+  }
+  if (td.push.world > 0) {
+    // this sample's dZ4 row (1 KB per plane) to every rank's gather area, 16 bytes per store, then one counted
+    // arrival per peer: the peers' fc1_wgrad over the global minibatch needs nothing else from this rank
+    __syncthreads();
+    const HeadPush& hp = td.push;
+    if (t < 2 * (kHidden / 8)) {
+      const int pl = t / (kHidden / 8), c = t % (kHidden / 8);
+      const uint4 v = reinterpret_cast<const uint4*>(s_row[pl])[c];
+      const int64_t par = int64_t((*reinterpret_cast<const volatile uint32_t*>(hp.epoch) + 1u) & 1u) * hp.parity16;
+      const int64_t at = par + pl * hp.lo16 + (int64_t(hp.rank) * hp.rows + b) * (kHidden / 8) + c;
+#pragma unroll
+      for (int p = 0; p < kXMaxWorld; ++p)
+        if (p < hp.world) hp.gat[p][at] = v;
+    }
+    __syncthreads();
+    if (t < hp.world) {
+      asm volatile("fence.acq_rel.sys;" ::: "memory");   // the CTA's stores (observed through the barrier) first
+      asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(hp.cnt[t] + hp.rank) : "memory");
+    }
   }
   kt_end(kt);
 }
@@ -560,9 +585,10 @@ static int backward_and_update_gather(b200dqn_net* n, const FrameSource& fs, int
   B2_CHECK_CUDA(cudaStreamWaitEvent(sA, ev[0], 0));
   {
     NoPdlScope side;
-    B2_TRY(umma_push_dz4(n, sA));                            // peers' fc1_wgrad wait for these 64 KB
+    const bool head_pushed = comm_head_push(n, st, nullptr);  // the head kernel already sent this rank's dZ4 rows
+    if (!head_pushed) B2_TRY(umma_push_dz4(n, sA));          // peers' fc1_wgrad wait for these 64 KB
     B2_CHECK_CUDA(cudaStreamWaitEvent(sA, ev[14], 0));       // own H3 push (forward, umma_push_h3) has been issued
-    B2_TRY(comm_wait_pushes(n, sA));
+    B2_TRY(comm_wait_pushes(n, sA, head_pushed ? rows : 0));
     B2_TRY(umma_fc1_wgrad_gathered(n, sA));
     // fc2 (8 KB) on the stream the H3 push has left idle: nothing later in the step reads W5
     B2_CHECK_CUDA(cudaStreamWaitEvent(sN, ev[0], 0));
@@ -781,8 +807,9 @@ static int train_step(b200dqn_net* n, const FrameSource& fs, const uint8_t* acti
                    float(n->cfg.clip_error), n->d_delta, n->d_step, n->d_rowcost, n->d_dz4,
                    n->d_part + n->lt.part_off[4], nullptr, 0,
                    n->cfg.optimizer == B200DQN_OPT_ADAM ? n->d_optscal : nullptr, float(n->cfg.learning_rate), n->A,
-                   reinterpret_cast<uint32_t*>(n->d_cost + kCostRing + 1)};
+                   reinterpret_cast<uint32_t*>(n->d_cost + kCostRing + 1), HeadPush{}};
   umma_dz4_planes(n, &td.dz4_hi, &td.dz4_lo_off);
+  comm_head_push(n, st, &td.push);
   B2_TRY(forward(n, fs, 2, rows, st, td));
   return backward_and_update(n, fs, rows, st, true);
 }
@@ -905,7 +932,7 @@ extern "C" int b200dqn_net_create(int device, const b200dqn_net_config* cfg, b20
   // the gradient buffer is the one allocation peers map (comm.cu): their flag words sit behind it
   B2_CHECK_CUDA(fmalloc(&n->d_g, n->n_params + kXFlagWords));
   n->d_xflags = reinterpret_cast<uint32_t*>(n->d_g + n->n_params);
-  constexpr int kXWords = kXChannels * kXMaxBlocks + 1 + 2 * kXChannels + 2 * kXPushChannels;
+  constexpr int kXWords = kXChannels * kXMaxBlocks + 1 + 2 * kXChannels + 2 * kXPushChannels + 1;
   B2_CHECK_CUDA(cudaMalloc(&n->d_xepoch, kXWords * sizeof(uint32_t)));
   B2_CHECK_CUDA(cudaMemset(n->d_xepoch, 0, kXWords * sizeof(uint32_t)));
   n->d_xerr = n->d_xepoch + kXChannels * kXMaxBlocks;

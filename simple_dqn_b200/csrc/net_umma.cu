@@ -203,7 +203,7 @@ struct V2Fc1Dgrad {
       if (n0 + j < rows) {
         const int64_t i = int64_t(n0 + j) * kFlat + m;
         const float o = pf[j] > 0.f ? v[j] : 0.f;
-        dz3[i] = o;
+        if (dz3) dz3[i] = o;
         __half h, l;
         umma2::split1(o, h, l);
         dz3_16.hi[i] = h;
@@ -256,7 +256,7 @@ struct V2ConvDgrad {
     float o[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) o[j] = xv[j] > 0.f ? v[j] : 0.f;
-    st8(dx + i, o);
+    if (dx) st8(dx + i, o);
     if (dx16.hi) umma2::split8_planes(o, dx16.hi + i, dx16.hi + dx16.lo_off + i);
   }
 };
@@ -725,14 +725,22 @@ int umma_pack_layers(b200dqn_net* n, int which, int l0, int l1, cudaStream_t st)
   return rc;
 }
 
-// fc1 forward split-K over blockIdx.z (the head kernel sums the partials): 49 k-blocks of 64.  Batch <= 64: 13 splits
-// (4 k-blocks per CTA, 4 M-tiles x 13 x 2 nets = 104 CTAs); larger minibatches bring their own tiles, so fewer
-// splits keep the partial-sum traffic down.
-static inline int fc1_splits_for(int rows) { return rows <= 64 ? 13 : rows <= 256 ? 7 : 4; }
+// fc1 forward split-K over blockIdx.z (the head kernel sums the partials): 49 k-blocks of 64 -> 7 per CTA,
+// 4 M-tiles x 7 x 2 nets = 56 CTAs at batch 32; large minibatches bring their own tiles, so fewer splits keep the
+// partial-sum traffic down.  (13 splits = 104 CTAs was measured: fc1_fwd 6.3 -> 12 us inside the step — see below.)
+static inline int fc1_splits_for(int rows) {
+  static const int forced = getenv("B200DQN_FC1_SPLITS") ? atoi(getenv("B200DQN_FC1_SPLITS")) : 0;
+  if (forced >= 1 && forced <= kFc1Splits) return forced;
+  return rows <= 256 ? 7 : 4;
+}
 // Cluster split-K (umma2.cuh) for the kernels whose tile count leaves most of the 148 SMs idle at batch 32:
 //   conv2_fwd 42 tiles x 3 partners (8 k-blocks -> 3/3/2),  conv3_fwd 26 x 4 (9 -> 3/2/2/2),
-//   conv3_dgrad 21 x 4,  fc1_dgrad 25 x 4 (8 -> 2 each).  B200DQN_SPLITK=0 launches the single-CTA tiles.
-static const bool g_splitk = !(getenv("B200DQN_SPLITK") && atoi(getenv("B200DQN_SPLITK")) == 0);
+//   conv3_dgrad 21 x 4,  fc1_dgrad 25 x 4 (8 -> 2 each).
+// OFF by default (B200DQN_SPLITK=1 turns it on): parity-clean, but MEASURED SLOWER inside the step — 85.2 us vs
+// 73.6 us per step on a B200 (profiles/r2c_*): with 100+ CTAs of 193 KB shared memory per kernel the successor of the
+// PDL chain finds no free SM to pre-launch on (its prologue no longer hides behind the predecessor) and the cluster
+// needs all its SMs at once; the few-CTA tiles win because consecutive kernels CO-RESIDE.
+static const bool g_splitk = getenv("B200DQN_SPLITK") && atoi(getenv("B200DQN_SPLITK")) != 0;
 // Larger minibatches already fill the chip with tiles: split only while the tile count is below the SM count.
 static inline bool use_splitk(int tiles, int ks) { return g_splitk && tiles * ks <= 160; }
 constexpr int kUWgradKb = 4;      // minimum k-blocks (of 64 pixels) per wgrad split
@@ -858,11 +866,12 @@ int umma_forward(b200dqn_net* n, const uint8_t* const src[2], const int32_t* con
     static bool configured = false;
     if (!configured) {
       B2_CHECK_CUDA(cudaFuncSetAttribute(conv1tma::k_conv1_tma, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         conv1tma::kSmemBytes));
+                                         int(conv1tma::smem_bytes(2))));
       configured = true;
     }
+    const uint32_t smem = conv1tma::smem_bytes((nets == 2 && !shared5) ? 2 : 1);
     B2_CHECK_CUDA(launch_pdl(conv1tma::k_conv1_tma, dim3(rows * conv1tma::kTilesPerSample), dim3(umma2::kThreads2),
-                             conv1tma::kSmemBytes, st, m0, m1, p, ktrace_slot("conv1_fwd")));
+                             smem, st, m0, m1, p, ktrace_slot("conv1_fwd")));
     B2_PROF("conv1_fwd", st);
   } else {
     V2Conv1Fwd p;
@@ -878,7 +887,8 @@ int umma_forward(b200dqn_net* n, const uint8_t* const src[2], const int32_t* con
     using P = V2ConvFwd<kP1, kC1, 4, 2, kC2>;
     P p;
     for (int z = 0; z < 2; ++z) {
-      p.in16[z] = planes(0, z); p.wimg[z] = u->img_fwd[z][1]; p.out[z] = n->d_h2[z]; p.out16[z] = planes(1, z);
+      p.in16[z] = planes(0, z); p.wimg[z] = u->img_fwd[z][1]; p.out16[z] = planes(1, z);
+      p.out[z] = z ? nullptr : n->d_h2[z];     // nothing reads the target network's fp32 activations
     }
     p.rows = rows;
     const int tiles = (rows * kP2 * kP2 + 127) / 128 * nets;
@@ -890,7 +900,8 @@ int umma_forward(b200dqn_net* n, const uint8_t* const src[2], const int32_t* con
     using P = V2ConvFwd<kP2, kC2, 3, 1, kC3>;
     P p;
     for (int z = 0; z < 2; ++z) {
-      p.in16[z] = planes(1, z); p.wimg[z] = u->img_fwd[z][2]; p.out[z] = n->d_h3[z]; p.out16[z] = planes(2, z);
+      p.in16[z] = planes(1, z); p.wimg[z] = u->img_fwd[z][2]; p.out16[z] = planes(2, z);
+      p.out[z] = z ? nullptr : n->d_h3[z];
     }
     p.rows = rows;
     const int tiles = (rows * kP3 * kP3 + 127) / 128 * nets;
@@ -922,7 +933,8 @@ int umma_backward_op(b200dqn_net* n, int op, const uint8_t* src, const int32_t* 
     }
     case 1: {
       UmmaState* u = ust(n);
-      V2Fc1Dgrad p{u->img_dgr[0], PlanePair{u->dz16[0], u->dz_elems[0]}, n->d_h3[0], n->d_dz3,
+      // the fp32 copies of dZ3/dZ2/dZ1 have no reader in this engine (wgrads and dgrads take the fp16 planes)
+      V2Fc1Dgrad p{u->img_dgr[0], PlanePair{u->dz16[0], u->dz_elems[0]}, n->d_h3[0], n->keep_grads ? n->d_dz3 : nullptr,
                    PlanePair{u->dz16[1], u->dz_elems[1]}, rows};
       if (use_splitk(25 * ((rows + 31) / 32), 4)) return umma2::launch_umma2<V2Fc1Dgrad, 4>("fc1_dgrad", p, kFlat, rows, 1, st);
       return umma2::launch_umma2("fc1_dgrad", p, kFlat, rows, 1, st);
@@ -937,7 +949,7 @@ int umma_backward_op(b200dqn_net* n, int op, const uint8_t* src, const int32_t* 
     case 3: {
       UmmaState* u = ust(n);
       using P = V2ConvDgrad<kP2, kC2, 3, 1, kC3>;
-      P p{PlanePair{u->dz16[1], u->dz_elems[1]}, u->img_dgr[1], n->d_h2[0], n->d_dz2,
+      P p{PlanePair{u->dz16[1], u->dz_elems[1]}, u->img_dgr[1], n->d_h2[0], n->keep_grads ? n->d_dz2 : nullptr,
           PlanePair{u->dz16[2], u->dz_elems[2]}, rows};
       if (use_splitk((rows * P::HC * P::HC + 127) / 128, 4))
         return umma2::launch_umma2<P, 4>("conv3_dgrad", p, rows * P::HC * P::HC, kC2, 1, st);
@@ -953,7 +965,7 @@ int umma_backward_op(b200dqn_net* n, int op, const uint8_t* src, const int32_t* 
     case 5: {
       UmmaState* u = ust(n);
       using P = V2ConvDgrad<kP1, kC1, 4, 2, kC2>;
-      P p{PlanePair{u->dz16[2], u->dz_elems[2]}, u->img_dgr[2], n->d_h1[0], n->d_dz1,
+      P p{PlanePair{u->dz16[2], u->dz_elems[2]}, u->img_dgr[2], n->d_h1[0], n->keep_grads ? n->d_dz1 : nullptr,
           PlanePair{u->dz16[3], u->dz_elems[3]}, rows};
       return umma2::launch_umma2("conv2_dgrad", p, rows * P::HC * P::HC, kC1, 4, st);
     }
