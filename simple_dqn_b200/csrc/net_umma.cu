@@ -621,7 +621,10 @@ int umma_opt_fc1(b200dqn_net* n, int rows, cudaStream_t st, bool from_g) {
   UmmaState* u = ust(n);
   const LayerTable& lt = n->lt;
   const float* dw = from_g ? n->d_g + lt.off[3] : n->d_part + lt.part_off[3];
-  B2_CHECK_CUDA(launch_pdl(k_opt_fc1, dim3(2 * n->sm_count), dim3(256), 0, st, dw, n->d_w + lt.off[3],
+  // capped grid (CTAs per SM, grid-stride): the kernel shares the SMs — and the L2 — with the dgrad chain
+  static const int per_sm = getenv("B200DQN_OPT_FC1_CTAS") ? atoi(getenv("B200DQN_OPT_FC1_CTAS")) : 2;
+  const int ctas = per_sm > 0 ? per_sm * n->sm_count : n->sm_count / (-per_sm > 0 ? -per_sm : 1);
+  B2_CHECK_CUDA(launch_pdl(k_opt_fc1, dim3(ctas), dim3(256), 0, st, dw, n->d_w + lt.off[3],
                            n->d_s + lt.off[3], u->img_dgr[0], make_opt_args(n, rows), ktrace_slot("opt_fc1")));
   B2_PROF("opt_fc1", st);
   return umma2::launch_pack("pack_fc1f", PackFc1Fwd{n->d_w + lt.off[3]}, u->img_fwd[0][3], st, 2 * n->sm_count);
