@@ -22,7 +22,11 @@ def _gpus():
         return 0
 
 
+# every world size the box offers; B200DQN_TEST_WORLDS="4,8" narrows it (a W-GPU box is charged W x, so the
+# 8-GPU development runs pick their cases)
 WORLDS = [w for w in (2, 4, 8) if w <= _gpus()] or [2]
+if os.environ.get("B200DQN_TEST_WORLDS"):
+    WORLDS = [int(w) for w in os.environ["B200DQN_TEST_WORLDS"].split(",") if int(w) <= max(_gpus(), 2)] or WORLDS
 
 
 def _run(env_extra, port, world=2):

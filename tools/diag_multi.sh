@@ -1,0 +1,23 @@
+#!/bin/bash
+# multi-GPU development pass: $1 = number of GPUs on the box (2 or 8)
+set -x
+N=${1:-2}
+O=gpurun_out/r2m$N; mkdir -p $O
+tr() { python -m torch.distributed.run --nnodes=1 --nproc-per-node $1 --master-addr 127.0.0.1 --master-port $2 "${@:3}"; }
+if [ "$N" = "2" ]; then
+  B200DQN_TEST_WORLDS=2 timeout -s KILL 900 python -m pytest tests/test_gpu_multi.py -m gpu -q --maxfail=20 -k "oracle or match_nccl" > $O/pytest_multi.log 2>&1; echo "rc=$?" >> $O/pytest_multi.log
+  TIMELINE=1 timeout -s KILL 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29701 tools/mgpu_check.py > $O/timeline_w2.txt 2>&1
+  TIMELINE=1 B200DQN_HEAD_PUSH=0 timeout -s KILL 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29702 tools/mgpu_check.py > $O/timeline_w2_nopush.txt 2>&1
+  TIMELINE=1 B200DQN_FUSED_XLL=1 timeout -s KILL 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29703 tools/mgpu_check.py > $O/timeline_w2_fusedxll.txt 2>&1
+  timeout -s KILL 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29704 bench.py --gpus 2 --steps 1000 --warmup 50 > $O/bench_n2.json 2> $O/bench_n2.err
+else
+  B200DQN_TEST_WORLDS=8 timeout -s KILL 900 python -m pytest tests/test_gpu_multi.py -m gpu -q --maxfail=20 -k "oracle" > $O/pytest_multi_w8.log 2>&1; echo "rc=$?" >> $O/pytest_multi_w8.log
+  B200DQN_TEST_WORLDS=4 timeout -s KILL 400 python -m pytest tests/test_gpu_multi.py -m gpu -q --maxfail=20 -k "oracle and p2p-gather and not fused" > $O/pytest_multi_w4.log 2>&1; echo "rc=$?" >> $O/pytest_multi_w4.log
+  for W in 4 8; do
+    TIMELINE=1 timeout -s KILL 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node $W --master-addr 127.0.0.1 --master-port 2971$W tools/mgpu_check.py > $O/timeline_w$W.txt 2>&1
+  done
+  for W in 2 4 8; do
+    timeout -s KILL 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $W --master-addr 127.0.0.1 --master-port 2972$W bench.py --gpus $W --steps 1000 --warmup 50 > $O/bench_n$W.json 2> $O/bench_n$W.err
+  done
+fi
+echo done
