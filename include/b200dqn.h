@@ -220,6 +220,13 @@ int b200dqn_net_predict(b200dqn_net* n, const uint8_t* host_states, float* host_
 int b200dqn_net_predict_device(b200dqn_net* n, const uint8_t* dev_states, int live_rows, float* dev_q,
                                void* stream);
 
+/* The agent's action selection (src/agent.py:55-61) on a device-resident state window: forward for the live rows as ONE
+ * captured CUDA graph, Q-values back through host-mapped memory (no memcpy; the call polls).  host_q is (batch, A);
+ * rows >= live_rows are exact zeros.  Needs a non-default stream for the graph path (falls back to
+ * b200dqn_net_predict_device + copy otherwise).  Synchronises on the result only. */
+int b200dqn_net_predict_device_host(b200dqn_net* n, const uint8_t* dev_states, int live_rows, float* host_q,
+                                    void* stream);
+
 /* DeepQNetwork.train(minibatch, epoch) — src/deepqnetwork.py:107-172 — from HOST arrays as the
  * reference passes them (drop-in mode).  terminals is u8 0/1.  host_cost receives cost[0,0]
  * (:171); synchronises. */

@@ -85,6 +85,7 @@ SIGNATURES = {
     "b200dqn_net_sync_target": [_P, _P],
     "b200dqn_net_predict": [_P, _P, _P, _P],
     "b200dqn_net_predict_device": [_P, _P, C.c_int, _P, _P],
+    "b200dqn_net_predict_device_host": [_P, _P, C.c_int, _P, _P],
     "b200dqn_net_train": [_P, _P, _P, _P, _P, _P, _f32p, _P],
     "b200dqn_net_train_device": [_P, _P, _P, _P, _P, _P, _P],
     "b200dqn_net_train_sampled": [_P, _P, _P],

@@ -970,8 +970,8 @@ extern "C" int b200dqn_net_create(int device, const b200dqn_net_config* cfg, b20
   B2_CHECK_CUDA(cudaMallocHost(&n->h_pin, n->pin_bytes));
   {
     void* m = nullptr;
-    B2_CHECK_CUDA(cudaHostAlloc(&m, 256, cudaHostAllocMapped));
-    memset(m, 0, 256);
+    B2_CHECK_CUDA(cudaHostAlloc(&m, 4096, cudaHostAllocMapped));
+    memset(m, 0, 4096);
     n->h_res = static_cast<volatile uint32_t*>(m);
   }
   {
@@ -998,6 +998,7 @@ extern "C" int b200dqn_net_destroy(b200dqn_net* n) {
   umma_net_destroy(n);
   if (n->graph_exec) cudaGraphExecDestroy(n->graph_exec);
   if (n->graph_train_exec) cudaGraphExecDestroy(n->graph_train_exec);
+  if (n->graph_predict_exec) cudaGraphExecDestroy(n->graph_predict_exec);
   for (auto& sd : n->side) if (sd) cudaStreamDestroy(sd);
   for (auto& e : n->ev) if (e) cudaEventDestroy(e);
   if (n->d_tw != n->d_w) { cudaFree(n->d_tw); cudaFree(n->d_ts); }
@@ -1113,6 +1114,67 @@ extern "C" int b200dqn_net_predict_device(b200dqn_net* n, const uint8_t* dev_sta
     k_zero_rows<<<cdiv((n->nb - live_rows) * n->A, 128), 128, 0, st>>>(dev_q, live_rows, n->nb, n->A);
     B2_LAUNCH_CHECK();
   }
+  return B200DQN_OK;
+}
+
+// Q rows of a fast-path predict -> host-mapped memory: data, system fence, sequence number
+__global__ void k_publish_q_counter(const float* __restrict__ q, int count, volatile uint32_t* host_res, uint32_t* counter) {
+  for (int i = threadIdx.x; i < count; i += blockDim.x) host_res[kHostQ + i] = __float_as_uint(q[i]);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t seq = *counter + 1;     // device-resident count of fast-path predicts: the graph replays unchanged
+    *counter = seq;
+    __threadfence_system();
+    host_res[2] = seq;
+  }
+}
+
+// agent.py:55-61 on a device-resident state window (StateBuffer): the forward pass for the live rows, captured once
+// into a CUDA graph (one launch per env step), Q rows back through host-mapped memory (no memcpy, polled).
+// host_q receives (batch, A); rows >= live_rows are exact zeros (no biases: Q(0) = 0).
+extern "C" int b200dqn_net_predict_device_host(b200dqn_net* n, const uint8_t* dev_states, int live_rows, float* host_q,
+                                               void* stream) {
+  B2_REQUIRE(n && dev_states && host_q && live_rows >= 1 && live_rows <= n->nb, B200DQN_EINVAL,
+             "net_predict_device_host: bad argument");
+  DeviceGuard g(n->device);
+  cudaStream_t st = as_stream(stream);
+  const int count = live_rows * n->A;
+  if (count > kHostQFloats || st == nullptr || !n->use_graph || g_prof_on) {   // general path: device predict + copy
+    int rc = b200dqn_net_predict_device(n, dev_states, live_rows, n->d_q[0], stream);
+    if (rc) return rc;
+    B2_CHECK_CUDA(cudaMemcpyAsync(host_q, n->d_q[0], size_t(n->nb) * n->A * sizeof(float), cudaMemcpyDeviceToHost, st));
+    B2_CHECK_CUDA(cudaStreamSynchronize(st));
+    return B200DQN_OK;
+  }
+  if (!n->graph_predict_exec || n->graph_predict_states != dev_states || n->graph_predict_rows != live_rows ||
+      n->graph_predict_stream != st) {
+    if (n->graph_predict_exec) { cudaGraphExecDestroy(n->graph_predict_exec); n->graph_predict_exec = nullptr; }
+    cudaGraph_t graph = nullptr;
+    B2_CHECK_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    const int64_t state_frames = int64_t(n->nb) * kHist;
+    FrameSource fs{{dev_states, dev_states}, {n->d_iota4, n->d_iota4}, {0, 0}, {state_frames, state_frames}};
+    HeadTrainArgs no_td{};
+    int rc = forward(n, fs, 1, live_rows, st, no_td);
+    if (!rc) {
+      k_publish_q_counter<<<1, 64, 0, st>>>(n->d_q[0], count, n->h_res, n->d_optscal_u32());
+      if (cudaGetLastError() != cudaSuccess) rc = B200DQN_ECUDA;
+    }
+    cudaError_t e = cudaStreamEndCapture(st, &graph);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    B2_CHECK_CUDA(e);
+    B2_CHECK_CUDA(cudaGraphInstantiate(&n->graph_predict_exec, graph, 0));
+    cudaGraphDestroy(graph);
+    n->graph_predict_states = dev_states; n->graph_predict_rows = live_rows; n->graph_predict_stream = st;
+  }
+  B2_CHECK_CUDA(cudaGraphLaunch(n->graph_predict_exec, st));
+  n->predicts_launched += 1;
+  int rc = poll_mapped_seq(n->h_res + 2, n->predicts_launched, st, "predict result");
+  if (rc) return rc;
+  for (int i = 0; i < count; ++i) {
+    const uint32_t bits = n->h_res[kHostQ + i];
+    memcpy(host_q + i, &bits, sizeof(float));
+  }
+  memset(host_q + count, 0, (size_t(n->nb) * n->A - count) * sizeof(float));
   return B200DQN_OK;
 }
 

@@ -12,7 +12,8 @@ namespace b200 {
 constexpr int kLayers = 5;
 constexpr int kMaxActions = 32;
 constexpr int kCostRing = 1024;
-constexpr int kHostCosts = 60;            // per-step costs mirrored in host-mapped memory (a 256-byte block)
+constexpr int kHostCosts = 60;            // per-step costs mirrored in host-mapped memory
+constexpr int kHostQ = 64, kHostQFloats = 960;   // word offset / capacity of the Q rows in the host-mapped block
 constexpr int kFc1Splits = 14;            // 3136 / 14 = 224 = 14 * 16
 constexpr int kFc1Chunk = kFlat / kFc1Splits;
 
@@ -38,7 +39,9 @@ struct b200dqn_net {
   float* d_w = nullptr;   // online weights
   float* d_s = nullptr;   // online optimizer state: n_states planes of n_params (RMSProp 1, Adam 2, Adadelta 3)
   int n_states = 1;
-  float* d_optscal = nullptr;  // [0] Adam's step scalar l of the current step (written by the head kernel)
+  float* d_optscal = nullptr;  // [0] Adam's step scalar l of the current step (written by the head kernel);
+                               // [1] (as u32) fast-path predicts completed
+  uint32_t* d_optscal_u32() const { return reinterpret_cast<uint32_t*>(d_optscal) + 1; }
   float* d_tw = nullptr;  // target weights (== d_w when target_steps == 0)
   float* d_ts = nullptr;  // target optimizer state (copied for fidelity with :102-105)
   float* d_g = nullptr;   // summed gradients (all-reduce buffer / get_grads)
@@ -54,9 +57,15 @@ struct b200dqn_net {
   float* d_cost = nullptr;     // cost ring [kCostRing]
   uint32_t* d_step = nullptr;  // device step counter (cost ring cursor)
   float* d_rowcost = nullptr;    // [nb] per-sample cost
-  // host-mapped result block written by k_cost_finish: [0] train steps completed (published last, after a system
-  // fence), [1] action-range flag, [4 + (step % kHostCosts)] cost of that step
+  // host-mapped result block (4 KB): [0] train steps completed (published last, after a system fence), [1]
+  // action-range flag, [2] predicts completed, [4 + (step % kHostCosts)] cost of that step (k_cost_finish);
+  // [64 ..) Q rows of the last fast-path predict (k_publish_q)
   volatile uint32_t* h_res = nullptr;
+  uint32_t predicts_launched = 0;
+  cudaGraphExec_t graph_predict_exec = nullptr;   // forward on a device-resident state window + result publish
+  const uint8_t* graph_predict_states = nullptr;
+  int graph_predict_rows = 0;
+  cudaStream_t graph_predict_stream = nullptr;
   b200dqn_replay* step_replay = nullptr;   // set while a step that samples from a ring is being enqueued / captured
 
   // unfused-mode staging (host minibatch -> device)

@@ -256,11 +256,10 @@ class DeepQNetwork:
         assert tuple(states.shape) == ((self.batch_size, self.history_length,) + self.screen_dim)
         q = np.empty((self.batch_size, self.num_actions), dtype=np.float32)
         if isinstance(states, DeviceStates):
-            p, b = C.c_void_p(), C.c_size_t()
-            L.call("b200dqn_net_device_ptr", self._h, L.NET_PTR_Q_ONLINE, C.byref(p), C.byref(b))
-            L.call("b200dqn_net_predict_device", self._h, C.c_void_p(states.device_ptr()), states.live_rows, p,
-                   self._stream)
-            return self._read_f32(L.NET_PTR_Q_ONLINE, q.shape)
+            # one graph launch, Q row(s) back through host-mapped memory (agent.py:55-61 runs this every env step)
+            L.call("b200dqn_net_predict_device_host", self._h, C.c_void_p(states.device_ptr()), states.live_rows,
+                   L.np_ptr(q), self._stream)
+            return q
         st = np.ascontiguousarray(states, dtype=np.uint8)
         L.call("b200dqn_net_predict", self._h, L.np_ptr(st), L.np_ptr(q), self._stream)
         return q                                                        # (batch, A) == qvalues.T (:186)
