@@ -758,6 +758,8 @@ int umma_wgrad_kb(int layer, int rows) {
   const int kred = layer == 0 ? conv1_pixels_padded(rows) : layer == 1 ? rows * kP2 * kP2 : rows * kP3 * kP3;
   const int kbs = (kred + 63) / 64;
   int per = (kbs + 47) / 48;
+  if (layer == 0 && per < 8) per = 8;   // conv1: A tiles arrive by TMA bulk copies; 8 k-blocks per CTA keep the split count (and
+                                        // the optimizer's partial-sum loads) down: measured 43 splits -> opt_conv1 +1.5 us
   return per > kUWgradKb ? per : kUWgradKb;
 }
 int umma_wgrad_splits(int layer, int rows) {
