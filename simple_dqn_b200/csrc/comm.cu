@@ -88,9 +88,11 @@ int comm_xchg_range(b200dqn_net* n, int l0, int l1, int chan, cudaStream_t st, c
 
 constexpr int kXCounterWords = kXChannels * kXMaxBlocks + 1 + 2 * kXChannels + 2 * kXPushChannels + 1;
 
-// the head kernel pushes its dZ4 rows itself in the gather schedule unless B200DQN_HEAD_PUSH=0
+// B200DQN_HEAD_PUSH=1: the head kernel pushes its dZ4 rows itself (counted arrivals).  OFF by default: parity-clean
+// (tests/test_gpu_multi.py) but MEASURED SLOWER on 2 x B200 — 101 vs 92 us/step: the system-scope fence in front of
+// the arrival counter keeps every head CTA ~15 us on the critical chain (profiles/r2m2_*).
 bool comm_head_push(const b200dqn_net* n, cudaStream_t st, HeadPush* out) {
-  static const bool enabled = !(getenv("B200DQN_HEAD_PUSH") && atoi(getenv("B200DQN_HEAD_PUSH")) == 0);
+  static const bool enabled = getenv("B200DQN_HEAD_PUSH") && atoi(getenv("B200DQN_HEAD_PUSH")) != 0;
   if (!enabled || !comm_gather_active(n, st)) return false;
   if (out) {
     HeadPush h{};
@@ -169,6 +171,32 @@ int comm_push_planes(b200dqn_net* n, int chan, const void* hi, int64_t lo_off_el
   const char* label = chan == 0 ? "push_h3" : "push_dz4";
   B2_CHECK_CUDA(launch_pdl(k_xpush, dim3(nblk), dim3(kXThreads), 0, st, a, ktrace_slot(label)));
   B2_PROF(label, st);
+  return B200DQN_OK;
+}
+
+// dZ4 rows of every rank into the local gather area in the LL protocol (one kernel on every rank: push + collect);
+// off with B200DQN_DZ_LL=0 (then: plain push + flag wait)
+bool comm_dz4_ll_enabled() {
+  static const bool enabled = !(getenv("B200DQN_DZ_LL") && atoi(getenv("B200DQN_DZ_LL")) == 0);
+  return enabled;
+}
+int comm_gather_dz4_ll(b200dqn_net* n, const void* hi, int64_t lo_off_elems, cudaStream_t st) {
+  B2_REQUIRE(n->xchg_ok && n->d_xbuf && n->x_dzll_lines > 0, B200DQN_ESTATE, "LL gather not initialised");
+  XGatherLL a{};
+  a.src[0] = static_cast<const uint4*>(hi);
+  a.src[1] = reinterpret_cast<const uint4*>(static_cast<const __half*>(hi) + lo_off_elems);
+  a.n16 = int64_t(n->nb) * kHidden * 2 / 16;
+  for (int p = 0; p < n->world; ++p) a.recv[p] = reinterpret_cast<uint4*>(n->xbuf[p] + n->x_dzll_off);
+  a.gather = reinterpret_cast<uint4*>(n->d_xbuf + n->x_dz_off);
+  a.parity16 = n->x_dz_parity / 16;
+  a.lo16 = a.n16 * n->world;
+  a.lines_per_src = n->x_dzll_lines;
+  a.rank = n->rank; a.world = n->world;
+  a.epoch = n->d_xpush_epoch + 1; a.ticket = n->d_xpush_epoch + kXPushChannels + 1; a.err = n->d_xerr;
+  const int nblk = int(std::min<int64_t>(64, std::max<int64_t>(1, (2 * a.n16 + kXThreads - 1) / kXThreads)));
+  NoPdlScope plain;
+  B2_CHECK_CUDA(launch_pdl(k_xgather_ll, dim3(nblk), dim3(kXThreads), 0, st, a, ktrace_slot("gather_dz4")));
+  B2_PROF("gather_dz4", st);
   return B200DQN_OK;
 }
 
@@ -251,7 +279,9 @@ static int xchg_setup(b200dqn_net* n, cudaStream_t ws) {
   n->x_dz_lo = int64_t(W) * n->nb * kHidden;
   n->x_dz_parity = 2 * n->x_dz_lo * 2;
   n->x_dz_off = up(n->x_h3_off + 2 * n->x_h3_parity);
-  const int64_t xbytes = up(n->x_dz_off + 2 * n->x_dz_parity);
+  n->x_dzll_off = up(n->x_dz_off + 2 * n->x_dz_parity);
+  n->x_dzll_lines = 4 * (int64_t(n->nb) * kHidden * 2 / 16);
+  const int64_t xbytes = up(n->x_dzll_off + 2 * int64_t(W) * n->x_dzll_lines * 16);
   if (want) {
     if (cudaMalloc(&n->d_xbuf, xbytes) != cudaSuccess || cudaMemsetAsync(n->d_xbuf, 0, xbytes, ws) != cudaSuccess ||
         cudaIpcGetMemHandle(&mine.handle2, n->d_xbuf) != cudaSuccess) {
@@ -396,9 +426,23 @@ static int xchg_setup(b200dqn_net* n, cudaStream_t ws) {
         for (int64_t i = 0; i < mine_h3 && push_ok; ++i) push_ok = hh[(int64_t(pl) * W + p) * mine_h3 + i] == uint8_t(p + 1);
         for (int64_t i = 0; i < mine_dz && push_ok; ++i) push_ok = hd[(int64_t(pl) * W + p) * mine_dz + i] == uint8_t(p + 1);
       }
+    // the LL gather of dZ4 (second dZ4 epoch -> parity 0 of the plain area)
+    bool gat_ok = true;
+    if (comm_dz4_ll_enabled()) {
+      if ((rc = comm_gather_dz4_ll(n, tmp, mine_dz / 2, ws))) return rc;
+      std::vector<uint8_t> hg(n->x_dz_parity);
+      B2_CHECK_CUDA(cudaMemcpyAsync(hg.data(), n->d_xbuf + n->x_dz_off, hg.size(), cudaMemcpyDeviceToHost, ws));
+      B2_CHECK_CUDA(cudaMemcpyAsync(&err, n->d_xerr, sizeof(err), cudaMemcpyDeviceToHost, ws));
+      B2_CHECK_CUDA(cudaStreamSynchronize(ws));
+      gat_ok = err == 0;
+      for (int pl = 0; pl < 2 && gat_ok; ++pl)
+        for (int p = 0; p < W && gat_ok; ++p)
+          for (int64_t i = 0; i < mine_dz && gat_ok; ++i) gat_ok = hg[(int64_t(pl) * W + p) * mine_dz + i] == uint8_t(p + 1);
+    }
     B2_CHECK_CUDA(cudaMemsetAsync(n->d_g, 0, n->n_params * sizeof(float), ws));
     B2_CHECK_CUDA(cudaStreamSynchronize(ws));
-    if ((rc = agree(ll_ok && push_ok, ll_ok ? "the plane push" : "the LL all-reduce"))) return rc < 0 ? rc : B200DQN_OK;
+    if ((rc = agree(ll_ok && push_ok && gat_ok, !ll_ok ? "the LL all-reduce" : !push_ok ? "the plane push" : "the LL gather")))
+      return rc < 0 ? rc : B200DQN_OK;
   }
   return B200DQN_OK;
 }

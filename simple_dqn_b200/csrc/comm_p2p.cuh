@@ -77,6 +77,22 @@ struct HeadPush {
   const uint32_t* epoch;           // completed dZ4 pushes (the next one uses parity (epoch + 1) & 1)
 };
 
+// dZ4 rows gathered in the LL protocol (k_xgather_ll): no flag word, no system-scope fence on the critical branch
+// (the fence of the plain push costs ~8 us on this part) — every 16-byte unit of this rank's hi/lo rows travels as two
+// LL lines to every peer, the receiver polls its own memory and writes the plain planes fc1_wgrad gathers from.
+struct XGatherLL {
+  const uint4* src[2];       // local hi plane, lo plane (this rank's rows)
+  int64_t n16;               // 16-byte units per plane
+  uint4* recv[kXMaxWorld];   // rank p's LL line area as mapped here
+  uint4* gather;             // LOCAL plain gather area, parity 0
+  int64_t parity16, lo16;    // plain area: units per parity, offset of the lo plane
+  int64_t lines_per_src;     // LL lines per (parity, source) = 4 * n16
+  int rank, world;
+  uint32_t* epoch;           // completed dZ4 gathers (shared with the plain push channel 1)
+  uint32_t* ticket;
+  uint32_t* err;
+};
+
 struct XPeers {
   float4* g[kXMaxWorld];        // rank p's gradient buffer as mapped here ([rank] = the local one)
   uint32_t* flags[kXMaxWorld];  // rank p's flag words
@@ -163,6 +179,15 @@ __device__ __forceinline__ bool ll_wait(const uint4* line, uint32_t e, uint32_t*
   }
   a = b = 0.f;
   return false;
+}
+
+// raw variant: both data words as they are
+__device__ __forceinline__ bool ll_wait_u(const uint4* line, uint32_t e, uint32_t* err, uint32_t& a, uint32_t& b) {
+  float fa, fb;
+  const bool ok = ll_wait(line, e, err, fa, fb);
+  a = __float_as_uint(fa);
+  b = __float_as_uint(fb);
+  return ok;
 }
 
 #endif  // __CUDACC__
@@ -329,6 +354,51 @@ __global__ void __launch_bounds__(kXThreads) k_xpush(XPushArgs a, KTrace kt) {
   kt_end(kt);
 }
 
+// ---- LL all-gather of a hi/lo plane pair (dZ4): push own units as LL lines, poll the peers', write plain planes
+__global__ void __launch_bounds__(kXThreads) k_xgather_ll(XGatherLL a, KTrace kt) {
+  kt_begin(kt);
+  const int t = threadIdx.x;
+  const uint32_t e = *reinterpret_cast<volatile uint32_t*>(a.epoch) + 1;
+  const int64_t par_ll = int64_t(e & 1) * a.world * a.lines_per_src;
+  uint4* plain = a.gather + int64_t(e & 1) * a.parity16;
+  const int64_t stride = int64_t(gridDim.x) * kXThreads;
+  for (int64_t i = int64_t(blockIdx.x) * kXThreads + t; i < 2 * a.n16; i += stride) {
+    const int pl = i >= a.n16 ? 1 : 0;
+    const int64_t j = i - pl * a.n16;
+    const uint4 v = a.src[pl][j];
+    const int64_t line = par_ll + int64_t(a.rank) * a.lines_per_src + 2 * i;
+#pragma unroll
+    for (int p = 0; p < kXMaxWorld; ++p)
+      if (p < a.world && p != a.rank) {
+        st_ll(a.recv[p] + line, v.x, v.y, e);
+        st_ll(a.recv[p] + line + 1, v.z, v.w, e);
+      }
+    plain[pl * a.lo16 + int64_t(a.rank) * a.n16 + j] = v;     // this rank's own rows
+  }
+  for (int64_t i = int64_t(blockIdx.x) * kXThreads + t; i < 2 * a.n16; i += stride) {
+    const int pl = i >= a.n16 ? 1 : 0;
+    const int64_t j = i - pl * a.n16;
+    for (int p = 0; p < a.world; ++p) {
+      if (p == a.rank) continue;
+      const uint4* line = a.recv[a.rank] + par_ll + int64_t(p) * a.lines_per_src + 2 * i;
+      uint4 v;
+      ll_wait_u(line, e, a.err, v.x, v.y);
+      ll_wait_u(line + 1, e, a.err, v.z, v.w);
+      plain[pl * a.lo16 + int64_t(p) * a.n16 + j] = v;
+    }
+  }
+  __syncthreads();
+  if (t == 0) {
+    __threadfence();
+    if (atomicAdd(a.ticket, 1u) == gridDim.x - 1) {
+      *a.ticket = 0;
+      __threadfence();
+      *reinterpret_cast<volatile uint32_t*>(a.epoch) = e;
+    }
+  }
+  kt_end(kt);
+}
+
 // wait until every rank's push of the current epoch has landed here (one block; runs ahead of the consumer).
 // dz_rows > 0: the dZ4 rows come from the peers' head kernels and are COUNTED (HeadPush): wait for
 // dz_rows x (count_epoch + 1) arrivals per source, then advance count_epoch and the dZ4 epoch (the parity selector).
@@ -338,7 +408,7 @@ __global__ void k_xwait(uint32_t* pflags, uint32_t* epoch, int world, uint32_t* 
   const int t = threadIdx.x;
   if (t < world) {
     xwait(pflags + t, *reinterpret_cast<const volatile uint32_t*>(epoch), err);            // channel 0: H3 planes
-  } else if (t < 2 * world) {
+  } else if (t < 2 * world && dz_rows >= 0) {      // dz_rows < 0: the dZ4 rows do not come through this wait at all
     const int p = t - world;
     if (dz_rows == 0)
       xwait(pflags + kXMaxWorld + p, *reinterpret_cast<const volatile uint32_t*>(epoch + 1), err);
@@ -346,7 +416,7 @@ __global__ void k_xwait(uint32_t* pflags, uint32_t* epoch, int world, uint32_t* 
       xwait(pflags + kXCountWord + p, uint32_t(dz_rows) * (*reinterpret_cast<const volatile uint32_t*>(count_epoch) + 1u), err);
   }
   __syncthreads();
-  if (dz_rows && t == 0) {
+  if (dz_rows > 0 && t == 0) {
     count_epoch[0] += 1;
     epoch[1] += 1;
   }

@@ -175,7 +175,7 @@ k_head(const float* __restrict__ part, int splits, int rows, int nets, float* h4
 // chain (the stream of the fc2 optimizer): nothing on the device waits for the scalar.
 __global__ void __launch_bounds__(256)
 k_cost_finish(const float* __restrict__ row_cost, int rows, float* cost_ring, uint32_t* step,
-              volatile uint32_t* host_res, const uint32_t* __restrict__ sampler_words, volatile uint32_t* host_words,
+              volatile uint32_t* host_res, uint32_t* sampler_words, volatile uint32_t* host_words, int bump_samples,
               const KTrace kt) {
   __shared__ float s_c[1024];
   kt_begin(kt);
@@ -189,6 +189,8 @@ k_cost_finish(const float* __restrict__ row_cost, int rows, float* cost_ring, ui
     __syncthreads();
   }
   if (threadIdx.x == 0) {
+    // an index draw fused into conv1 leaves "samplings done" to this kernel: every CTA of conv1 reads the counter
+    if (sampler_words && bump_samples) sampler_words[2] += 1;
     const uint32_t sidx = *step;
     const float cost = tot / float(rows);
     cost_ring[sidx % kCostRing] = cost;
@@ -470,8 +472,9 @@ static int cost_finish_on(b200dqn_net* n, int rows, cudaStream_t s) {
   NoPdlScope plain;
   b200dqn_replay* r = n->step_replay;     // the ring this step samples from (nullptr: host-supplied minibatch)
   B2_CHECK_CUDA(launch_pdl(k_cost_finish, dim3(1), dim3(256), 0, s, (const float*)n->d_rowcost, rows, n->d_cost, n->d_step,
-                           n->h_res, (const uint32_t*)(r ? r->d_words : nullptr),
-                           (volatile uint32_t*)(r ? r->h_words : nullptr), ktrace_slot("cost")));
+                           n->h_res, r ? r->d_words : (uint32_t*)nullptr,
+                           (volatile uint32_t*)(r ? r->h_words : nullptr), n->step_fuse_sample ? 1 : 0,
+                           ktrace_slot("cost")));
   B2_PROF("cost", s);
   return B200DQN_OK;
 }
@@ -580,15 +583,19 @@ static int backward_and_update_gather(b200dqn_net* n, const FrameSource& fs, int
   cudaStream_t sA = n->side[0], sB = n->side[1], sC = n->side[2], sN = n->side[3];
   cudaEvent_t* ev = n->ev;
   // experimental: one launch per conv layer for reduce + LL exchange + RMSProp (umma_opt_conv_xll), off by default
-  static const bool fused_xll = getenv("B200DQN_FUSED_XLL") != nullptr;
+  // one launch per conv layer for reduce + LL exchange + update (umma_opt_conv_xll): default since it was validated on
+  // hardware at W = 2 (tests/test_gpu_multi.py; ~4.5 us per step); B200DQN_FUSED_XLL=0 restores the three launches
+  static const bool fused_xll = !(getenv("B200DQN_FUSED_XLL") && atoi(getenv("B200DQN_FUSED_XLL")) == 0);
   B2_CHECK_CUDA(cudaEventRecord(ev[0], st));                 // head done: dZ4 planes, dW5 partials
   B2_CHECK_CUDA(cudaStreamWaitEvent(sA, ev[0], 0));
   {
     NoPdlScope side;
-    const bool head_pushed = comm_head_push(n, st, nullptr);  // the head kernel already sent this rank's dZ4 rows
-    if (!head_pushed) B2_TRY(umma_push_dz4(n, sA));          // peers' fc1_wgrad wait for these 64 KB
+    const bool head_pushed = comm_head_push(n, st, nullptr);  // (opt-in) the head kernel already sent this rank's dZ4 rows
+    const bool dz_ll = !head_pushed && comm_dz4_ll_enabled();
+    if (dz_ll) B2_TRY(umma_gather_dz4_ll(n, sA));            // all ranks' dZ4 rows, LL protocol: no flag, no system fence
+    else if (!head_pushed) B2_TRY(umma_push_dz4(n, sA));     // peers' fc1_wgrad wait for these 64 KB
     B2_CHECK_CUDA(cudaStreamWaitEvent(sA, ev[14], 0));       // own H3 push (forward, umma_push_h3) has been issued
-    B2_TRY(comm_wait_pushes(n, sA, head_pushed ? rows : 0));
+    B2_TRY(comm_wait_pushes(n, sA, dz_ll ? -1 : head_pushed ? rows : 0));
     B2_TRY(umma_fc1_wgrad_gathered(n, sA));
     // fc2 (8 KB) on the stream the H3 push has left idle: nothing later in the step reads W5
     B2_CHECK_CUDA(cudaStreamWaitEvent(sN, ev[0], 0));
@@ -1327,13 +1334,18 @@ extern "C" int b200dqn_net_train_fused(b200dqn_net* n, b200dqn_replay* r, int ns
       cudaGraph_t graph = nullptr;
       B2_CHECK_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
       const long long launches_before = g_launch_count;
+      const bool fuse = umma_can_fuse_sample(n, r);
       {
         const bool prev = g_pdl_suppressed;
-        if (ktrace_tick(st)) g_pdl_suppressed = true;   // the sampler must not start ahead of the tick
-        rc = launch_sample(r, st);
+        const bool gated = ktrace_tick(st);
+        if (gated) g_pdl_suppressed = true;   // the step's first kernel must not start ahead of the tick
+        if (!fuse) rc = launch_sample(r, st);
         g_pdl_suppressed = prev;
+        n->step_first_no_pdl = fuse && gated;
       }
+      n->step_fuse_sample = fuse;
       if (!rc) rc = train_on_ring(n, r, st);
+      n->step_fuse_sample = n->step_first_no_pdl = false;
       n->graph_launches = int(g_launch_count - launches_before);
       cudaError_t e = cudaStreamEndCapture(st, &graph);
       if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
@@ -1344,13 +1356,19 @@ extern "C" int b200dqn_net_train_fused(b200dqn_net* n, b200dqn_replay* r, int ns
     }
     for (int i = 0; i < nsteps; ++i) B2_CHECK_CUDA(cudaGraphLaunch(n->graph_exec, st));
   } else {
+    const bool fuse = umma_can_fuse_sample(n, r) && st != nullptr && !g_prof_on;
     for (int i = 0; i < nsteps; ++i) {
       const bool prev = g_pdl_suppressed;
-      if (ktrace_tick(st)) g_pdl_suppressed = true;
-      rc = launch_sample(r, st);
+      const bool gated = ktrace_tick(st);
+      if (gated) g_pdl_suppressed = true;
+      if (!fuse) rc = launch_sample(r, st);
       g_pdl_suppressed = prev;
       if (rc) return rc;
-      if ((rc = train_on_ring(n, r, st))) return rc;
+      n->step_fuse_sample = fuse;
+      n->step_first_no_pdl = fuse && gated;
+      rc = train_on_ring(n, r, st);
+      n->step_fuse_sample = n->step_first_no_pdl = false;
+      if (rc) return rc;
     }
   }
   n->train_iterations += nsteps;

@@ -67,6 +67,8 @@ struct b200dqn_net {
   int graph_predict_rows = 0;
   cudaStream_t graph_predict_stream = nullptr;
   b200dqn_replay* step_replay = nullptr;   // set while a step that samples from a ring is being enqueued / captured
+  bool step_fuse_sample = false;           // ... and its index draw happens inside conv1 (conv1_tma.cuh)
+  bool step_first_no_pdl = false;          // the step's first kernel must not start ahead of the trace tick
 
   // unfused-mode staging (host minibatch -> device)
   uint8_t* d_pre = nullptr, *d_post = nullptr, *d_act = nullptr, *d_term = nullptr;
@@ -120,6 +122,7 @@ struct b200dqn_net {
   int64_t x_ll_off = 0, x_ll_lines = 0;               // bytes; LL lines per (parity, source)
   int64_t x_h3_off = 0, x_h3_parity = 0, x_h3_lo = 0;   // bytes; bytes per parity; lo plane offset in elements
   int64_t x_dz_off = 0, x_dz_parity = 0, x_dz_lo = 0;
+  int64_t x_dzll_off = 0, x_dzll_lines = 0;           // LL line area of the dZ4 gather: bytes; lines per (parity, source)
   uint32_t* d_xll_epoch = nullptr;   // [kXChannels] epochs, then [kXChannels] tickets (LL exchange)
   uint32_t* d_xpush_epoch = nullptr; // [kXPushChannels] epochs, then tickets (plane push)
 };

@@ -22,6 +22,7 @@ int umma_target_synced(b200dqn_net* n, cudaStream_t st);    // target <- online
 int umma_forward(b200dqn_net* n, const uint8_t* const src[2], const int32_t* const idx[2], const int shift[2],
                  const int64_t nframes[2], int nets, int rows, cudaStream_t st);
 int umma_fc1_splits(int rows);
+bool umma_can_fuse_sample(const b200dqn_net* n, const b200dqn_replay* r);   // index draw inside conv1 (conv1_tma.cuh)?
 // RMSProp of the fc1 layer + refresh of both of its tile images in one smem-free kernel
 int umma_opt_fc1(b200dqn_net* n, int rows, cudaStream_t st, bool from_g = false);
 int umma_fc1_wgrad_fused(b200dqn_net* n, int rows, cudaStream_t st, bool keep_grads);
@@ -50,10 +51,13 @@ int comm_xll_args(b200dqn_net* n, int layer, XllArgs* out);   // launch argument
 int umma_opt_conv_xll(b200dqn_net* n, int l, int rows, cudaStream_t st, const char* label);   // experimental, fused
 int comm_push_planes(b200dqn_net* n, int chan, const void* hi, int64_t lo_off_elems, cudaStream_t st);
 int comm_wait_pushes(b200dqn_net* n, cudaStream_t st, int dz_rows = 0);   // dz_rows > 0: counted head pushes
+bool comm_dz4_ll_enabled();
+int comm_gather_dz4_ll(b200dqn_net* n, const void* hi, int64_t lo_off_elems, cudaStream_t st);   // LL all-gather of the dZ4 planes
 bool comm_head_push(const b200dqn_net* n, cudaStream_t st, HeadPush* out);   // gather schedule + head-side dZ4 push on?
 // gather schedule hooks of the tcgen05 engine (net_umma.cu)
 int umma_push_h3(b200dqn_net* n, cudaStream_t st);       // after conv3_fwd: rows of the online net's H3 planes
 int umma_push_dz4(b200dqn_net* n, cudaStream_t st);      // after the head
+int umma_gather_dz4_ll(b200dqn_net* n, cudaStream_t st); // after the head: LL all-gather of dZ4 (default)
 int umma_fc1_wgrad_gathered(b200dqn_net* n, cudaStream_t st);   // dW4 over all world x nb rows
 void comm_destroy(b200dqn_net* n);
 

@@ -58,109 +58,28 @@ __global__ void k_add_meta_batch(uint8_t* actions, int64_t* rewards, uint8_t* te
 // state in three dependency-free segments when the position reaches 624 (see
 // oracle/mt19937.py::twist_segmented for the proof-by-test of that formulation).
 // ------------------------------------------------------------------------------------------
-constexpr int kMtN = 624;
-constexpr int kMtM = 397;
-
-__device__ __forceinline__ uint32_t mt_mix(uint32_t cur, uint32_t nxt, uint32_t far) {
-  uint32_t y = (cur & 0x80000000u) | (nxt & 0x7fffffffu);
-  return far ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-}
-
-__device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
-  y ^= (y >> 11);
-  y ^= (y << 7) & 0x9d2c5680u;
-  y ^= (y << 15) & 0xefc60000u;
-  y ^= (y >> 18);
-  return y;
-}
-
 constexpr int kSampleThreads = 256;
 
 __global__ void __launch_bounds__(kSampleThreads, 1)
 k_sample(uint32_t* __restrict__ mt_state, const uint8_t* __restrict__ terminals,
          const int64_t* __restrict__ cursor, int hist, int batch, int32_t* __restrict__ idx_out,
          uint32_t* __restrict__ words_out, const KTrace kt) {
-  __shared__ uint32_t mt[kMtN + 1];
-  __shared__ int warp_cnt[kSampleThreads / 32];
-  __shared__ int s_cut;
+  __shared__ SampleShared sh;
   const int tid = threadIdx.x;
-  const int lane = tid & 31, wid = tid >> 5;
   kt_begin(kt);
   pdl_wait();
   pdl_launch_dependents();
-
-  for (int i = tid; i < kMtN + 1; i += kSampleThreads) mt[i] = mt_state[i];
+  const uint32_t k = words_out[2];                      // samplings done so far: selects the state slot
+  const uint32_t* cur = mt_state + (k & 1u) * kMtSlot;
+  uint32_t* nxt = mt_state + ((k + 1u) & 1u) * kMtSlot;
+  for (int i = tid; i < kMtN + 1; i += kSampleThreads) sh.mt[i] = cur[i];
   __syncthreads();
-
-  const int64_t count = cursor[0], current = cursor[1];
-  const uint32_t n = static_cast<uint32_t>(count - hist);  // width of randrange(hist, count)
-  const int kbits = 32 - __clz(n);                         // n.bit_length(), n >= 1
-  int pos = static_cast<int>(mt[kMtN]);
-  int accepted = 0;
-  uint32_t words = 0;
-
-  while (accepted < batch) {
-    if (pos >= kMtN) {  // genrand_uint32: regenerate the whole key, position 0
-      for (int i = tid; i < 227; i += kSampleThreads) mt[i] = mt_mix(mt[i], mt[i + 1], mt[i + kMtM]);
-      __syncthreads();
-      for (int i = 227 + tid; i < 454; i += kSampleThreads) mt[i] = mt_mix(mt[i], mt[i + 1], mt[i - 227]);
-      __syncthreads();
-      for (int i = 454 + tid; i < 623; i += kSampleThreads) mt[i] = mt_mix(mt[i], mt[i + 1], mt[i - 227]);
-      __syncthreads();
-      if (tid == 0) mt[623] = mt_mix(mt[623], mt[0], mt[396]);
-      __syncthreads();
-      pos = 0;
-    }
-    const int avail = min(kMtN - pos, kSampleThreads);
-    bool ok = false;
-    int index = 0;
-    if (tid < avail) {
-      const uint32_t r = mt_temper(mt[pos + tid]) >> (32 - kbits);
-      if (r < n) {
-        index = hist + static_cast<int>(r);
-        ok = !(index >= current && index - hist < current);  // :61 wraps over the write pointer
-        // :65 episode end — all `hist` bytes are requested at once (no short-circuit: one memory latency, not four)
-        unsigned any = 0;
-        for (int j = 1; j <= hist; ++j) any |= terminals[index - j];
-        ok = ok && any == 0;
-      }
-    }
-    const unsigned ballot = __ballot_sync(0xffffffffu, ok);
-    if (lane == 0) warp_cnt[wid] = __popc(ballot);
-    if (tid == 0) s_cut = -1;
-    __syncthreads();
-    int before = 0, total = 0;
-#pragma unroll
-    for (int wi = 0; wi < kSampleThreads / 32; ++wi) {
-      const int c = warp_cnt[wi];
-      if (wi < wid) before += c;
-      total += c;
-    }
-    const int rank = accepted + before + __popc(ballot & ((1u << lane) - 1u));
-    if (ok && rank < batch) {
-      idx_out[rank] = index;
-      if (rank == batch - 1) s_cut = tid;  // the word that completed the minibatch
-    }
-    __syncthreads();
-    if (accepted + total >= batch) {
-      const int used = s_cut + 1;
-      pos += used;
-      words += used;
-      accepted = batch;
-    } else {
-      accepted += total;
-      pos += avail;
-      words += avail;
-    }
-    __syncthreads();
-  }
-  if (tid == 0) mt[kMtN] = static_cast<uint32_t>(pos);
-  __syncthreads();
-  for (int i = tid; i < kMtN + 1; i += kSampleThreads) mt_state[i] = mt[i];
+  const uint32_t words = sample_block(sh, terminals, cursor[0], cursor[1], hist, batch, idx_out, tid, kSampleThreads);
+  for (int i = tid; i < kMtN + 1; i += kSampleThreads) nxt[i] = sh.mt[i];
   if (tid == 0) {
     words_out[0] = words;
     words_out[1] += words;
-    words_out[2] += 1;            // samplings completed
+    words_out[2] = k + 1;         // samplings completed
   }
   kt_end(kt);
 }
@@ -212,7 +131,7 @@ int replay_set_rng_async(b200dqn_replay* r, const uint32_t* key624, uint32_t pos
   uint32_t* pin = r->h_mt + size_t(slot) * 640;
   memcpy(pin, key624, 624 * sizeof(uint32_t));
   pin[624] = pos;
-  B2_CHECK_CUDA(cudaMemcpyAsync(r->d_mt, pin, 625 * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+  B2_CHECK_CUDA(cudaMemcpyAsync(r->mt_slot_ptr(), pin, 625 * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
   B2_CHECK_CUDA(cudaEventRecord(r->mt_done[slot], st));
   r->rng_set = true;
   return B200DQN_OK;
@@ -314,7 +233,7 @@ extern "C" int b200dqn_replay_create(int device, int64_t size, int screen_h, int
   B2_CHECK_CUDA(cudaMalloc(&r->d_rewards, size * sizeof(int64_t)));
   B2_CHECK_CUDA(cudaMalloc(&r->d_terminals, size));
   B2_CHECK_CUDA(cudaMalloc(&r->d_cursor, 2 * sizeof(int64_t)));
-  B2_CHECK_CUDA(cudaMalloc(&r->d_mt, 625 * sizeof(uint32_t)));
+  B2_CHECK_CUDA(cudaMalloc(&r->d_mt, 2 * 640 * sizeof(uint32_t)));
   B2_CHECK_CUDA(cudaMalloc(&r->d_idx, batch_size * sizeof(int32_t)));
   B2_CHECK_CUDA(cudaMalloc(&r->d_words, 4 * sizeof(uint32_t)));
   B2_CHECK_CUDA(cudaMalloc(&r->d_pre, state_bytes));
@@ -328,7 +247,7 @@ extern "C" int b200dqn_replay_create(int device, int64_t size, int screen_h, int
   B2_CHECK_CUDA(cudaMemset(r->d_rewards, 0, size * sizeof(int64_t)));
   B2_CHECK_CUDA(cudaMemset(r->d_terminals, 0, size));
   B2_CHECK_CUDA(cudaMemset(r->d_cursor, 0, 2 * sizeof(int64_t)));
-  B2_CHECK_CUDA(cudaMemset(r->d_mt, 0, 625 * sizeof(uint32_t)));
+  B2_CHECK_CUDA(cudaMemset(r->d_mt, 0, 2 * 640 * sizeof(uint32_t)));
   B2_CHECK_CUDA(cudaMemset(r->d_idx, 0, batch_size * sizeof(int32_t)));
   B2_CHECK_CUDA(cudaMemset(r->d_words, 0, 4 * sizeof(uint32_t)));
   B2_CHECK_CUDA(cudaMallocHost(&r->h_stage, size_t(b200dqn_replay::kSlots) * r->frame_bytes));
@@ -463,7 +382,7 @@ extern "C" int b200dqn_replay_set_rng(b200dqn_replay* r, const uint32_t host_mt6
   B2_REQUIRE(host_mt625[624] <= 624, B200DQN_EINVAL, "replay_set_rng: MT19937 position %u > 624", host_mt625[624]);
   DeviceGuard g(r->device);
   cudaStream_t st = as_stream(stream);
-  B2_CHECK_CUDA(cudaMemcpyAsync(r->d_mt, host_mt625, 625 * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+  B2_CHECK_CUDA(cudaMemcpyAsync(r->mt_slot_ptr(), host_mt625, 625 * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
   B2_CHECK_CUDA(cudaStreamSynchronize(st));
   r->rng_set = true;
   return B200DQN_OK;
@@ -480,7 +399,7 @@ extern "C" int b200dqn_replay_get_rng(b200dqn_replay* r, uint32_t host_mt625[625
   B2_REQUIRE(r && host_mt625, B200DQN_EINVAL, "replay_get_rng: null argument");
   DeviceGuard g(r->device);
   cudaStream_t st = as_stream(stream);
-  B2_CHECK_CUDA(cudaMemcpyAsync(host_mt625, r->d_mt, 625 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  B2_CHECK_CUDA(cudaMemcpyAsync(host_mt625, r->mt_slot_ptr(), 625 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   B2_CHECK_CUDA(cudaStreamSynchronize(st));
   return B200DQN_OK;
 }
@@ -573,7 +492,7 @@ extern "C" int b200dqn_replay_device_ptr(b200dqn_replay* r, int which, void** de
     case B200DQN_PTR_MB_TERMINALS: p = r->d_mb_terminals; b = r->batch; break;
     case B200DQN_PTR_INDEXES: p = r->d_idx; b = r->batch * sizeof(int32_t); break;
     case B200DQN_PTR_WORDS_CONSUMED: p = r->d_words; b = 2 * sizeof(uint32_t); break;
-    case B200DQN_PTR_MT_STATE: p = r->d_mt; b = 625 * sizeof(uint32_t); break;
+    case B200DQN_PTR_MT_STATE: p = r->mt_slot_ptr(); b = 625 * sizeof(uint32_t); break;
     default: B2_REQUIRE(false, B200DQN_EINVAL, "replay_device_ptr: unknown selector %d", which);
   }
   *dev_ptr = p;
