@@ -20,7 +20,6 @@
 #pragma once
 #include <cuda.h>
 
-#include "replay.cuh"
 #include "umma2.cuh"
 
 namespace b200 {
@@ -54,18 +53,7 @@ struct Params {
   __half* out16[2];          // hi planes
   int64_t lo_off;            // lo plane = hi + lo_off (elements)
   uint8_t* im2col;           // online network's A tiles [rows * 4][4][16 KB] (nullptr = off)
-  // fused index draw (ring train step): every CTA runs the sampling loop of getMinibatch itself — the random
-  // index draw, the validity mask and the frame gather are ONE kernel; CTA 0 leaves the advanced MT19937 state,
-  // the index list and the word count for the rest of the step
-  int fuse_sample;
-  uint32_t* mt_state;        // [2][kMtSlot], slot = samplings done & 1
-  uint32_t* words;           // [0] words of this draw, [1] running total, [2] samplings done (bumped by the cost kernel)
-  const uint8_t* terminals;
-  const int64_t* cursor;     // {count, current}
-  int hist, gbatch, my_first;   // global minibatch size; first sample of this rank inside it
-  int32_t* idx_out;          // [gbatch]
 };
-constexpr int kMaxFusedBatch = 2048;   // index list lives in the (idle) third stage during the draw
 
 __device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const CUtensorMap* map, int c0, int c1, int c2,
                                             uint64_t* bar) {
@@ -142,33 +130,10 @@ k_conv1_tma(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CU
     if (nboxes == 2) tma_prefetch_desc(&map1);
     for (int j = 0; j < kRing && j < nslots; ++j) fetch_weights(j);
   }
-  pdl_wait();   // the sampled indexes (or, fused, the ring contents and the MT state) come from the predecessors
-  __shared__ int s_frame;
-  if (p.fuse_sample) {
-    // scratch = the A tile of stage 2, idle until slot 2 is converted (its weight tiles sit behind it)
-    SampleShared& sh = *reinterpret_cast<SampleShared*>(smem_gen + 2 * kStage);
-    int32_t* s_idx = reinterpret_cast<int32_t*>(smem_gen + 2 * kStage + 4096);
-    const uint32_t k = p.words[2];
-    const uint32_t* cur = p.mt_state + (k & 1u) * kMtSlot;
-    for (int i = tid; i < kMtN + 1; i += blockDim.x) sh.mt[i] = cur[i];
-    __syncthreads();
-    const uint32_t words = sample_block(sh, p.terminals, p.cursor[0], p.cursor[1], p.hist, p.gbatch, s_idx, tid,
-                                        int(blockDim.x));
-    if (blockIdx.x == 0) {
-      uint32_t* nxt = p.mt_state + ((k + 1u) & 1u) * kMtSlot;
-      for (int i = tid; i < kMtN + 1; i += blockDim.x) nxt[i] = sh.mt[i];
-      for (int i = tid; i < p.gbatch; i += blockDim.x) p.idx_out[i] = s_idx[i];
-      if (tid == 0) {
-        p.words[0] = words;
-        p.words[1] += words;
-      }
-    }
-    if (tid == 0) s_frame = s_idx[p.my_first + n] + p.shift[0];
-    __syncthreads();
-  }
+  pdl_wait();   // the sampled indexes come from the predecessor
   if (tid == 0) {
     for (int b = 0; b < nboxes; ++b) {
-      const int frame = p.fuse_sample ? s_frame : p.idx[b][n] + p.shift[b];
+      const int frame = p.idx[b][n] + p.shift[b];
       mbar_arrive_expect_tx(&s_box[b], uint32_t(box_frames) * kFrameBoxBytes);
       tma_load_3d(box_base + b * kBoxStride, b ? &map1 : &map0, 0, t * 5, frame, &s_box[b]);
     }

@@ -175,7 +175,7 @@ k_head(const float* __restrict__ part, int splits, int rows, int nets, float* h4
 // chain (the stream of the fc2 optimizer): nothing on the device waits for the scalar.
 __global__ void __launch_bounds__(256)
 k_cost_finish(const float* __restrict__ row_cost, int rows, float* cost_ring, uint32_t* step,
-              volatile uint32_t* host_res, uint32_t* sampler_words, volatile uint32_t* host_words, int bump_samples,
+              volatile uint32_t* host_res, const uint32_t* __restrict__ sampler_words, volatile uint32_t* host_words,
               const KTrace kt) {
   __shared__ float s_c[1024];
   kt_begin(kt);
@@ -189,8 +189,6 @@ k_cost_finish(const float* __restrict__ row_cost, int rows, float* cost_ring, ui
     __syncthreads();
   }
   if (threadIdx.x == 0) {
-    // an index draw fused into conv1 leaves "samplings done" to this kernel: every CTA of conv1 reads the counter
-    if (sampler_words && bump_samples) sampler_words[2] += 1;
     const uint32_t sidx = *step;
     const float cost = tot / float(rows);
     cost_ring[sidx % kCostRing] = cost;
@@ -472,9 +470,8 @@ static int cost_finish_on(b200dqn_net* n, int rows, cudaStream_t s) {
   NoPdlScope plain;
   b200dqn_replay* r = n->step_replay;     // the ring this step samples from (nullptr: host-supplied minibatch)
   B2_CHECK_CUDA(launch_pdl(k_cost_finish, dim3(1), dim3(256), 0, s, (const float*)n->d_rowcost, rows, n->d_cost, n->d_step,
-                           n->h_res, r ? r->d_words : (uint32_t*)nullptr,
-                           (volatile uint32_t*)(r ? r->h_words : nullptr), n->step_fuse_sample ? 1 : 0,
-                           ktrace_slot("cost")));
+                           n->h_res, (const uint32_t*)(r ? r->d_words : nullptr),
+                           (volatile uint32_t*)(r ? r->h_words : nullptr), ktrace_slot("cost")));
   B2_PROF("cost", s);
   return B200DQN_OK;
 }
@@ -1334,18 +1331,13 @@ extern "C" int b200dqn_net_train_fused(b200dqn_net* n, b200dqn_replay* r, int ns
       cudaGraph_t graph = nullptr;
       B2_CHECK_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
       const long long launches_before = g_launch_count;
-      const bool fuse = umma_can_fuse_sample(n, r);
       {
         const bool prev = g_pdl_suppressed;
-        const bool gated = ktrace_tick(st);
-        if (gated) g_pdl_suppressed = true;   // the step's first kernel must not start ahead of the tick
-        if (!fuse) rc = launch_sample(r, st);
+        if (ktrace_tick(st)) g_pdl_suppressed = true;   // the sampler must not start ahead of the tick
+        rc = launch_sample(r, st);
         g_pdl_suppressed = prev;
-        n->step_first_no_pdl = fuse && gated;
       }
-      n->step_fuse_sample = fuse;
       if (!rc) rc = train_on_ring(n, r, st);
-      n->step_fuse_sample = n->step_first_no_pdl = false;
       n->graph_launches = int(g_launch_count - launches_before);
       cudaError_t e = cudaStreamEndCapture(st, &graph);
       if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
@@ -1356,19 +1348,13 @@ extern "C" int b200dqn_net_train_fused(b200dqn_net* n, b200dqn_replay* r, int ns
     }
     for (int i = 0; i < nsteps; ++i) B2_CHECK_CUDA(cudaGraphLaunch(n->graph_exec, st));
   } else {
-    const bool fuse = umma_can_fuse_sample(n, r) && st != nullptr && !g_prof_on;
     for (int i = 0; i < nsteps; ++i) {
       const bool prev = g_pdl_suppressed;
-      const bool gated = ktrace_tick(st);
-      if (gated) g_pdl_suppressed = true;
-      if (!fuse) rc = launch_sample(r, st);
+      if (ktrace_tick(st)) g_pdl_suppressed = true;
+      rc = launch_sample(r, st);
       g_pdl_suppressed = prev;
       if (rc) return rc;
-      n->step_fuse_sample = fuse;
-      n->step_first_no_pdl = fuse && gated;
-      rc = train_on_ring(n, r, st);
-      n->step_fuse_sample = n->step_first_no_pdl = false;
-      if (rc) return rc;
+      if ((rc = train_on_ring(n, r, st))) return rc;
     }
   }
   n->train_iterations += nsteps;

@@ -67,8 +67,6 @@ struct b200dqn_net {
   int graph_predict_rows = 0;
   cudaStream_t graph_predict_stream = nullptr;
   b200dqn_replay* step_replay = nullptr;   // set while a step that samples from a ring is being enqueued / captured
-  bool step_fuse_sample = false;           // ... and its index draw happens inside conv1 (conv1_tma.cuh)
-  bool step_first_no_pdl = false;          // the step's first kernel must not start ahead of the trace tick
 
   // unfused-mode staging (host minibatch -> device)
   uint8_t* d_pre = nullptr, *d_post = nullptr, *d_act = nullptr, *d_term = nullptr;

@@ -754,13 +754,6 @@ constexpr int kUWgradKb = 4;      // minimum k-blocks (of 64 pixels) per wgrad s
 static const bool g_conv1_tma = !(getenv("B200DQN_CONV1") && strcmp(getenv("B200DQN_CONV1"), "ldg") == 0);
 static inline int conv1_pixels_padded(int rows) { return g_conv1_tma ? rows * conv1tma::kTilesPerSample * 128 : rows * kP1 * kP1; }
 
-// the index draw of getMinibatch inside the first conv kernel (north_star: "a single kernel does the random index
-// draw, validity mask and 4-frame gather"): tcgen05 engine + TMA conv1, B200DQN_FUSE_SAMPLE=0 keeps k_sample
-bool umma_can_fuse_sample(const b200dqn_net* n, const b200dqn_replay* r) {
-  static const bool enabled = !(getenv("B200DQN_FUSE_SAMPLE") && atoi(getenv("B200DQN_FUSE_SAMPLE")) == 0);
-  return enabled && g_conv1_tma && n->cfg.math_mode == B200DQN_MATH_TCGEN05 && r->batch <= conv1tma::kMaxFusedBatch;
-}
-
 int umma_wgrad_kb(int layer, int rows) {
   const int kred = layer == 0 ? conv1_pixels_padded(rows) : layer == 1 ? rows * kP2 * kP2 : rows * kP3 * kP3;
   const int kbs = (kred + 63) / 64;
@@ -871,13 +864,6 @@ int umma_forward(b200dqn_net* n, const uint8_t* const src[2], const int32_t* con
     p.out[1] = nullptr;                       // nothing reads the target network's fp32 H1
     p.shared5 = shared5 ? 1 : 0; p.nets = nets; p.rows = rows; p.lo_off = u->h_elems[0];
     p.im2col = (nets == 2 && rows == n->nb) ? u->im2col1 : nullptr;
-    if (n->step_fuse_sample && shared5 && n->step_replay) {
-      b200dqn_replay* r = n->step_replay;
-      p.fuse_sample = 1;
-      p.mt_state = r->d_mt; p.words = r->d_words; p.terminals = r->d_terminals; p.cursor = r->d_cursor;
-      p.hist = r->hist; p.gbatch = r->batch; p.my_first = n->rank * n->nb; p.idx_out = r->d_idx;
-    }
-    B2_REQUIRE(!n->step_fuse_sample || p.fuse_sample, B200DQN_ESTATE, "fused index draw without a ring step");
     CUtensorMap m0, m1;
     const int64_t nframes0 = nframes[0], nframes1 = nframes[1];
     if ((rc = conv1tma::make_frame_map(&m0, src[0], nframes0, shared5 ? kHist + 1 : kHist))) return rc;
@@ -889,14 +875,8 @@ int umma_forward(b200dqn_net* n, const uint8_t* const src[2], const int32_t* con
       configured = true;
     }
     const uint32_t smem = conv1tma::smem_bytes((nets == 2 && !shared5) ? 2 : 1);
-    {
-      const bool prev = g_pdl_suppressed;
-      if (n->step_first_no_pdl) g_pdl_suppressed = true;
-      const cudaError_t e = launch_pdl(conv1tma::k_conv1_tma, dim3(rows * conv1tma::kTilesPerSample),
-                                       dim3(umma2::kThreads2), smem, st, m0, m1, p, ktrace_slot("conv1_fwd"));
-      g_pdl_suppressed = prev;
-      B2_CHECK_CUDA(e);
-    }
+    B2_CHECK_CUDA(launch_pdl(conv1tma::k_conv1_tma, dim3(rows * conv1tma::kTilesPerSample), dim3(umma2::kThreads2),
+                             smem, st, m0, m1, p, ktrace_slot("conv1_fwd")));
     B2_PROF("conv1_fwd", st);
   } else {
     V2Conv1Fwd p;

@@ -22,7 +22,6 @@ int umma_target_synced(b200dqn_net* n, cudaStream_t st);    // target <- online
 int umma_forward(b200dqn_net* n, const uint8_t* const src[2], const int32_t* const idx[2], const int shift[2],
                  const int64_t nframes[2], int nets, int rows, cudaStream_t st);
 int umma_fc1_splits(int rows);
-bool umma_can_fuse_sample(const b200dqn_net* n, const b200dqn_replay* r);   // index draw inside conv1 (conv1_tma.cuh)?
 // RMSProp of the fc1 layer + refresh of both of its tile images in one smem-free kernel
 int umma_opt_fc1(b200dqn_net* n, int rows, cudaStream_t st, bool from_g = false);
 int umma_fc1_wgrad_fused(b200dqn_net* n, int rows, cudaStream_t st, bool keep_grads);
