@@ -33,7 +33,8 @@ def _run(env_extra, port, world=2):
     env = dict(os.environ, **env_extra)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
            "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tools", "mgpu_check.py")]
-    p = subprocess.run(cmd, env=env, cwd=ROOT, capture_output=True, text=True, timeout=420)
+    p = subprocess.run(cmd, env=env, cwd=ROOT, capture_output=True, text=True,
+                       timeout=int(os.environ.get("B200DQN_TEST_TIMEOUT", "420")))
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
     return p.stdout
 
@@ -41,8 +42,9 @@ def _run(env_extra, port, world=2):
 @pytest.mark.gpu
 @pytest.mark.skipif(_gpus() < 2, reason="needs two GPUs")
 @pytest.mark.parametrize("world", WORLDS)
-@pytest.mark.parametrize("env", [{}, {"B200DQN_FUSED_XLL": "1"}, {"B200DQN_P2P_SCHED": "layer"}, {"B200DQN_COMM": "nccl"}],
-                         ids=["p2p-gather", "p2p-gather-fused-conv-exchange", "p2p-two-shot", "nccl"])
+@pytest.mark.parametrize("env", [{}, {"B200DQN_FUSED_XLL": "0", "B200DQN_DZ_LL": "0"}, {"B200DQN_P2P_SCHED": "layer"},
+                                 {"B200DQN_COMM": "nccl"}],
+                         ids=["p2p-gather", "p2p-gather-unfused-exchange-plain-push", "p2p-two-shot", "nccl"])
 def test_ranks_stay_identical(env, world):
     out = _run(env, 29610 + world, world)
     assert "ranks diverged" not in out
@@ -57,8 +59,9 @@ def test_ranks_stay_identical(env, world):
 @pytest.mark.gpu
 @pytest.mark.skipif(_gpus() < 2, reason="needs two GPUs")
 @pytest.mark.parametrize("world", WORLDS)
-@pytest.mark.parametrize("env", [{}, {"B200DQN_FUSED_XLL": "1"}, {"B200DQN_P2P_SCHED": "layer"}, {"B200DQN_COMM": "nccl"}],
-                         ids=["p2p-gather", "p2p-gather-fused-conv-exchange", "p2p-two-shot", "nccl"])
+@pytest.mark.parametrize("env", [{}, {"B200DQN_FUSED_XLL": "0", "B200DQN_DZ_LL": "0"}, {"B200DQN_P2P_SCHED": "layer"},
+                                 {"B200DQN_COMM": "nccl"}],
+                         ids=["p2p-gather", "p2p-gather-unfused-exchange-plain-push", "p2p-two-shot", "nccl"])
 def test_n_ranks_equal_the_oracle_at_the_global_batch(env, world):
     """W ranks x 32 samples are ONE step of the single-process reference at batch_size = W * 32 —
     the global minibatch indexes bit for bit (same MT19937 stream), the weights after 3 steps within the
@@ -81,7 +84,8 @@ def test_gather_gradients_match_nccl():
         rows = re.findall(r"\[rank (\d) [^\]]*\] layer (\d) grad crc ([0-9a-f]{8})  sum (\S+)  abs (\S+)", out)
         assert len(rows) == 10, out[-2000:]
         return {(int(r), int(l)): (crc, float(s), float(a)) for r, l, crc, s, a in rows}
-    g, n = grads({}, 29611), grads({"B200DQN_COMM": "nccl"}, 29612)
+    # the per-layer LL all-reduce kernel (k_xll) leaves the reduced gradient in d_g; the default fused kernel does not
+    g, n = grads({"B200DQN_FUSED_XLL": "0"}, 29611), grads({"B200DQN_COMM": "nccl"}, 29612)
     for l in range(5):
         assert g[(0, l)] == g[(1, l)], "ranks disagree on layer %d" % l
         if l != 3:

@@ -13,13 +13,16 @@ if [ "$N" = "2" ]; then
   TIMELINE=1 B200DQN_FUSED_XLL=0 timeout -s KILL 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29703 tools/mgpu_check.py > $O/timeline_w2_unfusedxll.txt 2>&1
   timeout -s KILL 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29704 bench.py --gpus 2 --steps 1000 --warmup 50 > $O/bench_n2.json 2> $O/bench_n2.err
 else
-  B200DQN_TEST_WORLDS=8 timeout -s KILL 900 python -m pytest tests/test_gpu_multi.py -m gpu -q --maxfail=20 -k "oracle" > $O/pytest_multi_w8.log 2>&1; echo "rc=$?" >> $O/pytest_multi_w8.log
-  B200DQN_TEST_WORLDS=4 timeout -s KILL 400 python -m pytest tests/test_gpu_multi.py -m gpu -q --maxfail=20 -k "oracle and p2p-gather and not fused" > $O/pytest_multi_w4.log 2>&1; echo "rc=$?" >> $O/pytest_multi_w4.log
-  for W in 4 8; do
-    TIMELINE=1 timeout -s KILL 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node $W --master-addr 127.0.0.1 --master-port 2971$W tools/mgpu_check.py > $O/timeline_w$W.txt 2>&1
-  done
-  for W in 2 4 8; do
-    timeout -s KILL 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $W --master-addr 127.0.0.1 --master-port 2972$W bench.py --gpus $W --steps 1000 --warmup 50 > $O/bench_n$W.json 2> $O/bench_n$W.err
-  done
+  # 8-GPU box: charged 8x — most important first, every step under a hard cap
+  export B200DQN_TEST_TIMEOUT=150
+  B200DQN_TEST_WORLDS=8 timeout -s KILL 170 python -m pytest tests/test_gpu_multi.py -m gpu -q -k "oracle and p2p-gather and not unfused" > $O/pytest_w8_default.log 2>&1; echo "rc=$?" >> $O/pytest_w8_default.log
+  TIMELINE=1 timeout -s KILL 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29718 tools/mgpu_check.py > $O/timeline_w8.txt 2>&1
+  timeout -s KILL 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29728 bench.py --gpus 8 --steps 1000 --warmup 50 > $O/bench_n8.json 2> $O/bench_n8.err
+  B200DQN_TEST_WORLDS=4 timeout -s KILL 170 python -m pytest tests/test_gpu_multi.py -m gpu -q -k "oracle and p2p-gather and not unfused" > $O/pytest_w4_default.log 2>&1; echo "rc=$?" >> $O/pytest_w4_default.log
+  TIMELINE=1 timeout -s KILL 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29714 tools/mgpu_check.py > $O/timeline_w4.txt 2>&1
+  timeout -s KILL 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29724 bench.py --gpus 4 --steps 1000 --warmup 50 > $O/bench_n4.json 2> $O/bench_n4.err
+  timeout -s KILL 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29722 bench.py --gpus 2 --steps 1000 --warmup 50 > $O/bench_n2.json 2> $O/bench_n2.err
+  timeout -s KILL 200 python bench.py --gpus 1 --steps 1000 --warmup 50 --no-cpu > $O/bench_n1.json 2> $O/bench_n1.err
+  B200DQN_TEST_WORLDS=8 timeout -s KILL 330 python -m pytest tests/test_gpu_multi.py -m gpu -q -k "oracle and (nccl or two-shot or unfused)" > $O/pytest_w8_others.log 2>&1; echo "rc=$?" >> $O/pytest_w8_others.log
 fi
 echo done
