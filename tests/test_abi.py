@@ -84,3 +84,23 @@ def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(L, "LIB_PATH", "/nonexistent/libb200dqn.so")
     with pytest.raises(ImportError, match="no CPU fallback"):
         L.load()
+
+
+def test_argument_errors_surface_before_any_device_work():
+    """Argument validation of the C-ABI happens ahead of the first CUDA call, so it can be exercised without a GPU:
+    a ring smaller than the 8-frame ingestion bank (the deferred flush may wrap at most once) and an
+    unknown optimizer / math mode are EINVAL -> AssertionError, the reference's error convention."""
+    import ctypes as C
+
+    import pytest
+
+    from simple_dqn_b200 import _lib as L
+    h = C.c_void_p()
+    with pytest.raises(AssertionError):
+        L.call("b200dqn_replay_create", 0, 4, 84, 84, 4, 32, C.byref(h))
+    cfg = L.NetConfig()
+    L.call("b200dqn_net_config_default", C.byref(cfg), 4)
+    assert cfg.optimizer == L.OPT_RMSPROP and cfg.batch_size == 32
+    cfg.optimizer = 7
+    with pytest.raises(AssertionError):
+        L.call("b200dqn_net_create", 0, C.byref(cfg), C.byref(h))

@@ -146,3 +146,31 @@ def test_state_buffer_matches_reference_golden_and_oracle():
     assert not buf.buffer.any()
     with pytest.raises(AssertionError):
         buf.add(np.zeros((3, 3), np.uint8))
+
+
+def test_stale_device_handle_and_out_of_range_action_are_rejected():
+    """a DeviceMinibatch that was overwritten by a later draw must not silently train on the newer
+    indexes, and an action >= num_actions in the ring (the reference would raise IndexError at
+    deepqnetwork.py:141) must surface as an error instead of an out-of-bounds read."""
+    from simple_dqn_b200 import DeepQNetwork, ReplayMemory, Stream
+    st = Stream()
+    ring = ReplayOracle(600, batch_size=32)
+    synthetic_ring(ring, seed=3, block=50, terminal_p=0.01, num_actions=4)
+    mem = ReplayMemory(600, make_args(), rng="device", device_minibatch=True, stream=st)
+    mem.add_batch(ring.actions, ring.rewards, ring.screens, ring.terminals)
+    mem.set_cursor(ring.count, ring.current)
+    net = DeepQNetwork(4, make_args(), math_mode="tcgen05", stream=st)
+    net.callback = type("CB", (), {"on_train": staticmethod(lambda c: None)})()
+    random.seed(3)
+    first = mem.getMinibatch()
+    second = mem.getMinibatch()
+    with pytest.raises(AssertionError):
+        net.train(first, 0)                      # overwritten by `second`
+    net.train(second, 0)                         # the current handle trains
+    bad = ring.actions.copy()
+    bad[:] = 9                                   # every action out of range for A = 4
+    mem2 = ReplayMemory(600, make_args(), rng="device", device_minibatch=True, stream=st)
+    mem2.add_batch(bad, ring.rewards, ring.screens, ring.terminals)
+    mem2.set_cursor(ring.count, ring.current)
+    with pytest.raises(AssertionError):
+        net.train(mem2.getMinibatch(), 0)
