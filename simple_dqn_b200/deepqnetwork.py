@@ -246,6 +246,39 @@ class DeepQNetwork:
         mem._sample_ticket += nsteps
         mem._host_state_in_sync = None        # the device stream ran ahead of the host's `random`
 
+    def step_host(self, mem, actions, rewards, screens, terminals, train_repeat=1):
+        """agent.py:102-114 for a caller that owns the loop, as ONE library call: the (action, reward, screen,
+        terminal) of the env steps since the last train are appended to `mem`, then `train_repeat` x
+        (mem.getMinibatch(); self.train(...)) run on the device.  With ``mem.rng_mode == "python"`` the process-global
+        `random` stays in lock-step (state up if it moved, words consumed back).  Returns the costs (float32 array)
+        and delivers them to ``callback.on_train`` in order, like the reference's per-train callback."""
+        n = len(actions)
+        a = np.ascontiguousarray(actions, dtype=np.uint8)
+        r = np.ascontiguousarray(rewards, dtype=np.int64)
+        s = np.ascontiguousarray(screens, dtype=np.uint8)
+        t = np.ascontiguousarray(terminals, dtype=np.uint8)
+        assert s.shape == (n,) + tuple(mem.dims) and a.shape == r.shape == t.shape == (n,)
+        costs = np.zeros(max(train_repeat, 1), dtype=np.float32)
+        words = C.c_uint32()
+        lockstep = mem.rng_mode == "python"
+        key, pos = mem._host_upload_args() if (lockstep and train_repeat) else (None, 0)
+        if not lockstep and not mem._rng_on_device:
+            mem.seed_device_rng()
+        L.call("b200dqn_net_step_host", self._h, mem._h, n, L.np_ptr(a), L.np_ptr(r), L.np_ptr(s), L.np_ptr(t),
+               int(train_repeat), key, pos, L.np_ptr(costs) if train_repeat else None,
+               C.byref(words) if (lockstep and train_repeat) else None, self._stream)
+        if train_repeat:
+            mem._sample_ticket += train_repeat
+            if lockstep:
+                mem._host_advance(words.value)
+            else:
+                mem._host_state_in_sync = None
+            for c in costs[:train_repeat]:
+                self.train_iterations += 1
+                if self.callback:
+                    self.callback.on_train(np.float32(c))
+        return costs[:train_repeat]
+
     def last_costs(self, count=1):
         out = np.empty(count, dtype=np.float32)
         L.call("b200dqn_net_read_costs", self._h, int(count), L.np_ptr(out), self._stream)

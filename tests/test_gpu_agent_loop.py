@@ -97,3 +97,38 @@ def test_host_minibatch_and_device_handle_paths_agree(mode):
     agent_rows = np.setdiff1d(np.arange(len(ta["q_rows"])), np.array(sa, dtype=np.int64))
     assert (ta["q_rows"][agent_rows] == tb["q_rows"][agent_rows]).all()
     assert all((a == b).all() for a, b in zip(wa, wb))
+
+
+def test_step_host_equals_the_separate_calls():
+    """b200dqn_net_step_host (frames of the env steps + train_repeat x (sample, train) in one call) does exactly what
+    4 x mem.add + train_repeat x (getMinibatch, train) does: same costs, same weights, same `random` position."""
+    import random
+    spec = CASES["pong_repeat2"]
+    cfg = AL.loop_config(**spec["cfg"])
+    rs = np.random.RandomState(5)
+    frames = rs.randint(0, 256, (60, 84, 84)).astype(np.uint8)
+    acts = rs.randint(0, 6, 60).astype(np.uint8)
+    rews = rs.randint(-2, 3, 60).astype(np.int64)
+    terms = (rs.rand(60) < 0.05)
+    out = []
+    for one_call in (False, True):
+        mem, net, _ = _product(cfg, 6, "tcgen05", device_minibatch=True)
+        costs = []
+        net.callback = type("CB", (), {"on_train": staticmethod(costs.append)})()
+        mem.add_batch(acts[:40], rews[:40], frames[:40], terms[:40])
+        random.seed(99)
+        for k in range(5):
+            lo = 40 + 4 * k
+            random.random()                               # the agent draws between trains (agent.py:50)
+            if one_call:
+                net.step_host(mem, acts[lo:lo + 4], rews[lo:lo + 4], frames[lo:lo + 4], terms[lo:lo + 4], train_repeat=2)
+            else:
+                for j in range(lo, lo + 4):
+                    mem.add(int(acts[j]), int(rews[j]), frames[j], bool(terms[j]))
+                for _ in range(2):
+                    net.train(mem.getMinibatch(), 0)
+        out.append((np.array(costs, np.float32), net.get_weights(with_states=False), random.getstate(), mem.count, mem.current))
+    (ca, wa, ra, na, cura), (cb, wb, rb, nb_, curb) = out
+    assert len(ca) == len(cb) == 10 and (ca == cb).all()
+    assert all((x == y).all() for x, y in zip(wa, wb))
+    assert ra == rb and (na, cura) == (nb_, curb)
