@@ -617,10 +617,74 @@ k_opt_fc1(const float* __restrict__ dw, float* __restrict__ w, float* __restrict
   kt_end(kt);
 }
 
+// fc1 optimizer, one pass for everything: a CTA owns a [64 flat indexes x 64 hidden units] block of W4 — exactly one
+// k-block of the column-oriented (forward) tile image and one 128-byte row segment of the row-oriented (dgrad)
+// image.  Phase 1 (thread <-> 8 consecutive hidden units of one flat index): the configured update on W/S in place +
+// the dgrad-image chunk; the new weights are parked in shared memory.  Phase 2 (thread <-> 8 consecutive flat
+// indexes of one hidden unit): the forward-image chunk, read column-wise from the parked block.  Replaces
+// k_opt_fc1 + k_pack_image<PackFc1Fwd>: W4 is not re-read (6.4 MB less L2 traffic per step) and one launch less on
+// the branch that forms the tail of the data-parallel step.
+__global__ void __launch_bounds__(256)
+k_opt_fc1_both(const float* __restrict__ dw, float* __restrict__ w, float* __restrict__ sst, uint8_t* __restrict__ img_dgr,
+               uint8_t* __restrict__ img_fwd, const OptArgs opt, const KTrace kt) {
+  constexpr int kT = 64, kPitch = kT + 1;
+  __shared__ float tile[kT * kPitch];
+  kt_begin(kt);
+  pdl_wait();
+  pdl_launch_dependents();
+  const float l_step = opt_step_scalar(opt);
+  const int tid = threadIdx.x;
+  constexpr int kTilesN = kHidden / kT, kTilesM = kFlat / kT;
+  for (int tl = blockIdx.x; tl < kTilesM * kTilesN; tl += gridDim.x) {
+    const int m0 = (tl / kTilesN) * kT, n0 = (tl % kTilesN) * kT;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int ml = (tid >> 3) + 32 * i, nl = (tid & 7) * 8;
+      const int m = m0 + ml, nn = n0 + nl;
+      const int64_t e = int64_t(m) * kHidden + nn;
+      float g[8], wv[8];
+      ld8(dw + e, g);
+      opt_update_vec<8>(opt, l_step, g, wv, w + e, sst + e);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) tile[ml * kPitch + nl + j] = wv[j];
+      uint4 hi, lo;
+      umma::split8(wv, hi, lo);
+      uint8_t* base = img_dgr + (int64_t(m / 128) * (kHidden / 64) + nn / 64) * (128 * 256) +
+                      umma::sw128_off(m % 128, (nn % 64) / 8);
+      *reinterpret_cast<uint4*>(base) = hi;
+      *reinterpret_cast<uint4*>(base + 128 * 128) = lo;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int nl = tid & 63, c = (tid >> 6) + 4 * i;      // hidden unit, 8-wide chunk of the k-block
+      float wv[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) wv[j] = tile[(c * 8 + j) * kPitch + nl];
+      uint4 hi, lo;
+      umma::split8(wv, hi, lo);
+      const int nn = n0 + nl;
+      uint8_t* base = img_fwd + (int64_t(nn / 128) * (kFlat / 64) + m0 / 64) * (128 * 256) + umma::sw128_off(nn % 128, c);
+      *reinterpret_cast<uint4*>(base) = hi;
+      *reinterpret_cast<uint4*>(base + 128 * 128) = lo;
+    }
+    __syncthreads();
+  }
+  kt_end(kt);
+}
+
 int umma_opt_fc1(b200dqn_net* n, int rows, cudaStream_t st, bool from_g) {
   UmmaState* u = ust(n);
   const LayerTable& lt = n->lt;
   const float* dw = from_g ? n->d_g + lt.off[3] : n->d_part + lt.part_off[3];
+  static const bool one_pass = getenv("B200DQN_OPT_FC1_ONEPASS") && atoi(getenv("B200DQN_OPT_FC1_ONEPASS")) != 0;
+  if (one_pass) {
+    B2_CHECK_CUDA(launch_pdl(k_opt_fc1_both, dim3(2 * n->sm_count), dim3(256), 0, st, dw, n->d_w + lt.off[3],
+                             n->d_s + lt.off[3], u->img_dgr[0], u->img_fwd[0][3], make_opt_args(n, rows),
+                             ktrace_slot("opt_fc1")));
+    B2_PROF("opt_fc1", st);
+    return B200DQN_OK;
+  }
   // capped grid (CTAs per SM, grid-stride): the kernel shares the SMs — and the L2 — with the dgrad chain
   static const int per_sm = getenv("B200DQN_OPT_FC1_CTAS") ? atoi(getenv("B200DQN_OPT_FC1_CTAS")) : 2;
   const int ctas = per_sm > 0 ? per_sm * n->sm_count : n->sm_count / (-per_sm > 0 ? -per_sm : 1);
