@@ -180,7 +180,7 @@ bool comm_dz4_ll_enabled() {
   static const bool enabled = !(getenv("B200DQN_DZ_LL") && atoi(getenv("B200DQN_DZ_LL")) == 0);
   return enabled;
 }
-int comm_gather_dz4_ll(b200dqn_net* n, const void* hi, int64_t lo_off_elems, cudaStream_t st) {
+int comm_gather_dz4_ll(b200dqn_net* n, const void* hi, int64_t lo_off_elems, cudaStream_t st, bool wait_h3) {
   B2_REQUIRE(n->xchg_ok && n->d_xbuf && n->x_dzll_lines > 0, B200DQN_ESTATE, "LL gather not initialised");
   XGatherLL a{};
   a.src[0] = static_cast<const uint4*>(hi);
@@ -193,6 +193,8 @@ int comm_gather_dz4_ll(b200dqn_net* n, const void* hi, int64_t lo_off_elems, cud
   a.lines_per_src = n->x_dzll_lines;
   a.rank = n->rank; a.world = n->world;
   a.epoch = n->d_xpush_epoch + 1; a.ticket = n->d_xpush_epoch + kXPushChannels + 1; a.err = n->d_xerr;
+  a.h3_flags = wait_h3 ? reinterpret_cast<const uint32_t*>(n->d_xbuf) : nullptr;
+  a.h3_epoch = n->d_xpush_epoch;
   const int nblk = int(std::min<int64_t>(64, std::max<int64_t>(1, (2 * a.n16 + kXThreads - 1) / kXThreads)));
   NoPdlScope plain;
   B2_CHECK_CUDA(launch_pdl(k_xgather_ll, dim3(nblk), dim3(kXThreads), 0, st, a, ktrace_slot("gather_dz4")));
@@ -429,7 +431,7 @@ static int xchg_setup(b200dqn_net* n, cudaStream_t ws) {
     // the LL gather of dZ4 (second dZ4 epoch -> parity 0 of the plain area)
     bool gat_ok = true;
     if (comm_dz4_ll_enabled()) {
-      if ((rc = comm_gather_dz4_ll(n, tmp, mine_dz / 2, ws))) return rc;
+      if ((rc = comm_gather_dz4_ll(n, tmp, mine_dz / 2, ws, true))) return rc;
       std::vector<uint8_t> hg(n->x_dz_parity);
       B2_CHECK_CUDA(cudaMemcpyAsync(hg.data(), n->d_xbuf + n->x_dz_off, hg.size(), cudaMemcpyDeviceToHost, ws));
       B2_CHECK_CUDA(cudaMemcpyAsync(&err, n->d_xerr, sizeof(err), cudaMemcpyDeviceToHost, ws));

@@ -91,6 +91,10 @@ struct XGatherLL {
   uint32_t* epoch;           // completed dZ4 gathers (shared with the plain push channel 1)
   uint32_t* ticket;
   uint32_t* err;
+  // the H3 rows (plain push, channel 0) must have landed as well before fc1_wgrad may start: their flags are polled
+  // here, so that no separate wait kernel sits between this one and the consumer
+  const uint32_t* h3_flags;  // [kXMaxWorld] local push flags of channel 0 (nullptr: do not wait)
+  const uint32_t* h3_epoch;  // completed H3 pushes of this rank (= the epoch every peer's flag must have reached)
 };
 
 struct XPeers {
@@ -387,6 +391,7 @@ __global__ void __launch_bounds__(kXThreads) k_xgather_ll(XGatherLL a, KTrace kt
       plain[pl * a.lo16 + int64_t(p) * a.n16 + j] = v;
     }
   }
+  if (a.h3_flags && t < a.world) xwait(a.h3_flags + t, *reinterpret_cast<const volatile uint32_t*>(a.h3_epoch), a.err);
   __syncthreads();
   if (t == 0) {
     __threadfence();

@@ -589,10 +589,14 @@ static int backward_and_update_gather(b200dqn_net* n, const FrameSource& fs, int
     NoPdlScope side;
     const bool head_pushed = comm_head_push(n, st, nullptr);  // (opt-in) the head kernel already sent this rank's dZ4 rows
     const bool dz_ll = !head_pushed && comm_dz4_ll_enabled();
-    if (dz_ll) B2_TRY(umma_gather_dz4_ll(n, sA));            // all ranks' dZ4 rows, LL protocol: no flag, no system fence
-    else if (!head_pushed) B2_TRY(umma_push_dz4(n, sA));     // peers' fc1_wgrad wait for these 64 KB
     B2_CHECK_CUDA(cudaStreamWaitEvent(sA, ev[14], 0));       // own H3 push (forward, umma_push_h3) has been issued
-    B2_TRY(comm_wait_pushes(n, sA, dz_ll ? -1 : head_pushed ? rows : 0));
+    if (dz_ll) {
+      // all ranks' dZ4 rows in the LL protocol (no flag word, no system fence); the same kernel polls the H3 flags
+      B2_TRY(umma_gather_dz4_ll(n, sA));
+    } else {
+      if (!head_pushed) B2_TRY(umma_push_dz4(n, sA));        // peers' fc1_wgrad wait for these 64 KB
+      B2_TRY(comm_wait_pushes(n, sA, head_pushed ? rows : 0));
+    }
     B2_TRY(umma_fc1_wgrad_gathered(n, sA));
     // fc2 (8 KB) on the stream the H3 push has left idle: nothing later in the step reads W5
     B2_CHECK_CUDA(cudaStreamWaitEvent(sN, ev[0], 0));

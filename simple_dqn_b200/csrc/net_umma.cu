@@ -1077,7 +1077,7 @@ int umma_push_dz4(b200dqn_net* n, cudaStream_t st) {
 }
 int umma_gather_dz4_ll(b200dqn_net* n, cudaStream_t st) {
   UmmaState* u = ust(n);
-  return comm_gather_dz4_ll(n, u->dz16[0], u->dz_elems[0], st);
+  return comm_gather_dz4_ll(n, u->dz16[0], u->dz_elems[0], st, true);   // also waits for the peers' H3 rows
 }
 int umma_fc1_wgrad_gathered(b200dqn_net* n, cudaStream_t st) {
   WFc1WgradGather p{reinterpret_cast<const __half*>(n->d_xbuf + n->x_h3_off),

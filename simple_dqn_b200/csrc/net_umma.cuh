@@ -51,7 +51,7 @@ int umma_opt_conv_xll(b200dqn_net* n, int l, int rows, cudaStream_t st, const ch
 int comm_push_planes(b200dqn_net* n, int chan, const void* hi, int64_t lo_off_elems, cudaStream_t st);
 int comm_wait_pushes(b200dqn_net* n, cudaStream_t st, int dz_rows = 0);   // dz_rows > 0: counted head pushes
 bool comm_dz4_ll_enabled();
-int comm_gather_dz4_ll(b200dqn_net* n, const void* hi, int64_t lo_off_elems, cudaStream_t st);   // LL all-gather of the dZ4 planes
+int comm_gather_dz4_ll(b200dqn_net* n, const void* hi, int64_t lo_off_elems, cudaStream_t st, bool wait_h3);   // LL all-gather of the dZ4 planes
 bool comm_head_push(const b200dqn_net* n, cudaStream_t st, HeadPush* out);   // gather schedule + head-side dZ4 push on?
 // gather schedule hooks of the tcgen05 engine (net_umma.cu)
 int umma_push_h3(b200dqn_net* n, cudaStream_t st);       // after conv3_fwd: rows of the online net's H3 planes
