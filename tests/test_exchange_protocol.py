@@ -7,8 +7,11 @@ arbitrary interleavings of W ranks, which a 2-GPU box cannot enumerate:
 * k_xll (one-shot LL all-reduce): every line carries {data, epoch}; receive areas are double-buffered by the parity
   of the layer's epoch; a receiver accepts a line only when its flag EQUALS the epoch it expects; the layer is the
   channel (a line's flags only ever carry its own layer's epoch sequence).
-* k_xpush / k_xwait (plane gather for fc1_wgrad): gather areas double-buffered by the parity of the push epoch, one
-  monotonic flag per (channel, source); the consumer waits for flag >= its own epoch.
+* k_xpush / k_xwait (plane gather of H3 for fc1_wgrad): gather areas double-buffered by the parity of the push epoch,
+  one monotonic flag per (channel, source); the consumer waits for flag >= its own epoch.
+* k_xgather_ll (round 2: the dZ4 rows): the same LL lines as k_xll on a channel of their own, but the receiver STORES
+  each source's payload instead of adding it; its known-answer test at comm_init runs on the same channel, so the
+  epoch sequence of a line never repeats.
 
 Ranks are generators that yield before every shared-memory access; a seeded scheduler picks who moves next.  A rank
 finishes all exchanges of step s before it starts step s + 1 (stream order of the captured step), and the exchanges
@@ -19,6 +22,7 @@ import random
 import pytest
 
 LAYERS = (0, 1, 2, 4)          # LL channels (fc1 = 3 is gathered, not reduced)
+DZ = 6                         # LL channel of the dZ4 all-gather
 PARITY_MASK = [1]              # 1: receive areas double-buffered by epoch parity (the design); 0: single buffer
 
 
@@ -26,7 +30,7 @@ class World:
     def __init__(self, W):
         self.W = W
         # LL receive areas: [rank][parity][src][layer] -> (payload, flag)
-        self.ll = [[[{l: (None, 0) for l in LAYERS} for _ in range(W)] for _ in range(2)] for _ in range(W)]
+        self.ll = [[[{l: (None, 0) for l in LAYERS + (DZ,)} for _ in range(W)] for _ in range(2)] for _ in range(W)]
         # gather areas: [rank][chan][parity][src] -> payload; push flags: [rank][chan][src]
         self.gat = [[[[None] * W for _ in range(2)] for _ in range(2)] for _ in range(W)]
         self.pflag = [[[0] * W for _ in range(2)] for _ in range(W)]
@@ -68,9 +72,9 @@ def push(w, r, chan, epoch_of, payload):
     epoch_of[chan] = e
 
 
-def wait_and_read(w, r, epoch_of):
+def wait_and_read(w, r, epoch_of, chans=(0, 1)):
     out = []
-    for chan in (0, 1):
+    for chan in chans:
         e = epoch_of[chan]
         for p in range(w.W):
             while True:
@@ -83,7 +87,7 @@ def wait_and_read(w, r, epoch_of):
 
 def rank_program(w, r, steps, rng, kat_chan_of, errors):
     ll_epoch, push_epoch = {}, {0: 0, 1: 0}
-    for c in set(LAYERS) | {5}:
+    for c in set(LAYERS) | {5, DZ}:
         ll_epoch[c] = 0
     # comm_init known-answer tests
     for l in LAYERS:
@@ -93,14 +97,21 @@ def rank_program(w, r, steps, rng, kat_chan_of, errors):
     yield from push(w, r, 0, push_epoch, ("kat", r))
     yield from push(w, r, 1, push_epoch, ("kat", r))
     yield from wait_and_read(w, r, push_epoch)
+    got = yield from ll_exchange(w, r, DZ, ll_epoch, ("katdz", r))
+    if got != [("katdz", p) for p in range(w.W)]:
+        errors.append(("kat-dz", r, got))
     for s in range(1, steps + 1):
         # H3 push early in the step, dZ4 push after the head, then the consumer; LL layers in any order
         yield from push(w, r, 0, push_epoch, ("h3", s, r))
-        yield from push(w, r, 1, push_epoch, ("dz4", s, r))
         order = list(LAYERS)
         rng.shuffle(order)
         pending = [ll_exchange(w, r, l, ll_epoch, ("g", s, l, r)) for l in order]
-        pending.append(wait_and_read(w, r, push_epoch))
+
+        def fc1_branch():          # dZ4 all-gather in LL lines, H3 flags polled by the same kernel
+            dz = yield from ll_exchange(w, r, DZ, ll_epoch, ("dz4", s, r))
+            (h3,) = yield from wait_and_read(w, r, push_epoch, chans=(0,))
+            return h3, dz
+        pending.append(fc1_branch())
         results = {}
         live = list(range(len(pending)))
         while live:                            # branches of one step advance independently
