@@ -11,8 +11,11 @@ A = 4, terminals ~ Bernoulli(0.005), random.seed(1), Xavier weights (RandomState
 
 N > 1 is launched by the driver through torch.distributed.run (one rank per GPU, NCCL).  Rank 0
 prints ONE JSON line.  `value` times the fused device path with inputs resident in HBM; `e2e`
-times the public drop-in API from HOST buffers (frames appended with mem.add, RNG state uploaded,
-cost read back) — see DESIGN.md §Measurement.
+times the public drop-in classes from HOST buffers (frames appended with mem.add, the host `random`
+kept in lock-step, cost delivered to the callback inside train()); `roofline` comes from the in-graph
+%globaltimer timeline of the production graph (208 profiled steps regardless of --steps) with the
+replay-gather HBM fraction and the conv-stack tensor fraction as first-class fields;
+`predict_latency` times the agent's action selection — see DESIGN.md §6.
 """
 import argparse
 import json

@@ -128,7 +128,8 @@ int b200dqn_replay_set_rng_parts(b200dqn_replay* r, const uint32_t* host_key624,
  * tests (:61, :65) and keeps the first `batch` accepted indexes in acceptance order.
  * Results stay on the device (B200DQN_PTR_INDEXES, B200DQN_PTR_WORDS_CONSUMED). */
 int b200dqn_replay_sample(b200dqn_replay* r, void* stream);
-/* Same, and returns how many MT19937 words the draw consumed (synchronises): the host keeps its own
+/* Same, and returns how many MT19937 words the draw consumed (waits for the sampler only, by polling a host-mapped
+ * word — no memcpy, no stream synchronisation): the host keeps its own
  * `random` in lock-step by discarding that many 32-bit words instead of downloading the 2.5 KB state. */
 int b200dqn_replay_sample_sync(b200dqn_replay* r, uint32_t* host_words_consumed, void* stream);
 /* Test hook: bypass the sampler and use caller-chosen indexes (host int32[batch]). */
@@ -246,7 +247,8 @@ int b200dqn_net_train_fused(b200dqn_net* n, b200dqn_replay* r, int nsteps, void*
  * _set_indexes): the `net.train(mem.getMinibatch())` pair of agent.py:112-114 when getMinibatch
  * returned a device handle.  Frames are read in place from the ring.  Asynchronous. */
 int b200dqn_net_train_sampled(b200dqn_net* n, b200dqn_replay* r, void* stream);
-/* Same, then copies cost[0,0] of this step to host_cost (4-byte D2H; synchronises) for the
+/* Same, then returns cost[0,0] of this step in host_cost (written to host-mapped memory by the step's cost kernel; the
+ * call polls that word: no memcpy, no stream synchronisation — the rest of the step may still be running) for the
  * `callback.on_train(cost)` of src/deepqnetwork.py:171-172. */
 int b200dqn_net_train_sampled_cost(b200dqn_net* n, b200dqn_replay* r, float* host_cost, void* stream);
 /* src/agent.py:102-114 as ONE call, for a caller that drives the loop itself (one host->device hop per train step):
