@@ -250,8 +250,27 @@ __global__ void __launch_bounds__(kThreads2, 1) k_umma2(const P p, const int tra
         brow[i] = p.b_row(z, n0 + (P::kBRowMajorThreads ? (id >> 3) : (id % BN)));
       }
     }
-    // Everything above (TMEM alloc, barrier init, the gather index tables) overlapped the previous kernel
-    // of the chain; only from here on do we touch its outputs.  (The MMA warp never reads global memory.)
+    // Weight tile images do not depend on the predecessor kernel (they were refreshed by the PREVIOUS step's
+    // optimizer, long finished): the TMA bulk copies of the first S k-blocks are issued ahead of the dependency
+    // wait, so that for the weight-heavy kernels (fc1 forward / dgrad: 32 KB of image per k-block) the first
+    // stages are already full when the activations may be touched.
+    if constexpr (kAnyBulk) {
+      if (tid == 0) {
+#pragma unroll
+        for (int j = 0; j < S; ++j) {
+          if (j < nkb) {
+            uint8_t* st_gen = smem_gen + j * C::kStageBytes;
+            mbar_arrive_expect_tx(&s_full[j], kBulkBytes);
+            if constexpr (P::kAMode == kBulk)
+              tma_bulk_g2s(st_gen, p.a_tile(z, mtile, kb0 + j), 2 * C::kABytes, &s_full[j]);
+            if constexpr (P::kBMode == kBulk)
+              tma_bulk_g2s(st_gen + C::kAStage, p.b_tile(z, blockIdx.y, kb0 + j), 2 * C::kBBytes, &s_full[j]);
+          }
+        }
+      }
+    }
+    // Everything above (TMEM alloc, barrier init, the gather index tables, the first weight tiles) overlapped the
+    // previous kernel of the chain; only from here on do we touch its outputs.  (The MMA warp never reads global memory.)
     pdl_wait();
     // kReg operands: per-row source pointers, once per kernel (they may depend on upstream data — the
     // sampled indexes — so they are built after the wait, but not again for every k-block)
@@ -283,7 +302,7 @@ __global__ void __launch_bounds__(kThreads2, 1) k_umma2(const P p, const int tra
       const uint32_t st_addr = smem_base + s * C::kStageBytes;
       uint8_t* st_gen = smem_gen + s * C::kStageBytes;
       const uint32_t a_hi = st_addr, a_lo = st_addr + C::kABytes, b_hi = st_addr + C::kAStage, b_lo = b_hi + C::kBBytes;
-      if (kAnyBulk && tid == 0) {
+      if (kAnyBulk && tid == 0 && j >= S) {   // the first S k-blocks' images were requested before the dependency wait
         mbar_arrive_expect_tx(&s_full[s], kBulkBytes);
         if constexpr (P::kAMode == kBulk)
           tma_bulk_g2s(st_gen, p.a_tile(z, mtile, kb), 2 * C::kABytes, &s_full[s]);
