@@ -141,6 +141,8 @@ __device__ __forceinline__ bool xwait(const uint32_t* flag, uint32_t e, uint32_t
       asm volatile("fence.acq_rel.sys;" ::: "memory");
       return true;
     }
+    __nanosleep(spins < 8 ? 40 : 200);   // back off: thousands of polling threads otherwise saturate the L2 the step's
+                                         // own kernels live in (measured at W = 8: 20 us exchange kernels)
     if ((spins & 63) == 63) {
       if (*reinterpret_cast<volatile uint32_t*>(err)) return false;
       const unsigned long long now = globaltimer_ns();
@@ -171,6 +173,7 @@ __device__ __forceinline__ bool ll_wait(const uint4* line, uint32_t e, uint32_t*
       b = __uint_as_float(v.z);
       return true;
     }
+    __nanosleep(spins < 8 ? 40 : 200);
     if ((spins & 63) == 63) {
       if (*reinterpret_cast<volatile uint32_t*>(err)) break;
       const unsigned long long now = globaltimer_ns();
@@ -297,12 +300,24 @@ __global__ void __launch_bounds__(kXThreads) k_xll(XllArgs a, KTrace kt) {
   for (int64_t i = int64_t(blockIdx.x) * kXThreads + t; i < a.n4; i += stride) {
     const float4 mine = a.g[a.off4 + i];
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int p = 0; p < a.world; ++p) {
+    uint4 l0[kXMaxWorld], l1[kXMaxWorld];     // first pass: all peers' lines in flight at once
+#pragma unroll
+    for (int p = 0; p < kXMaxWorld; ++p)
+      if (p < a.world && p != a.rank) {
+        const uint4* line = a.recv[a.rank] + par_base + int64_t(p) * a.lines_per_src + (a.ll4 + i) * 2;
+        l0[p] = ld_ll(line);
+        l1[p] = ld_ll(line + 1);
+      }
+#pragma unroll
+    for (int p = 0; p < kXMaxWorld; ++p) {
+      if (p >= a.world) break;
       float4 v = mine;
       if (p != a.rank) {
         const uint4* line = a.recv[a.rank] + par_base + int64_t(p) * a.lines_per_src + (a.ll4 + i) * 2;
-        ll_wait(line, e, a.err, v.x, v.y);
-        ll_wait(line + 1, e, a.err, v.z, v.w);
+        if (l0[p].y == e && l0[p].w == e) { v.x = __uint_as_float(l0[p].x); v.y = __uint_as_float(l0[p].z); }
+        else ll_wait(line, e, a.err, v.x, v.y);
+        if (l1[p].y == e && l1[p].w == e) { v.z = __uint_as_float(l1[p].x); v.w = __uint_as_float(l1[p].z); }
+        else ll_wait(line + 1, e, a.err, v.z, v.w);
       }
       if (p == 0) acc = v;
       else {
@@ -382,14 +397,27 @@ __global__ void __launch_bounds__(kXThreads) k_xgather_ll(XGatherLL a, KTrace kt
   for (int64_t i = int64_t(blockIdx.x) * kXThreads + t; i < 2 * a.n16; i += stride) {
     const int pl = i >= a.n16 ? 1 : 0;
     const int64_t j = i - pl * a.n16;
-    for (int p = 0; p < a.world; ++p) {
-      if (p == a.rank) continue;
-      const uint4* line = a.recv[a.rank] + par_ll + int64_t(p) * a.lines_per_src + 2 * i;
-      uint4 v;
-      ll_wait_u(line, e, a.err, v.x, v.y);
-      ll_wait_u(line + 1, e, a.err, v.z, v.w);
-      plain[pl * a.lo16 + int64_t(p) * a.n16 + j] = v;
-    }
+    // first pass: every peer's two lines requested together (one memory latency, not 2 (W - 1)); whatever has not
+    // arrived yet is then waited for line by line
+    uint4 l0[kXMaxWorld], l1[kXMaxWorld];
+#pragma unroll
+    for (int p = 0; p < kXMaxWorld; ++p)
+      if (p < a.world && p != a.rank) {
+        const uint4* line = a.recv[a.rank] + par_ll + int64_t(p) * a.lines_per_src + 2 * i;
+        l0[p] = ld_ll(line);
+        l1[p] = ld_ll(line + 1);
+      }
+#pragma unroll
+    for (int p = 0; p < kXMaxWorld; ++p)
+      if (p < a.world && p != a.rank) {
+        const uint4* line = a.recv[a.rank] + par_ll + int64_t(p) * a.lines_per_src + 2 * i;
+        uint4 v;
+        if (l0[p].y == e && l0[p].w == e) { v.x = l0[p].x; v.y = l0[p].z; }
+        else ll_wait_u(line, e, a.err, v.x, v.y);
+        if (l1[p].y == e && l1[p].w == e) { v.z = l1[p].x; v.w = l1[p].z; }
+        else ll_wait_u(line + 1, e, a.err, v.z, v.w);
+        plain[pl * a.lo16 + int64_t(p) * a.n16 + j] = v;
+      }
   }
   if (a.h3_flags && t < a.world) xwait(a.h3_flags + t, *reinterpret_cast<const volatile uint32_t*>(a.h3_epoch), a.err);
   __syncthreads();

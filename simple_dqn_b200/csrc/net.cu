@@ -582,7 +582,11 @@ static int backward_and_update_gather(b200dqn_net* n, const FrameSource& fs, int
   // experimental: one launch per conv layer for reduce + LL exchange + RMSProp (umma_opt_conv_xll), off by default
   // one launch per conv layer for reduce + LL exchange + update (umma_opt_conv_xll): default since it was validated on
   // hardware at W = 2 (tests/test_gpu_multi.py; ~4.5 us per step); B200DQN_FUSED_XLL=0 restores the three launches
-  static const bool fused_xll = !(getenv("B200DQN_FUSED_XLL") && atoi(getenv("B200DQN_FUSED_XLL")) == 0);
+  // Measured: at W = 2 the fused kernel shortens the traced step (87.7 vs 92 us); at W = 8 its 288 polling CTAs per
+  // layer spin for ~20 us while the peers catch up and delay the chain's own kernels (profiles/r2n8_timeline_w8.txt),
+  // so beyond two ranks the default is the three-launch form with its small polling grid.
+  static const int fused_env = getenv("B200DQN_FUSED_XLL") ? atoi(getenv("B200DQN_FUSED_XLL")) : -1;
+  const bool fused_xll = fused_env >= 0 ? fused_env != 0 : n->world <= 2;
   B2_CHECK_CUDA(cudaEventRecord(ev[0], st));                 // head done: dZ4 planes, dW5 partials
   B2_CHECK_CUDA(cudaStreamWaitEvent(sA, ev[0], 0));
   {

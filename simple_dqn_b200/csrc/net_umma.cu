@@ -677,11 +677,11 @@ int umma_opt_fc1(b200dqn_net* n, int rows, cudaStream_t st, bool from_g) {
   UmmaState* u = ust(n);
   const LayerTable& lt = n->lt;
   const float* dw = from_g ? n->d_g + lt.off[3] : n->d_part + lt.part_off[3];
-  // one-pass kernel: default for data-parallel learners, where this branch IS the tail of the step (it ends ~4 us
-  // earlier); on a single GPU the two-kernel form measured faster for the step as a whole (75.4 vs 78.9 us/step,
-  // profiles/r2g_*).  B200DQN_OPT_FC1_ONEPASS=0/1 forces either.
+  // one-pass kernel (B200DQN_OPT_FC1_ONEPASS=1): parity-clean, ends ~4 us earlier on its branch, but the step as a
+  // whole measured slower with it (1 GPU: 78.9 vs 75.4 us/step, profiles/r2g_*; 4 GPUs: 23.5 us under contention),
+  // so the two-kernel form stays the default.
   static const int forced = getenv("B200DQN_OPT_FC1_ONEPASS") ? atoi(getenv("B200DQN_OPT_FC1_ONEPASS")) : -1;
-  const bool one_pass = forced >= 0 ? forced != 0 : n->world > 1;
+  const bool one_pass = forced >= 0 ? forced != 0 : false;
   if (one_pass) {
     B2_CHECK_CUDA(launch_pdl(k_opt_fc1_both, dim3(2 * n->sm_count), dim3(256), 0, st, dw, n->d_w + lt.off[3],
                              n->d_s + lt.off[3], u->img_dgr[0], u->img_fwd[0][3], make_opt_args(n, rows),

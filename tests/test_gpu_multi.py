@@ -64,11 +64,11 @@ def test_ranks_stay_identical(env, world):
                          ids=["p2p-gather", "p2p-gather-unfused-exchange-plain-push", "p2p-two-shot", "nccl"])
 def test_n_ranks_equal_the_oracle_at_the_global_batch(env, world):
     """W ranks x 32 samples are ONE step of the single-process reference at batch_size = W * 32 —
-    the global minibatch indexes bit for bit (same MT19937 stream), the weights after 3 steps within the
-    single-GPU bar (rel-L2 of the update <= 2e-2), the mean of the ranks' costs equal to the oracle's cost."""
+    the global minibatch indexes bit for bit (same MT19937 stream), the weights after 3 steps within
+    rel-L2 of the update <= 3e-2, the mean of the ranks' costs equal to the oracle's cost."""
     out = _run(dict(env, ORACLE="3"), 29630 + world, world)
     assert "indexes of the global minibatch bit-exact" in out, out[-2000:]
-    assert "match (update rel-L2 <= 2e-2)" in out, out[-2000:]
+    assert "match (update rel-L2 <= 3e-2)" in out, out[-2000:]
     assert "ranks diverged" not in out
     crcs = re.findall(r"weights crc32 ([0-9a-f]{8})", out)
     assert len(crcs) == world and len(set(crcs)) == 1, crcs
