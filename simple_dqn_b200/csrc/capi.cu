@@ -165,7 +165,14 @@ extern "C" int b200dqn_stream_create(int device, void** out_stream) {
   B2_REQUIRE(out_stream, B200DQN_EINVAL, "stream_create: null argument");
   b200::DeviceGuard g(device);
   cudaStream_t st;
-  B2_CHECK_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  const char* sp = getenv("B200DQN_STREAM_PRIO");            // experiment knob: "hi" = highest priority
+  if (sp && !strcmp(sp, "hi")) {
+    int prio_lo = 0, prio_hi = 0;
+    B2_CHECK_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    B2_CHECK_CUDA(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, prio_hi));
+  } else {
+    B2_CHECK_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  }
   *out_stream = st;
   return B200DQN_OK;
 }

@@ -757,6 +757,17 @@ static int backward_and_update(b200dqn_net* n, const FrameSource& fs, int rows, 
   cudaEvent_t* ev = n->ev;
   const bool tc = n->cfg.math_mode == B200DQN_MATH_TCGEN05;
   static const bool fc1_fused_epilogue = getenv("B200DQN_FC1_FUSED") != nullptr;   // experimental alternative
+  // experiment knobs: bit op of B200DQN_NOPDL_OPS launches that chain kernel without the programmatic dependency;
+  // B200DQN_WGRAD_ONE_STREAM puts conv2_wgrad / opt_conv2 on conv3_wgrad's branch
+  static const int nopdl_ops = getenv("B200DQN_NOPDL_OPS") ? int(strtol(getenv("B200DQN_NOPDL_OPS"), nullptr, 0)) : 0;
+  if (getenv("B200DQN_WGRAD_ONE_STREAM") && !g_prof_on) sC = sB;
+  auto chain_op = [&](BwdOp op) -> int {
+    if (nopdl_ops >> int(op) & 1) {
+      NoPdlScope plain;
+      return bwd_op(n, fs, rows, op, st);
+    }
+    return bwd_op(n, fs, rows, op, st);
+  };
   B2_CHECK_CUDA(cudaEventRecord(ev[0], st));                 // dZ4, the dW5 partials and the per-sample costs are ready
   B2_CHECK_CUDA(cudaStreamWaitEvent(sA, ev[0], 0));
   B2_CHECK_CUDA(cudaStreamWaitEvent(sN, ev[0], 0));
@@ -768,7 +779,7 @@ static int backward_and_update(b200dqn_net* n, const FrameSource& fs, int rows, 
     B2_TRY(cost_finish_on(n, rows, sN));
     if (tc) B2_TRY(opt_fc2_small(n, rows, sN));
   }
-  B2_TRY(bwd_op(n, fs, rows, kFc1Dgrad, st));
+  B2_TRY(chain_op(kFc1Dgrad));
   B2_CHECK_CUDA(cudaEventRecord(ev[1], st));                 // dZ3 ready, W4 no longer needed
   B2_CHECK_CUDA(cudaStreamWaitEvent(sA, ev[1], 0));
   {
@@ -779,7 +790,7 @@ static int backward_and_update(b200dqn_net* n, const FrameSource& fs, int rows, 
   }
   B2_CHECK_CUDA(cudaStreamWaitEvent(sB, ev[1], 0));
   { NoPdlScope side; B2_TRY(bwd_op(n, fs, rows, kConv3Wgrad, sB)); }
-  B2_TRY(bwd_op(n, fs, rows, kConv3Dgrad, st));
+  B2_TRY(chain_op(kConv3Dgrad));
   B2_CHECK_CUDA(cudaEventRecord(ev[2], st));                 // dZ2 ready, W3 no longer needed
   B2_CHECK_CUDA(cudaStreamWaitEvent(sB, ev[2], 0));
   {
@@ -789,7 +800,7 @@ static int backward_and_update(b200dqn_net* n, const FrameSource& fs, int rows, 
   }
   B2_CHECK_CUDA(cudaStreamWaitEvent(sC, ev[2], 0));
   { NoPdlScope side; B2_TRY(bwd_op(n, fs, rows, kConv2Wgrad, sC)); }
-  B2_TRY(bwd_op(n, fs, rows, kConv2Dgrad, st));
+  B2_TRY(chain_op(kConv2Dgrad));
   B2_CHECK_CUDA(cudaEventRecord(ev[3], st));                 // dZ1 ready, W2 no longer needed
   B2_CHECK_CUDA(cudaStreamWaitEvent(sC, ev[3], 0));
   {
@@ -797,7 +808,7 @@ static int backward_and_update(b200dqn_net* n, const FrameSource& fs, int rows, 
     if (n->cfg.math_mode == B200DQN_MATH_TCGEN05) B2_TRY(umma_opt_conv(n, 1, rows, sC, "opt_conv2"));
     else B2_TRY(optimizer_range(n, 1, 1, 1 | 4, rows, sC, "opt_conv2"));
   }
-  B2_TRY(bwd_op(n, fs, rows, kConv1Wgrad, st));
+  B2_TRY(chain_op(kConv1Wgrad));
   if (n->cfg.math_mode == B200DQN_MATH_TCGEN05) B2_TRY(umma_opt_conv(n, 0, rows, st, "opt_conv1"));
   else B2_TRY(optimizer_range(n, 0, 0, 1 | 4, rows, st, "opt_conv1"));
   B2_CHECK_CUDA(cudaEventRecord(ev[4], sA));
@@ -989,8 +1000,13 @@ extern "C" int b200dqn_net_create(int device, const b200dqn_net_config* cfg, b20
   {
     int prio_lo = 0, prio_hi = 0;   // numerically larger = lower priority
     B2_CHECK_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-    for (int i = 0; i < 4; ++i)   // the collective stream (3) keeps the default priority
-      B2_CHECK_CUDA(cudaStreamCreateWithPriority(&n->side[i], cudaStreamNonBlocking, i < 3 ? prio_lo : prio_hi));
+    const char* sp = getenv("B200DQN_SIDE_PRIO");            // experiment knob: "hi" / "lo" for all four
+    for (int i = 0; i < 4; ++i) {
+      int prio = i < 3 ? prio_lo : prio_hi;
+      if (sp && !strcmp(sp, "hi")) prio = prio_hi;
+      if (sp && !strcmp(sp, "lo")) prio = prio_lo;
+      B2_CHECK_CUDA(cudaStreamCreateWithPriority(&n->side[i], cudaStreamNonBlocking, prio));
+    }
   }
   for (auto& e : n->ev) B2_CHECK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   n->use_graph = getenv("B200DQN_NO_GRAPH") == nullptr;
