@@ -208,8 +208,7 @@ def kernel_model(label, nb, world=1):
         "conv2_dgrad": ("tensor", 0, f(MAC["conv2"])), "conv1_wgrad": ("tensor", nb * 35280, f(MAC["conv1"])),
         # elementwise kernels: bytes they must move (fp32 dW, W, S in; W, S out; fp16 hi/lo image out)
         "optimizer": ("hbm", 5 * 4 * N_PARAMS, 0.0),
-        "opt_fc1": ("hbm", (5 * 4 + 4) * n_fc1, 0.0),
-        "pack_fc1f": ("hbm", (4 + 4) * n_fc1, 0.0),
+        "opt_fc1": ("hbm", (5 * 4 + 4) * n_fc1, 0.0),   # the one fc1 tile image (hi + lo fp16) is refreshed in the same pass
         "opt_fc2": ("latency", (nb + 4) * 4 * small["fc2"], 0.0),
         "opt_conv1": ("latency", (5 * 4 + 4) * small["conv1"], 0.0),
         "opt_conv2": ("latency", (5 * 4 + 8) * small["conv2"], 0.0),

@@ -781,17 +781,27 @@ static int backward_and_update(b200dqn_net* n, const FrameSource& fs, int rows, 
   }
   B2_TRY(chain_op(kFc1Dgrad));
   B2_CHECK_CUDA(cudaEventRecord(ev[1], st));                 // dZ3 ready, W4 no longer needed
-  B2_CHECK_CUDA(cudaStreamWaitEvent(sA, ev[1], 0));
-  {
+  // experiment knob B200DQN_OPT_FC1_WHEN: "ev2" / "ev3" = also wait for conv3_dgrad / conv2_dgrad, "last" = same
+  // dependencies but captured after every other node of the step, "skip" = not launched (timing studies only)
+  static const char* fc1_when_env = getenv("B200DQN_OPT_FC1_WHEN");
+  const int fc1_when = !fc1_when_env || g_prof_on ? 0 : !strcmp(fc1_when_env, "ev2") ? 2 : !strcmp(fc1_when_env, "ev3") ? 3
+                       : !strcmp(fc1_when_env, "last") ? 4 : !strcmp(fc1_when_env, "skip") ? 5 : 0;
+  auto opt_fc1_now = [&]() -> int {
     NoPdlScope side;
-    if (tc && fc1_fused_epilogue) B2_TRY(umma_fc1_wgrad_fused(n, rows, sA, n->keep_grads));
-    else if (tc) B2_TRY(umma_opt_fc1(n, rows, sA));          // smem-free: co-resides with the dgrad chain
-    else B2_TRY(optimizer_range(n, 3, 4, 1 | 4, rows, sA, "opt_fc"));
-  }
+    if (tc && fc1_fused_epilogue) return umma_fc1_wgrad_fused(n, rows, sA, n->keep_grads);
+    if (tc) return umma_opt_fc1(n, rows, sA);                // smem-free: co-resides with the dgrad chain
+    return optimizer_range(n, 3, 4, 1 | 4, rows, sA, "opt_fc");
+  };
+  B2_CHECK_CUDA(cudaStreamWaitEvent(sA, ev[1], 0));
+  if (fc1_when == 0) B2_TRY(opt_fc1_now());
   B2_CHECK_CUDA(cudaStreamWaitEvent(sB, ev[1], 0));
   { NoPdlScope side; B2_TRY(bwd_op(n, fs, rows, kConv3Wgrad, sB)); }
   B2_TRY(chain_op(kConv3Dgrad));
   B2_CHECK_CUDA(cudaEventRecord(ev[2], st));                 // dZ2 ready, W3 no longer needed
+  if (fc1_when == 2) {
+    B2_CHECK_CUDA(cudaStreamWaitEvent(sA, ev[2], 0));
+    B2_TRY(opt_fc1_now());
+  }
   B2_CHECK_CUDA(cudaStreamWaitEvent(sB, ev[2], 0));
   {
     NoPdlScope side;
@@ -802,6 +812,10 @@ static int backward_and_update(b200dqn_net* n, const FrameSource& fs, int rows, 
   { NoPdlScope side; B2_TRY(bwd_op(n, fs, rows, kConv2Wgrad, sC)); }
   B2_TRY(chain_op(kConv2Dgrad));
   B2_CHECK_CUDA(cudaEventRecord(ev[3], st));                 // dZ1 ready, W2 no longer needed
+  if (fc1_when == 3) {
+    B2_CHECK_CUDA(cudaStreamWaitEvent(sA, ev[3], 0));
+    B2_TRY(opt_fc1_now());
+  }
   B2_CHECK_CUDA(cudaStreamWaitEvent(sC, ev[3], 0));
   {
     NoPdlScope side;
@@ -811,6 +825,7 @@ static int backward_and_update(b200dqn_net* n, const FrameSource& fs, int rows, 
   B2_TRY(chain_op(kConv1Wgrad));
   if (n->cfg.math_mode == B200DQN_MATH_TCGEN05) B2_TRY(umma_opt_conv(n, 0, rows, st, "opt_conv1"));
   else B2_TRY(optimizer_range(n, 0, 0, 1 | 4, rows, st, "opt_conv1"));
+  if (fc1_when == 4) B2_TRY(opt_fc1_now());
   B2_CHECK_CUDA(cudaEventRecord(ev[4], sA));
   B2_CHECK_CUDA(cudaEventRecord(ev[5], sB));
   B2_CHECK_CUDA(cudaEventRecord(ev[6], sC));

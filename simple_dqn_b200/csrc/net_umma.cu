@@ -142,8 +142,13 @@ struct V2Fc1Fwd {
   static constexpr bool kAExact = false, kARowMajorThreads = false, kBRowMajorThreads = true;
   static constexpr int kAMode = umma2::kBulk, kBMode = umma2::kAsync;
   static constexpr bool kStagedEpilogue = false, kDumpA = false, kPrefetch = false;   // strided outputs; lanes run along m
+  // The weights come from the ROW-oriented fc1 image (the one fc1_dgrad reads K-major: rows = flat index, 64 hidden
+  // units per 128-byte row): read with "row = k" it is an M-contiguous (MN-major) A operand, so the forward needs no
+  // image of its own and nothing has to be re-packed after the optimizer.
+  static constexpr bool kAMnMajor = true;
+  static constexpr uint32_t kAMnLoOffset = 128 * 128;   // lo half of a [hi 128x128 B | lo 128x128 B] tile
   PlanePair in16[2];        // H3 planes [rows][3136]
-  const uint8_t* wimg[2];   // [4 mtiles][49 kb][hi 128x128 | lo 128x128]
+  const uint8_t* wimg[2];   // [25 flat tiles][8 hidden blocks][hi 128x128 | lo 128x128]
   float* part;              // [2*splits][rows][512]
   int rows, splits;
   __device__ int M(int) const { return kHidden; }
@@ -153,8 +158,10 @@ struct V2Fc1Fwd {
     kb = (z % splits) * per;
     ke = min(kb + per, kFlat / 64);
   }
-  __device__ const uint8_t* a_tile(int z, int mtile, int kb) const {
-    return ((z / splits) ? wimg[1] : wimg[0]) + (int64_t(mtile) * (kFlat / 64) + kb) * (128 * 256);
+  // hi sub-tile [64 flat rows x 64 hidden] of hidden block 2*mtile + chunk, flat k-block kb
+  __device__ const uint8_t* a_sub(int z, int mtile, int kb, int chunk) const {
+    return ((z / splits) ? wimg[1] : wimg[0]) + (int64_t(kb >> 1) * (kHidden / 64) + 2 * mtile + chunk) * (128 * 256) +
+           (kb & 1) * (64 * 128);
   }
   __device__ umma2::Planes b_planes(int z) const { return {(z / splits) ? in16[1].hi : in16[0].hi, in16[0].lo_off}; }
   __device__ umma2::RowCtx b_row(int, int n) const { return {int64_t(n) * kFlat, 0, 0, n < rows}; }
@@ -212,8 +219,9 @@ struct V2Fc1Dgrad {
   }
 };
 
-template <int H, int C, int R, int ST, int KO>
+template <int H, int C, int R, int ST, int KO, int STG = 0>
 struct V2ConvDgrad {
+  static constexpr int kStagesOverride = STG;   // 0 = the deepest ring that fits (umma2::Cfg2)
   static constexpr int P = (H - R) / ST + 1, RT = R / ST, HC = (H + ST - 1) / ST, K = RT * RT * KO;
   static_assert(K % 64 == 0 && KO % 8 == 0, "k-blocks of 64");
   static constexpr int kBN = C;
@@ -264,11 +272,11 @@ struct V2ConvDgrad {
 // ---- wgrad (MN-major operands, umma_mn.cuh) -----------------------------------------------------
 // conv2 / conv3: dW[(r,s,c)][ko] = sum_{n,p,q} X[n, p*ST+r, q*ST+s, c] * dZ[n,p,q,ko]
 // One 64-wide m chunk is a contiguous run of the NHWC input: (s, c) are adjacent dims and R*C % 64 == 0.
-template <int H, int C, int R, int ST, int KO>
+template <int H, int C, int R, int ST, int KO, int STG = 4>
 struct WConvWgrad {
   static constexpr int P = (H - R) / ST + 1, KW = R * R * C;
   static_assert((R * C) % 64 == 0 && KO == 64, "64-element runs must not straddle a filter row");
-  static constexpr int kBN = 64, kStages = 4;
+  static constexpr int kBN = 64, kStages = STG;   // 4 stages = 193 KB (one CTA per SM), 2 stages = 97 KB (two)
   static constexpr bool kAExact = false, kARegs = false, kABulk = false, kFusedUpdate = false;
   PlanePair x16;    // [rows][H][H][C]
   PlanePair dz16;   // [rows][P][P][KO]
@@ -394,8 +402,7 @@ struct WFc1WgradFused {
   float* w;           // W4 [3136][512]
   float* s;           // RMSProp state
   float* dw_out;      // optional copy of dW4 (b200dqn_net_get_grads), nullptr in production
-  uint8_t* img_fwd;   // [4 n-tiles][49 kb][hi 128x128 | lo]
-  uint8_t* img_dgr;   // [25 m-tiles][8 kb][hi 128x128 | lo]
+  uint8_t* img_dgr;   // [25 m-tiles][8 kb][hi 128x128 | lo] — the one fc1 image (forward reads it MN-major)
   int rows;
   OptArgs opt;
   __device__ int M(int) const { return kFlat; }
@@ -422,14 +429,7 @@ struct WFc1WgradFused {
     *reinterpret_cast<uint4*>(base) = hi;
     *reinterpret_cast<uint4*>(base + 128 * 128) = lo;
   }
-  __device__ void pack_col8(int, int m8, int n, const float wv[8]) const {
-    uint4 hi, lo;
-    umma::split8(wv, hi, lo);
-    uint8_t* base = img_fwd + (int64_t(n / 128) * (kFlat / 64) + m8 / 64) * (128 * 256) +
-                    umma::sw128_off(n % 128, (m8 % 64) / 8);
-    *reinterpret_cast<uint4*>(base) = hi;
-    *reinterpret_cast<uint4*>(base + 128 * 128) = lo;
-  }
+  __device__ void pack_col8(int, int, int, const float*) const {}   // no column-oriented image any more
 };
 
 // ---- weight tile-image sources (k_pack_image) --------------------------------------------------
@@ -445,18 +445,7 @@ struct PackFwdConv {   // B operand of a forward conv: rows = output channel n, 
     for (int j = 0; j < 8; ++j) v[j] = w[(k0 + j) * N + r];
   }
 };
-struct PackFc1Fwd {    // A operand of the swapped fc1 forward: rows = hidden unit m, K = flat index
-  static constexpr bool kRowMajorThreads = false;
-  const float* w;      // W4 [3136][512]
-  __host__ __device__ int tiles() const { return kHidden / 128; }
-  __host__ __device__ int rows() const { return 128; }
-  __host__ __device__ int kblocks() const { return kFlat / 64; }
-  __device__ void src8(int tile, int r, int k0, float v[8]) const {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = w[(k0 + j) * kHidden + tile * 128 + r];
-  }
-};
-struct PackFc1Dgrad {  // A operand of fc1 dgrad: rows = flat index m, K = hidden unit
+struct PackFc1Dgrad {  // the fc1 image: rows = flat index m, 64 hidden units per row (dgrad: K-major A; forward: MN-major A)
   static constexpr bool kRowMajorThreads = true;
   const float* w;
   __host__ __device__ int tiles() const { return (kFlat + 127) / 128; }
@@ -617,85 +606,20 @@ k_opt_fc1(const float* __restrict__ dw, float* __restrict__ w, float* __restrict
   kt_end(kt);
 }
 
-// fc1 optimizer, one pass for everything: a CTA owns a [64 flat indexes x 64 hidden units] block of W4 — exactly one
-// k-block of the column-oriented (forward) tile image and one 128-byte row segment of the row-oriented (dgrad)
-// image.  Phase 1 (thread <-> 8 consecutive hidden units of one flat index): the configured update on W/S in place +
-// the dgrad-image chunk; the new weights are parked in shared memory.  Phase 2 (thread <-> 8 consecutive flat
-// indexes of one hidden unit): the forward-image chunk, read column-wise from the parked block.  Replaces
-// k_opt_fc1 + k_pack_image<PackFc1Fwd>: W4 is not re-read (6.4 MB less L2 traffic per step) and one launch less on
-// the branch that forms the tail of the data-parallel step.
-__global__ void __launch_bounds__(256)
-k_opt_fc1_both(const float* __restrict__ dw, float* __restrict__ w, float* __restrict__ sst, uint8_t* __restrict__ img_dgr,
-               uint8_t* __restrict__ img_fwd, const OptArgs opt, const KTrace kt) {
-  constexpr int kT = 64, kPitch = kT + 1;
-  __shared__ float tile[kT * kPitch];
-  kt_begin(kt);
-  pdl_wait();
-  pdl_launch_dependents();
-  const float l_step = opt_step_scalar(opt);
-  const int tid = threadIdx.x;
-  constexpr int kTilesN = kHidden / kT, kTilesM = kFlat / kT;
-  for (int tl = blockIdx.x; tl < kTilesM * kTilesN; tl += gridDim.x) {
-    const int m0 = (tl / kTilesN) * kT, n0 = (tl % kTilesN) * kT;
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int ml = (tid >> 3) + 32 * i, nl = (tid & 7) * 8;
-      const int m = m0 + ml, nn = n0 + nl;
-      const int64_t e = int64_t(m) * kHidden + nn;
-      float g[8], wv[8];
-      ld8(dw + e, g);
-      opt_update_vec<8>(opt, l_step, g, wv, w + e, sst + e);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) tile[ml * kPitch + nl + j] = wv[j];
-      uint4 hi, lo;
-      umma::split8(wv, hi, lo);
-      uint8_t* base = img_dgr + (int64_t(m / 128) * (kHidden / 64) + nn / 64) * (128 * 256) +
-                      umma::sw128_off(m % 128, (nn % 64) / 8);
-      *reinterpret_cast<uint4*>(base) = hi;
-      *reinterpret_cast<uint4*>(base + 128 * 128) = lo;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int nl = tid & 63, c = (tid >> 6) + 4 * i;      // hidden unit, 8-wide chunk of the k-block
-      float wv[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) wv[j] = tile[(c * 8 + j) * kPitch + nl];
-      uint4 hi, lo;
-      umma::split8(wv, hi, lo);
-      const int nn = n0 + nl;
-      uint8_t* base = img_fwd + (int64_t(nn / 128) * (kFlat / 64) + m0 / 64) * (128 * 256) + umma::sw128_off(nn % 128, c);
-      *reinterpret_cast<uint4*>(base) = hi;
-      *reinterpret_cast<uint4*>(base + 128 * 128) = lo;
-    }
-    __syncthreads();
-  }
-  kt_end(kt);
-}
-
 int umma_opt_fc1(b200dqn_net* n, int rows, cudaStream_t st, bool from_g) {
   UmmaState* u = ust(n);
   const LayerTable& lt = n->lt;
   const float* dw = from_g ? n->d_g + lt.off[3] : n->d_part + lt.part_off[3];
-  // one-pass kernel (B200DQN_OPT_FC1_ONEPASS=1): parity-clean, ends ~4 us earlier on its branch, but the step as a
-  // whole measured slower with it (1 GPU: 78.9 vs 75.4 us/step, profiles/r2g_*; 4 GPUs: 23.5 us under contention),
-  // so the two-kernel form stays the default.
-  static const int forced = getenv("B200DQN_OPT_FC1_ONEPASS") ? atoi(getenv("B200DQN_OPT_FC1_ONEPASS")) : -1;
-  const bool one_pass = forced >= 0 ? forced != 0 : false;
-  if (one_pass) {
-    B2_CHECK_CUDA(launch_pdl(k_opt_fc1_both, dim3(2 * n->sm_count), dim3(256), 0, st, dw, n->d_w + lt.off[3],
-                             n->d_s + lt.off[3], u->img_dgr[0], u->img_fwd[0][3], make_opt_args(n, rows),
-                             ktrace_slot("opt_fc1")));
-    B2_PROF("opt_fc1", st);
-    return B200DQN_OK;
-  }
+  // One kernel, one image: the update refreshes the row-oriented tile image in the same pass, and the forward reads
+  // that image too (MN-major) — the column-oriented forward image and its re-pack kernel (round 1-2: 6.4 MB read +
+  // 6.4 MB written per step, 5 us at the end of the fc1 branch) are gone.
   // capped grid (CTAs per SM, grid-stride): the kernel shares the SMs — and the L2 — with the dgrad chain
   static const int per_sm = getenv("B200DQN_OPT_FC1_CTAS") ? atoi(getenv("B200DQN_OPT_FC1_CTAS")) : 2;
   const int ctas = per_sm > 0 ? per_sm * n->sm_count : n->sm_count / (-per_sm > 0 ? -per_sm : 1);
   B2_CHECK_CUDA(launch_pdl(k_opt_fc1, dim3(ctas), dim3(256), 0, st, dw, n->d_w + lt.off[3],
                            n->d_s + lt.off[3], u->img_dgr[0], make_opt_args(n, rows), ktrace_slot("opt_fc1")));
   B2_PROF("opt_fc1", st);
-  return umma2::launch_pack("pack_fc1f", PackFc1Fwd{n->d_w + lt.off[3]}, u->img_fwd[0][3], st, 2 * n->sm_count);
+  return B200DQN_OK;
 }
 
 // RMSProp + image refresh of conv layer l (0..2), fused (single-GPU path of the tcgen05 engine).
@@ -762,7 +686,7 @@ static int64_t fwd_image_bytes(int layer) {
     case 0: return int64_t(kK1 / 64) * kC1 * 256;
     case 1: return int64_t(kK2 / 64) * kC2 * 256;
     case 2: return int64_t(kK3 / 64) * kC3 * 256;
-    default: return int64_t(kHidden / 128) * (kFlat / 64) * 128 * 256;
+    default: return int64_t((kFlat + 127) / 128) * (kHidden / 64) * 128 * 256;   // fc1: the row-oriented image
   }
 }
 
@@ -787,8 +711,7 @@ int umma_pack_layers(b200dqn_net* n, int which, int l0, int l1, cudaStream_t st)
           rc = umma2::launch_pack("pack_c3d", PackConvDgrad<kP2, kC2, 3, 1, kC3>{w + lt.off[2]}, u->img_dgr[1], st);
         break;
       case 3:
-        rc = umma2::launch_pack("pack_fc1f", PackFc1Fwd{w + lt.off[3]}, u->img_fwd[which][3], st);
-        if (!rc && !which) rc = umma2::launch_pack("pack_fc1d", PackFc1Dgrad{w + lt.off[3]}, u->img_dgr[0], st);
+        rc = umma2::launch_pack("pack_fc1", PackFc1Dgrad{w + lt.off[3]}, u->img_fwd[which][3], st);
         break;
       default: break;  // fc2 runs on CUDA cores (N = A <= 18)
     }
@@ -867,9 +790,9 @@ int umma_net_init(b200dqn_net* n) {
     }
   }
   B2_CHECK_CUDA(cudaMalloc(&u->im2col1, int64_t(nb) * conv1tma::kTilesPerSample * (kK1 / 64) * 128 * 128));
-  const int64_t dgr_bytes[3] = {int64_t((kFlat + 127) / 128) * (kHidden / 64) * 128 * 256,
-                                int64_t(kK3 / 64) * kC2 * 256, int64_t(4) * (256 / 64) * kC1 * 256};
-  for (int i = 0; i < 3; ++i) {
+  u->img_dgr[0] = u->img_fwd[0][3];   // fc1: ONE row-oriented image serves the dgrad (K-major) and the forward (MN-major)
+  const int64_t dgr_bytes[3] = {0, int64_t(kK3 / 64) * kC2 * 256, int64_t(4) * (256 / 64) * kC1 * 256};
+  for (int i = 1; i < 3; ++i) {
     B2_CHECK_CUDA(cudaMalloc(&u->img_dgr[i], dgr_bytes[i]));
     B2_CHECK_CUDA(cudaMemset(u->img_dgr[i], 0, dgr_bytes[i]));
   }
@@ -881,7 +804,7 @@ void umma_net_destroy(b200dqn_net* n) {
   if (!u) return;
   for (int i = 0; i < 3; ++i) {
     for (int z = 0; z < 2; ++z) cudaFree(u->h16[i][z]);
-    cudaFree(u->img_dgr[i]);
+    if (i > 0) cudaFree(u->img_dgr[i]);   // [0] aliases img_fwd[0][3]
   }
   for (int i = 0; i < 4; ++i) cudaFree(u->dz16[i]);
   cudaFree(u->im2col1);
@@ -993,6 +916,17 @@ int umma_forward(b200dqn_net* n, const uint8_t* const src[2], const int32_t* con
   return B200DQN_OK;
 }
 
+// B200DQN_STAGES2=label,label,...: run that kernel with a 2-stage operand ring (about half the shared memory, so two
+// CTAs of the step's kernels fit on an SM) instead of the deepest ring.
+static bool shallow_ring(const char* label) {
+  static const char* list = getenv("B200DQN_STAGES2");
+  if (!list) return false;
+  const size_t n = strlen(label);
+  for (const char* p = list; (p = strstr(p, label)) != nullptr; p += n)
+    if ((p == list || p[-1] == ',') && (p[n] == 0 || p[n] == ',')) return true;
+  return false;
+}
+
 int umma_backward_op(b200dqn_net* n, int op, const uint8_t* src, const int32_t* idx, int shift, int rows,
                      cudaStream_t st) {
   const LayerTable& lt = n->lt;
@@ -1015,6 +949,12 @@ int umma_backward_op(b200dqn_net* n, int op, const uint8_t* src, const int32_t* 
     case 2: {
       UmmaState* u = ust(n);
       using P = WConvWgrad<kP2, kC2, 3, 1, kC3>;
+      using P2 = WConvWgrad<kP2, kC2, 3, 1, kC3, 2>;
+      if (shallow_ring("conv3_wgrad")) {
+        P2 p{PlanePair{u->h16[1][0], u->h_elems[1]}, PlanePair{u->dz16[1], u->dz_elems[1]},
+             n->d_part + lt.part_off[2], rows, umma_wgrad_kb(2, rows)};
+        return umma_mn::launch_umma_mn("conv3_wgrad", p, P::KW, kC3, lt.splits[2], st);
+      }
       P p{PlanePair{u->h16[1][0], u->h_elems[1]}, PlanePair{u->dz16[1], u->dz_elems[1]},
           n->d_part + lt.part_off[2], rows, umma_wgrad_kb(2, rows)};
       return umma_mn::launch_umma_mn("conv3_wgrad", p, P::KW, kC3, lt.splits[2], st);
@@ -1031,6 +971,12 @@ int umma_backward_op(b200dqn_net* n, int op, const uint8_t* src, const int32_t* 
     case 4: {
       UmmaState* u = ust(n);
       using P = WConvWgrad<kP1, kC1, 4, 2, kC2>;
+      using P2 = WConvWgrad<kP1, kC1, 4, 2, kC2, 2>;
+      if (shallow_ring("conv2_wgrad")) {
+        P2 p{PlanePair{u->h16[0][0], u->h_elems[0]}, PlanePair{u->dz16[2], u->dz_elems[2]},
+             n->d_part + lt.part_off[1], rows, umma_wgrad_kb(1, rows)};
+        return umma_mn::launch_umma_mn("conv2_wgrad", p, P::KW, kC2, lt.splits[1], st);
+      }
       P p{PlanePair{u->h16[0][0], u->h_elems[0]}, PlanePair{u->dz16[2], u->dz_elems[2]},
           n->d_part + lt.part_off[1], rows, umma_wgrad_kb(1, rows)};
       return umma_mn::launch_umma_mn("conv2_wgrad", p, P::KW, kC2, lt.splits[1], st);
@@ -1038,6 +984,12 @@ int umma_backward_op(b200dqn_net* n, int op, const uint8_t* src, const int32_t* 
     case 5: {
       UmmaState* u = ust(n);
       using P = V2ConvDgrad<kP1, kC1, 4, 2, kC2>;
+      using P2 = V2ConvDgrad<kP1, kC1, 4, 2, kC2, 2>;
+      if (shallow_ring("conv2_dgrad")) {   // 81 KB per CTA: the 100 CTAs take 50 SMs instead of 100
+        P2 p{PlanePair{u->dz16[2], u->dz_elems[2]}, u->img_dgr[2], n->d_h1[0], n->keep_grads ? n->d_dz1 : nullptr,
+             PlanePair{u->dz16[3], u->dz_elems[3]}, rows};
+        return umma2::launch_umma2("conv2_dgrad", p, rows * P::HC * P::HC, kC1, 4, st);
+      }
       P p{PlanePair{u->dz16[2], u->dz_elems[2]}, u->img_dgr[2], n->d_h1[0], n->keep_grads ? n->d_dz1 : nullptr,
           PlanePair{u->dz16[3], u->dz_elems[3]}, rows};
       return umma2::launch_umma2("conv2_dgrad", p, rows * P::HC * P::HC, kC1, 4, st);
@@ -1058,7 +1010,7 @@ int umma_fc1_wgrad_fused(b200dqn_net* n, int rows, cudaStream_t st, bool keep_gr
   const LayerTable& lt = n->lt;
   WFc1WgradFused p{PlanePair{u->h16[2][0], u->h_elems[2]}, PlanePair{u->dz16[0], u->dz_elems[0]},
                    n->d_w + lt.off[3], n->d_s + lt.off[3], keep_grads ? n->d_part + lt.part_off[3] : nullptr,
-                   u->img_fwd[0][3], u->img_dgr[0], rows, make_opt_args(n, rows)};
+                   u->img_dgr[0], rows, make_opt_args(n, rows)};
   return umma_mn::launch_umma_mn("fc1_wgrad+opt", p, kFlat, kHidden, 1, st);
 }
 

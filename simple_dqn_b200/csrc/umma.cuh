@@ -37,6 +37,16 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
          | (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
 }
 
+// MN-major SWIZZLE_128B descriptor: LBO = byte stride between 64-element MN chunks, SBO = byte stride
+// between groups of 8 k rows (1024 when rows are packed).  A [64 k-rows x 128 B] sub-tile written in the K-major
+// SW128 pattern with "row = k" IS this layout — which is why the row-oriented fc1 weight image (rows = flat index,
+// 64 hidden units per 128-byte row) serves the dgrad as a K-major operand and the forward as an MN-major one.
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return uint64_t((smem_addr >> 4) & 0x3FFF) | (uint64_t((lbo_bytes >> 4) & 0x3FFF) << 16) | (uint64_t(64) << 32) |
+         (uint64_t(1) << 46) | (uint64_t(2) << 61);
+}
+constexpr uint32_t kIdescAMn = 1u << 15, kIdescBMn = 1u << 16;   // a_major / b_major = MN
+
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {  // whole warp
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
                "r"(ncols)

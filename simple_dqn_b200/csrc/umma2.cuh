@@ -13,6 +13,7 @@
 // Accumulation scheme (3 MMAs / k-step, fp32 in TMEM) as in umma.cuh.
 #pragma once
 #include <stdlib.h>
+#include <type_traits>
 
 #include "umma.cuh"
 
@@ -69,11 +70,46 @@ __device__ __forceinline__ void split8_planes(const float v[8], __half* hi_dst, 
 //                  starting at k index kk; false -> zero fill.   PlanePair-like a_planes(z) -> (hi, lo_off)
 //           same with b_row / b_chunk / b_planes for B
 //   kBulk : const uint8_t* a_tile(z, mtile, kb) / b_tile(z, ntile, kb)      -> [hi image | lo image]
+//           optional  static constexpr bool kAMnMajor = true  (bulk A only): the A tile is M-contiguous; it is fetched
+//           as two [64 k-rows x 128 B] sub-tiles per half,  a_sub(z, mtile, kb, chunk) -> hi sub-tile, the lo
+//           sub-tile kAMnLoOffset bytes behind it
 //   void store8(z, m, n0, const float v[8])
 //   static constexpr bool kDumpA: after k-block kb is staged, bulk-store the A_hi tile to a_dump(z, mtile, kb)
 //        (needs every k-block in its own stage: nkb <= kStages)
 //   static constexpr bool kStagedEpilogue: store8 writes 8 CONTIGUOUS outputs of row m (NHWC tensors) ->
 //        the tile is transposed through smem so that a warp's stores are whole cache lines
+template <class P, class = void>
+struct AMnMajor { static constexpr bool value = false; };
+template <class P>
+struct AMnMajor<P, std::void_t<decltype(P::kAMnMajor)>> { static constexpr bool value = P::kAMnMajor; };
+
+// The bulk copies of one k-block's operand images into stage memory `st_gen` (one thread).
+template <class P, class C>
+__device__ __forceinline__ void issue_bulk_stage(const P& p, int z, int mtile, int ntile, int kb, uint8_t* st_gen,
+                                                 uint64_t* bar) {
+  if constexpr (P::kAMode == kBulk) {
+    if constexpr (AMnMajor<P>::value) {
+      constexpr uint32_t kSub = 64 * 128;   // [64 k-rows x 128 B]
+      static_assert(2 * kSub == C::kABytes, "M = 128 is two 64-wide chunks");
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const uint8_t* src = p.a_sub(z, mtile, kb, c);
+        tma_bulk_g2s(st_gen + c * kSub, src, kSub, bar);
+        tma_bulk_g2s(st_gen + C::kABytes + c * kSub, src + P::kAMnLoOffset, kSub, bar);
+      }
+    } else {
+      tma_bulk_g2s(st_gen, p.a_tile(z, mtile, kb), 2 * C::kABytes, bar);
+    }
+  }
+  if constexpr (P::kBMode == kBulk)
+    tma_bulk_g2s(st_gen + C::kAStage, p.b_tile(z, ntile, kb), 2 * C::kBBytes, bar);
+}
+
+template <class P, class = void>
+struct StagesOf { static constexpr int value = 0; };
+template <class P>
+struct StagesOf<P, std::void_t<decltype(P::kStagesOverride)>> { static constexpr int value = P::kStagesOverride; };
+
 template <class P>
 struct Cfg2 {
   static constexpr int BN = P::kBN;
@@ -81,7 +117,9 @@ struct Cfg2 {
   static constexpr uint32_t kBBytes = BN * 128;
   static constexpr uint32_t kAStage = (P::kAExact ? 1 : 2) * kABytes;
   static constexpr uint32_t kStageBytes = kAStage + 2 * kBBytes;
-  static constexpr int kStages = (4 * kStageBytes <= 200 * 1024) ? 4 : 3;
+  // default: as deep a ring as one CTA per SM allows; a problem may ask for a shallower ring (kStagesOverride) so
+  // that two CTAs — of this or of another kernel of the step — share an SM
+  static constexpr int kStages = StagesOf<P>::value ? StagesOf<P>::value : (4 * kStageBytes <= 200 * 1024) ? 4 : 3;
   static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024;
   static constexpr uint32_t kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
                                         : (2 * BN <= 256) ? 256 : 512;
@@ -185,8 +223,10 @@ __global__ void __launch_bounds__(kThreads2, 1) k_umma2(const P p, const int tra
     // ================================================================ MMA issuer
     // The whole warp runs the loop converged; one elected lane issues (keeps descriptors in uniform
     // registers and avoids the per-instruction re-convergence loop ptxas emits inside divergent code).
-    constexpr uint32_t idesc1 = umma::make_idesc_f16(kBM, BN);
-    constexpr uint32_t idesc2 = umma::make_idesc_f16(kBM, 2 * BN);
+    constexpr bool kAMn = AMnMajor<P>::value;
+    constexpr uint32_t idesc1 = umma::make_idesc_f16(kBM, BN) | (kAMn ? umma::kIdescAMn : 0u);
+    constexpr uint32_t idesc2 = umma::make_idesc_f16(kBM, 2 * BN) | (kAMn ? umma::kIdescAMn : 0u);
+    constexpr uint32_t kAStep = kAMn ? 128 : 2;   // descriptor address units (16 B) per 16 k: 16 k-rows x 128 B or 32 B
     for (int it = 0; it < nkb; ++it) {
       const int s = it % S;
       mbar_wait(&s_full[s], (it / S) & 1);
@@ -194,8 +234,8 @@ __global__ void __launch_bounds__(kThreads2, 1) k_umma2(const P p, const int tra
       umma::fence_after_sync();
       B2_TRACE(lane == 0, 8 + it * 4 + 0);
       const uint32_t sa = smem_base + s * C::kStageBytes;
-      const uint64_t da_hi = umma::make_desc_sw128(sa);
-      const uint64_t da_lo = umma::make_desc_sw128(sa + C::kABytes);
+      const uint64_t da_hi = kAMn ? umma::make_desc_mn(sa, 64 * 128) : umma::make_desc_sw128(sa);
+      const uint64_t da_lo = kAMn ? umma::make_desc_mn(sa + C::kABytes, 64 * 128) : umma::make_desc_sw128(sa + C::kABytes);
       const uint64_t db = umma::make_desc_sw128(sa + C::kAStage);   // [B_hi ; B_lo], 2*BN rows
       if (elect_one()) {
         if constexpr (P::kDumpA) {
@@ -206,8 +246,8 @@ __global__ void __launch_bounds__(kThreads2, 1) k_umma2(const P p, const int tra
         }
 #pragma unroll
         for (int k = 0; k < kBK / 16; ++k) {
-          umma::mma_f16(tmem, da_hi + 2 * k, db + 2 * k, idesc2, (it > 0 || k > 0) ? 1u : 0u);
-          if (!P::kAExact) umma::mma_f16(tmem + BN, da_lo + 2 * k, db + 2 * k, idesc1, 1u);
+          umma::mma_f16(tmem, da_hi + kAStep * k, db + 2 * k, idesc2, (it > 0 || k > 0) ? 1u : 0u);
+          if (!P::kAExact) umma::mma_f16(tmem + BN, da_lo + kAStep * k, db + 2 * k, idesc1, 1u);
         }
         umma::mma_commit(&s_empty[s]);
         if (it == nkb - 1) {
@@ -261,10 +301,7 @@ __global__ void __launch_bounds__(kThreads2, 1) k_umma2(const P p, const int tra
           if (j < nkb) {
             uint8_t* st_gen = smem_gen + j * C::kStageBytes;
             mbar_arrive_expect_tx(&s_full[j], kBulkBytes);
-            if constexpr (P::kAMode == kBulk)
-              tma_bulk_g2s(st_gen, p.a_tile(z, mtile, kb0 + j), 2 * C::kABytes, &s_full[j]);
-            if constexpr (P::kBMode == kBulk)
-              tma_bulk_g2s(st_gen + C::kAStage, p.b_tile(z, blockIdx.y, kb0 + j), 2 * C::kBBytes, &s_full[j]);
+            issue_bulk_stage<P, C>(p, z, mtile, blockIdx.y, kb0 + j, st_gen, &s_full[j]);
           }
         }
       }
@@ -272,6 +309,7 @@ __global__ void __launch_bounds__(kThreads2, 1) k_umma2(const P p, const int tra
     // Everything above (TMEM alloc, barrier init, the gather index tables, the first weight tiles) overlapped the
     // previous kernel of the chain; only from here on do we touch its outputs.  (The MMA warp never reads global memory.)
     pdl_wait();
+    if (kt.flags & 1) pdl_launch_dependents();
     // kReg operands: per-row source pointers, once per kernel (they may depend on upstream data — the
     // sampled indexes — so they are built after the wait, but not again for every k-block)
     const uint8_t* areg[kACh];
@@ -304,10 +342,7 @@ __global__ void __launch_bounds__(kThreads2, 1) k_umma2(const P p, const int tra
       const uint32_t a_hi = st_addr, a_lo = st_addr + C::kABytes, b_hi = st_addr + C::kAStage, b_lo = b_hi + C::kBBytes;
       if (kAnyBulk && tid == 0 && j >= S) {   // the first S k-blocks' images were requested before the dependency wait
         mbar_arrive_expect_tx(&s_full[s], kBulkBytes);
-        if constexpr (P::kAMode == kBulk)
-          tma_bulk_g2s(st_gen, p.a_tile(z, mtile, kb), 2 * C::kABytes, &s_full[s]);
-        if constexpr (P::kBMode == kBulk)
-          tma_bulk_g2s(st_gen + C::kAStage, p.b_tile(z, blockIdx.y, kb), 2 * C::kBBytes, &s_full[s]);
+        issue_bulk_stage<P, C>(p, z, mtile, blockIdx.y, kb, st_gen, &s_full[s]);
       }
       if constexpr (P::kAMode == kAsync) {
 #pragma unroll

@@ -24,12 +24,7 @@ using umma2::Planes;
 
 constexpr int kKB = 64;  // reduction rows (pixels) per k-block
 
-// MN-major SWIZZLE_128B descriptor: LBO = byte stride between 64-element MN chunks, SBO = byte stride
-// between groups of 8 k rows (1024 when rows are packed).
-__device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
-  return uint64_t((smem_addr >> 4) & 0x3FFF) | (uint64_t((lbo_bytes >> 4) & 0x3FFF) << 16) | (uint64_t(64) << 32) |
-         (uint64_t(1) << 46) | (uint64_t(2) << 61);
-}
+using umma::make_desc_mn;   // MN-major SWIZZLE_128B descriptor (umma.cuh)
 __host__ __device__ constexpr uint32_t make_idesc_f16_mn(int M, int N) {
   return (1u << 4) | (1u << 15) | (1u << 16) | (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
 }
@@ -147,6 +142,7 @@ __global__ void __launch_bounds__(kThreads2, 1) k_umma_mn(const P p, const KTrac
     Planes apl{nullptr, 0};
     if constexpr (!P::kARegs && !P::kABulk) apl = p.a_planes(z);
     pdl_wait();   // prologue above overlapped the predecessor; the MMA warp never reads global memory
+    if (kt.flags & 1) pdl_launch_dependents();
     for (int j = 0; j < nkb; ++j) {
       const int s = j % S;
       if (j >= S) mbar_wait(&s_empty[s], ((j / S) - 1) & 1);
