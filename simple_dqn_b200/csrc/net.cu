@@ -514,6 +514,41 @@ static int opt_fc2_small(b200dqn_net* n, int rows, cudaStream_t s) {
 // Peer-memory exchange (comm_p2p.cuh): no shared communicator, so every layer's gradient is reduced
 // the moment its wgrad has finished, on that layer's own branch, and only conv1's 32 KB exchange is left
 // on the critical chain:  wgrad -> partial sums -> exchange (in place, all ranks) -> RMSProp from d_g.
+// ---- software-pipelined fc1 update (net.cuh: graph_def_exec) ----------------------------------------------------
+// In the deferred variant of the step graph the fc1 optimizer does not run where dW4 becomes available; the step
+// only marks the update as pending ...
+static int fc1_update_deferred(b200dqn_net* n, cudaStream_t branch) {
+  B2_CHECK_CUDA(cudaMemsetAsync(n->d_fc1_pending, 1, sizeof(uint32_t), branch));   // != 0
+  return B200DQN_OK;
+}
+// ... the NEXT step applies it first thing, on a side branch under its forward convolutions (joined before fc1_fwd) ...
+static int fc1_update_leading(b200dqn_net* n, cudaStream_t st) {
+  cudaStream_t sA = n->side[0];
+  B2_CHECK_CUDA(cudaEventRecord(n->ev[15], st));
+  B2_CHECK_CUDA(cudaStreamWaitEvent(sA, n->ev[15], 0));
+  {
+    NoPdlScope side;
+    B2_TRY(umma_opt_fc1(n, n->nb, sA, false, n->d_fc1_pending));
+  }
+  B2_CHECK_CUDA(cudaEventRecord(n->ev[16], sA));
+  return B200DQN_OK;
+}
+// ... and train_fused applies the last one before it returns.
+static int fc1_update_flush(b200dqn_net* n, cudaStream_t st) {
+  if (!n->fc1_pending) return B200DQN_OK;
+  {
+    NoPdlScope plain;
+    B2_TRY(umma_opt_fc1(n, n->nb, st, false, n->d_fc1_pending));
+  }
+  B2_CHECK_CUDA(cudaMemsetAsync(n->d_fc1_pending, 0, sizeof(uint32_t), st));
+  n->fc1_pending = false;
+  return B200DQN_OK;
+}
+static void destroy_step_graphs(b200dqn_net* n) {
+  if (n->graph_exec) { cudaGraphExecDestroy(n->graph_exec); n->graph_exec = nullptr; }
+  if (n->graph_def_exec) { cudaGraphExecDestroy(n->graph_def_exec); n->graph_def_exec = nullptr; }
+}
+
 static int backward_and_update_xchg(b200dqn_net* n, const FrameSource& fs, int rows, cudaStream_t st) {
   cudaStream_t sA = n->side[0], sB = n->side[1], sC = n->side[2];
   cudaEvent_t* ev = n->ev;
@@ -615,7 +650,8 @@ static int backward_and_update_gather(b200dqn_net* n, const FrameSource& fs, int
   {
     NoPdlScope side;
     B2_CHECK_CUDA(cudaStreamWaitEvent(sA, ev[1], 0));
-    B2_TRY(umma_opt_fc1(n, rows, sA));                       // dW4 is already the global sum
+    if (n->defer_fc1) B2_TRY(fc1_update_deferred(n, sA));    // applied under the next step's forward (net.cuh)
+    else B2_TRY(umma_opt_fc1(n, rows, sA));                  // dW4 is already the global sum
     B2_CHECK_CUDA(cudaStreamWaitEvent(sB, ev[1], 0));
     B2_TRY(bwd_op(n, fs, rows, kConv3Wgrad, sB));
     if (!fused_xll) {
@@ -789,6 +825,7 @@ static int backward_and_update(b200dqn_net* n, const FrameSource& fs, int rows, 
   auto opt_fc1_now = [&]() -> int {
     NoPdlScope side;
     if (tc && fc1_fused_epilogue) return umma_fc1_wgrad_fused(n, rows, sA, n->keep_grads);
+    if (tc && n->defer_fc1) return fc1_update_deferred(n, sA);   // applied under the next step's forward (net.cuh)
     if (tc) return umma_opt_fc1(n, rows, sA);                // smem-free: co-resides with the dgrad chain
     return optimizer_range(n, 3, 4, 1 | 4, rows, sA, "opt_fc");
   };
@@ -1024,6 +1061,8 @@ extern "C" int b200dqn_net_create(int device, const b200dqn_net_config* cfg, b20
     }
   }
   for (auto& e : n->ev) B2_CHECK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  B2_CHECK_CUDA(cudaMalloc(&n->d_fc1_pending, sizeof(uint32_t)));
+  B2_CHECK_CUDA(cudaMemset(n->d_fc1_pending, 0, sizeof(uint32_t)));
   n->use_graph = getenv("B200DQN_NO_GRAPH") == nullptr;
   n->use_branches = getenv("B200DQN_NO_BRANCHES") == nullptr;
   int rc = umma_net_init(n);
@@ -1039,8 +1078,9 @@ extern "C" int b200dqn_net_destroy(b200dqn_net* n) {
   cudaDeviceSynchronize();
   comm_destroy(n);
   umma_net_destroy(n);
-  if (n->graph_exec) cudaGraphExecDestroy(n->graph_exec);
+  destroy_step_graphs(n);
   if (n->graph_train_exec) cudaGraphExecDestroy(n->graph_train_exec);
+  cudaFree(n->d_fc1_pending);
   if (n->graph_predict_exec) cudaGraphExecDestroy(n->graph_predict_exec);
   for (auto& sd : n->side) if (sd) cudaStreamDestroy(sd);
   for (auto& e : n->ev) if (e) cudaEventDestroy(e);
@@ -1364,28 +1404,42 @@ extern "C" int b200dqn_net_train_fused(b200dqn_net* n, b200dqn_replay* r, int ns
   // and replayed: one graph launch per step instead of ~17 stream operations.
   const bool use_graph = n->use_graph && !g_prof_on && st != nullptr;
   if (use_graph) {
-    if (!n->graph_exec || n->graph_replay != r || n->graph_stream != st || n->graph_world != n->world ||
+    if (n->graph_replay != r || n->graph_stream != st || n->graph_world != n->world ||
         n->graph_trace_gen != g_ktrace_gen) {
-      if (n->graph_exec) { cudaGraphExecDestroy(n->graph_exec); n->graph_exec = nullptr; }
+      destroy_step_graphs(n);
+      n->graph_replay = r; n->graph_stream = st; n->graph_world = n->world; n->graph_trace_gen = g_ktrace_gen;
+    }
+    // several steps in one call: the fc1 update of step t rides under the forward of step t+1 (net.cuh)
+    static const bool defer_off = getenv("B200DQN_DEFER_FC1") && atoi(getenv("B200DQN_DEFER_FC1")) == 0;
+    const bool deferred = nsteps >= 2 && !defer_off && n->use_branches && n->cfg.math_mode == B200DQN_MATH_TCGEN05 &&
+                          (n->world == 1 || comm_gather_active(n, st));
+    cudaGraphExec_t* exec = deferred ? &n->graph_def_exec : &n->graph_exec;
+    if (!*exec) {
       cudaGraph_t graph = nullptr;
       B2_CHECK_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
       const long long launches_before = g_launch_count;
+      n->defer_fc1 = deferred;
       {
         const bool prev = g_pdl_suppressed;
         if (ktrace_tick(st)) g_pdl_suppressed = true;   // the sampler must not start ahead of the tick
-        rc = launch_sample(r, st);
+        rc = deferred ? fc1_update_leading(n, st) : B200DQN_OK;
+        if (!rc) rc = launch_sample(r, st);
         g_pdl_suppressed = prev;
       }
       if (!rc) rc = train_on_ring(n, r, st);
-      n->graph_launches = int(g_launch_count - launches_before);
+      n->defer_fc1 = false;
+      (deferred ? n->graph_def_launches : n->graph_launches) = int(g_launch_count - launches_before);
       cudaError_t e = cudaStreamEndCapture(st, &graph);
       if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
       B2_CHECK_CUDA(e);
-      B2_CHECK_CUDA(cudaGraphInstantiate(&n->graph_exec, graph, 0));
+      B2_CHECK_CUDA(cudaGraphInstantiate(exec, graph, 0));
       cudaGraphDestroy(graph);
-      n->graph_replay = r; n->graph_stream = st; n->graph_world = n->world; n->graph_trace_gen = g_ktrace_gen;
     }
-    for (int i = 0; i < nsteps; ++i) B2_CHECK_CUDA(cudaGraphLaunch(n->graph_exec, st));
+    for (int i = 0; i < nsteps; ++i) B2_CHECK_CUDA(cudaGraphLaunch(*exec, st));
+    if (deferred) {
+      n->fc1_pending = true;
+      B2_TRY(fc1_update_flush(n, st));
+    }
   } else {
     for (int i = 0; i < nsteps; ++i) {
       const bool prev = g_pdl_suppressed;
@@ -1493,7 +1547,7 @@ extern "C" int b200dqn_net_device_ptr(b200dqn_net* n, int which, void** dev_ptr,
 extern "C" int b200dqn_net_set_keep_grads(b200dqn_net* n, int keep) {
   B2_REQUIRE(n, B200DQN_EINVAL, "null net");
   n->keep_grads = keep != 0;
-  if (n->graph_exec) { cudaGraphExecDestroy(n->graph_exec); n->graph_exec = nullptr; }   // parameters are baked in
+  destroy_step_graphs(n);   // parameters are baked in
   if (n->graph_train_exec) { cudaGraphExecDestroy(n->graph_train_exec); n->graph_train_exec = nullptr; }
   return B200DQN_OK;
 }
@@ -1524,7 +1578,9 @@ extern "C" int b200dqn_net_launches_per_step(const b200dqn_net* n, int* launches
   B2_REQUIRE(n && launches, B200DQN_EINVAL, "null argument");
   // Counted at the launch sites while the step was captured into its CUDA graph; before the first
   // fused step: the static schedule (sample, 4 forward, head, 7 backward GEMMs, per-layer optimizers).
-  if (n->graph_launches > 0) {
+  if (n->graph_def_launches > 0) {          // the multi-step graph (one gated fc1 update at its head)
+    *launches = n->graph_def_launches;
+  } else if (n->graph_launches > 0) {
     *launches = n->graph_launches;
   } else {
     const bool tc = n->cfg.math_mode == B200DQN_MATH_TCGEN05;

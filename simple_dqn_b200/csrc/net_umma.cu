@@ -584,10 +584,14 @@ k_opt_conv(const float* __restrict__ part, int splits, float* __restrict__ w, fl
 // co-reside with the tcgen05 kernels of the critical chain instead of locking them out of the SMs.
 __global__ void __launch_bounds__(256)
 k_opt_fc1(const float* __restrict__ dw, float* __restrict__ w, float* __restrict__ sst, uint8_t* __restrict__ img_dgr,
-          const OptArgs opt, const KTrace kt) {
+          const OptArgs opt, const uint32_t* __restrict__ gate, const KTrace kt) {
   kt_begin(kt);
   pdl_wait();
   pdl_launch_dependents();
+  if (gate && *gate == 0) {   // nothing pending (first step after a flush): uniform across the grid
+    kt_end(kt);
+    return;
+  }
   constexpr int kNB = kHidden / 8;
   const float l_step = opt_step_scalar(opt);
   for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < kFlat * kNB; id += gridDim.x * blockDim.x) {
@@ -606,7 +610,7 @@ k_opt_fc1(const float* __restrict__ dw, float* __restrict__ w, float* __restrict
   kt_end(kt);
 }
 
-int umma_opt_fc1(b200dqn_net* n, int rows, cudaStream_t st, bool from_g) {
+int umma_opt_fc1(b200dqn_net* n, int rows, cudaStream_t st, bool from_g, const uint32_t* gate) {
   UmmaState* u = ust(n);
   const LayerTable& lt = n->lt;
   const float* dw = from_g ? n->d_g + lt.off[3] : n->d_part + lt.part_off[3];
@@ -617,7 +621,7 @@ int umma_opt_fc1(b200dqn_net* n, int rows, cudaStream_t st, bool from_g) {
   static const int per_sm = getenv("B200DQN_OPT_FC1_CTAS") ? atoi(getenv("B200DQN_OPT_FC1_CTAS")) : 2;
   const int ctas = per_sm > 0 ? per_sm * n->sm_count : n->sm_count / (-per_sm > 0 ? -per_sm : 1);
   B2_CHECK_CUDA(launch_pdl(k_opt_fc1, dim3(ctas), dim3(256), 0, st, dw, n->d_w + lt.off[3],
-                           n->d_s + lt.off[3], u->img_dgr[0], make_opt_args(n, rows), ktrace_slot("opt_fc1")));
+                           n->d_s + lt.off[3], u->img_dgr[0], make_opt_args(n, rows), gate, ktrace_slot("opt_fc1")));
   B2_PROF("opt_fc1", st);
   return B200DQN_OK;
 }
@@ -911,16 +915,32 @@ int umma_forward(b200dqn_net* n, const uint8_t* const src[2], const int32_t* con
     V2Fc1Fwd p;
     for (int z = 0; z < 2; ++z) { p.in16[z] = planes(2, z); p.wimg[z] = u->img_fwd[z][3]; }
     p.part = n->d_fc1part; p.rows = rows; p.splits = fc1_splits_for(rows);
-    if ((rc = umma2::launch_umma2("fc1_fwd", p, kHidden, rows, nets * p.splits, st))) return rc;
+    if (n->defer_fc1) {
+      // the previous step's fc1 update (side branch since the start of this step) must have refreshed the image; the
+      // kernel then has two parents, so it is launched as an ordinary node (its pre-wait weight prefetch would
+      // otherwise run ahead of the join)
+      static const bool keep_pdl = getenv("B200DQN_DEFER_PDL") != nullptr;
+      B2_CHECK_CUDA(cudaStreamWaitEvent(st, n->ev[16], 0));
+      if (keep_pdl) {
+        rc = umma2::launch_umma2("fc1_fwd", p, kHidden, rows, nets * p.splits, st);
+      } else {
+        NoPdlScope plain;
+        rc = umma2::launch_umma2("fc1_fwd", p, kHidden, rows, nets * p.splits, st);
+      }
+      if (rc) return rc;
+    } else if ((rc = umma2::launch_umma2("fc1_fwd", p, kHidden, rows, nets * p.splits, st))) return rc;
   }
   return B200DQN_OK;
 }
 
 // B200DQN_STAGES2=label,label,...: run that kernel with a 2-stage operand ring (about half the shared memory, so two
 // CTAs of the step's kernels fit on an SM) instead of the deepest ring.
+// Default: conv2_dgrad — 100 CTAs of 4 k-blocks each; at 81 KB instead of 161 KB they occupy 50 SMs instead of 100
+// while conv3_wgrad / conv2_wgrad / conv1_wgrad look for SMs (measured period 73.4 -> 71.9 us, profiles/r2o_periods.txt;
+// the conv wgrads themselves are slower with the shallow ring).
 static bool shallow_ring(const char* label) {
-  static const char* list = getenv("B200DQN_STAGES2");
-  if (!list) return false;
+  static const char* env = getenv("B200DQN_STAGES2");
+  static const char* list = env ? env : "conv2_dgrad";
   const size_t n = strlen(label);
   for (const char* p = list; (p = strstr(p, label)) != nullptr; p += n)
     if ((p == list || p[-1] == ',') && (p[n] == 0 || p[n] == ',')) return true;

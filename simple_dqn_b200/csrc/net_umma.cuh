@@ -23,7 +23,8 @@ int umma_forward(b200dqn_net* n, const uint8_t* const src[2], const int32_t* con
                  const int64_t nframes[2], int nets, int rows, cudaStream_t st);
 int umma_fc1_splits(int rows);
 // RMSProp of the fc1 layer + refresh of both of its tile images in one smem-free kernel
-int umma_opt_fc1(b200dqn_net* n, int rows, cudaStream_t st, bool from_g = false);
+// gate != nullptr: the kernel does nothing unless *gate != 0 (software-pipelined update, net.cuh)
+int umma_opt_fc1(b200dqn_net* n, int rows, cudaStream_t st, bool from_g = false, const uint32_t* gate = nullptr);
 int umma_fc1_wgrad_fused(b200dqn_net* n, int rows, cudaStream_t st, bool keep_grads);
 // fused split-K reduction + RMSProp + tile-image refresh of conv layer l (0..2), single-GPU tcgen05 path
 // from_g: read the (all-reduced) gradient from d_g instead of the split-K partials
