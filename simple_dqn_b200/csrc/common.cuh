@@ -109,6 +109,17 @@ struct NoPdlScope {
   ~NoPdlScope() { g_pdl_suppressed = prev; }
 };
 
+// B200DQN_CARVEOUT=1 (experiment, off by default): every kernel of the library asks for the LARGEST shared-memory
+// carveout, including the ones that use no shared memory at all.  The L1/shared split is an SM-wide setting that can
+// only change while the SM is idle: a streaming kernel (fc1 optimizer: 296 CTAs, 1 KB of shared memory) that configures
+// an SM for "mostly L1" locks the tcgen05 kernels (81-193 KB per CTA) out of that SM until its CTAs have left.
+// Measured (profiles/r2q_periods.txt): with the optimizer at the head of the step (B200DQN_DEFER_FC1=1) one carveout
+// for all kernels lets conv1 start at once (83.2 -> 75.9 us per step); in the default schedule, where the optimizer
+// starts under kernels that have already claimed their SMs, it costs 1.2 us (71.7 -> 72.9), hence off.
+void prefer_max_smem_carveout(const void* kernel);   // capi.cu; once per kernel
+template <class K>
+static inline void prefer_max_smem(K* kernel) { prefer_max_smem_carveout(reinterpret_cast<const void*>(kernel)); }
+
 // cluster_x > 1: thread-block clusters of that many CTAs along grid x (split-K partners reducing through DSMEM)
 template <class... KArgs, class... Args>
 static inline cudaError_t launch_pdl_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
@@ -135,6 +146,7 @@ static inline cudaError_t launch_pdl_cluster(void (*kernel)(KArgs...), dim3 grid
   cfg.attrs = attr;
   cfg.numAttrs = na;
   ++g_launch_count;
+  prefer_max_smem(kernel);
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 template <class... KArgs, class... Args>

@@ -1194,6 +1194,7 @@ extern "C" int b200dqn_net_predict_device(b200dqn_net* n, const uint8_t* dev_sta
     B2_CHECK_CUDA(cudaMemcpyAsync(dev_q, n->d_q[0], size_t(live_rows) * n->A * sizeof(float),
                                   cudaMemcpyDeviceToDevice, st));
   if (live_rows < n->nb) {
+    prefer_max_smem(k_zero_rows);
     k_zero_rows<<<cdiv((n->nb - live_rows) * n->A, 128), 128, 0, st>>>(dev_q, live_rows, n->nb, n->A);
     B2_LAUNCH_CHECK();
   }
@@ -1239,6 +1240,7 @@ extern "C" int b200dqn_net_predict_device_host(b200dqn_net* n, const uint8_t* de
     HeadTrainArgs no_td{};
     int rc = forward(n, fs, 1, live_rows, st, no_td);
     if (!rc) {
+      prefer_max_smem(k_publish_q_counter);
       k_publish_q_counter<<<1, 64, 0, st>>>(n->d_q[0], count, n->h_res, n->d_optscal_u32());
       if (cudaGetLastError() != cudaSuccess) rc = B200DQN_ECUDA;
     }
@@ -1409,9 +1411,12 @@ extern "C" int b200dqn_net_train_fused(b200dqn_net* n, b200dqn_replay* r, int ns
       destroy_step_graphs(n);
       n->graph_replay = r; n->graph_stream = st; n->graph_world = n->world; n->graph_trace_gen = g_ktrace_gen;
     }
-    // several steps in one call: the fc1 update of step t rides under the forward of step t+1 (net.cuh)
-    static const bool defer_off = getenv("B200DQN_DEFER_FC1") && atoi(getenv("B200DQN_DEFER_FC1")) == 0;
-    const bool deferred = nsteps >= 2 && !defer_off && n->use_branches && n->cfg.math_mode == B200DQN_MATH_TCGEN05 &&
+    // B200DQN_DEFER_FC1=1 (experiment, off by default): several steps in one call -> the fc1 update of step t rides under
+    // the forward of step t+1 (net.cuh).  Parity-clean (profiles/r2p_pytest.log) but slower: the 45 MB the update moves
+    // through L2 stretch whatever runs beside it, and the forward convolutions lose more (conv1 9.2 -> 13.9 us) than
+    // the dgrad chain gains; 75.9 (83.2 with the driver's carveouts) vs 71.7 us per step.
+    static const bool defer_on = getenv("B200DQN_DEFER_FC1") && atoi(getenv("B200DQN_DEFER_FC1")) != 0;
+    const bool deferred = nsteps >= 2 && defer_on && n->use_branches && n->cfg.math_mode == B200DQN_MATH_TCGEN05 &&
                           (n->world == 1 || comm_gather_active(n, st));
     cudaGraphExec_t* exec = deferred ? &n->graph_def_exec : &n->graph_exec;
     if (!*exec) {

@@ -90,7 +90,8 @@ struct b200dqn_net {
   int graph_world = 0;
   int graph_trace_gen = 0;
   int graph_launches = 0;   // kernels launched by one captured step
-  // Software-pipelined fc1 update (multi-step train_fused): the graph of step t applies step t-1's fc1 update on a
+  // Software-pipelined fc1 update (multi-step train_fused, opt-in B200DQN_DEFER_FC1=1 — measured slower, see
+  // b200dqn_net_train_fused): the graph of step t applies step t-1's fc1 update on a
   // side branch under its own forward convolutions (joined before fc1_fwd) instead of under the dgrad chain, where its
   // 296 CTAs compete with the tcgen05 kernels for registers and SM slots; the last step's update is flushed by
   // train_fused before it returns, so nothing outside that call ever sees a pending update.
