@@ -935,12 +935,13 @@ int umma_forward(b200dqn_net* n, const uint8_t* const src[2], const int32_t* con
 
 // B200DQN_STAGES2=label,label,...: run that kernel with a 2-stage operand ring (about half the shared memory, so two
 // CTAs of the step's kernels fit on an SM) instead of the deepest ring.
-// Default: conv2_dgrad — 100 CTAs of 4 k-blocks each; at 81 KB instead of 161 KB they occupy 50 SMs instead of 100
-// while conv3_wgrad / conv2_wgrad / conv1_wgrad look for SMs (measured period 73.4 -> 71.9 us, profiles/r2o_periods.txt;
-// the conv wgrads themselves are slower with the shallow ring).
-static bool shallow_ring(const char* label) {
+// Default on ONE GPU: conv2_dgrad — 100 CTAs of 4 k-blocks each; at 81 KB instead of 161 KB they occupy 50 SMs instead
+// of 100 while conv3_wgrad / conv2_wgrad / conv1_wgrad look for SMs (measured period 73.4 -> 71.9 us,
+// profiles/r2o_periods.txt; the conv wgrads themselves are slower with the shallow ring).  With data-parallel learners
+// the same choice costs 12 us per step (2 x B200: 96.0 vs 83.6 us, profiles/r2s_*), so there the default is none.
+static bool shallow_ring(const b200dqn_net* net, const char* label) {
   static const char* env = getenv("B200DQN_STAGES2");
-  static const char* list = env ? env : "conv2_dgrad";
+  const char* list = env ? env : net->world == 1 ? "conv2_dgrad" : "";
   const size_t n = strlen(label);
   for (const char* p = list; (p = strstr(p, label)) != nullptr; p += n)
     if ((p == list || p[-1] == ',') && (p[n] == 0 || p[n] == ',')) return true;
@@ -970,7 +971,7 @@ int umma_backward_op(b200dqn_net* n, int op, const uint8_t* src, const int32_t* 
       UmmaState* u = ust(n);
       using P = WConvWgrad<kP2, kC2, 3, 1, kC3>;
       using P2 = WConvWgrad<kP2, kC2, 3, 1, kC3, 2>;
-      if (shallow_ring("conv3_wgrad")) {
+      if (shallow_ring(n, "conv3_wgrad")) {
         P2 p{PlanePair{u->h16[1][0], u->h_elems[1]}, PlanePair{u->dz16[1], u->dz_elems[1]},
              n->d_part + lt.part_off[2], rows, umma_wgrad_kb(2, rows)};
         return umma_mn::launch_umma_mn("conv3_wgrad", p, P::KW, kC3, lt.splits[2], st);
@@ -992,7 +993,7 @@ int umma_backward_op(b200dqn_net* n, int op, const uint8_t* src, const int32_t* 
       UmmaState* u = ust(n);
       using P = WConvWgrad<kP1, kC1, 4, 2, kC2>;
       using P2 = WConvWgrad<kP1, kC1, 4, 2, kC2, 2>;
-      if (shallow_ring("conv2_wgrad")) {
+      if (shallow_ring(n, "conv2_wgrad")) {
         P2 p{PlanePair{u->h16[0][0], u->h_elems[0]}, PlanePair{u->dz16[2], u->dz_elems[2]},
              n->d_part + lt.part_off[1], rows, umma_wgrad_kb(1, rows)};
         return umma_mn::launch_umma_mn("conv2_wgrad", p, P::KW, kC2, lt.splits[1], st);
@@ -1005,7 +1006,7 @@ int umma_backward_op(b200dqn_net* n, int op, const uint8_t* src, const int32_t* 
       UmmaState* u = ust(n);
       using P = V2ConvDgrad<kP1, kC1, 4, 2, kC2>;
       using P2 = V2ConvDgrad<kP1, kC1, 4, 2, kC2, 2>;
-      if (shallow_ring("conv2_dgrad")) {   // 81 KB per CTA: the 100 CTAs take 50 SMs instead of 100
+      if (shallow_ring(n, "conv2_dgrad")) {   // 81 KB per CTA: the 100 CTAs take 50 SMs instead of 100
         P2 p{PlanePair{u->dz16[2], u->dz_elems[2]}, u->img_dgr[2], n->d_h1[0], n->keep_grads ? n->d_dz1 : nullptr,
              PlanePair{u->dz16[3], u->dz_elems[3]}, rows};
         return umma2::launch_umma2("conv2_dgrad", p, rows * P::HC * P::HC, kC1, 4, st);

@@ -93,6 +93,12 @@ dist.all_gather(allc, chk)
 say("weight checksums", [float(c) for c in allc])
 assert all(float(c) == float(allc[0]) for c in allc), "ranks diverged"
 t = time.time(); net.train_fused(mem, 500); torch.cuda.synchronize(); say("500 steps: %.1f us/step" % ((time.time() - t) / 500 * 1e6))
+# host cost of enqueueing one step (300 graph launches fit the launch queue: the host is not throttled by the device)
+for _ in range(3):
+    dist.barrier(); torch.cuda.synchronize()
+    t = time.time(); net.train_fused(mem, 300); t_enq = time.time() - t; torch.cuda.synchronize(); t_all = time.time() - t
+    say("300 steps: host enqueue %.1f us/step, until done %.1f us/step" % (t_enq / 300 * 1e6, t_all / 300 * 1e6))
+
 say("comm status after run:", net.comm_status())
 if os.environ.get("TIMELINE"):
     from simple_dqn_b200 import _lib as L

@@ -27,4 +27,9 @@ for rep in range(int(os.environ.get("REPS", "5"))):
     e1.record(ts)
     st.synchronize()
     res.append(e0.elapsed_time(e1) / 2000 * 1e3)
+import time
+for _ in range(2):
+    st.synchronize()
+    t = time.time(); net.train_fused(mem, 300); t_enq = time.time() - t; st.synchronize(); t_all = time.time() - t
+    print("300 steps: host enqueue %.1f us/step, until done %.1f us/step" % (t_enq / 300 * 1e6, t_all / 300 * 1e6))
 print("period_us min %.2f median %.2f  all %s" % (min(res), float(np.median(res)), " ".join("%.2f" % r for r in res)))
